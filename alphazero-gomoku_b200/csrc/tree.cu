@@ -1,0 +1,620 @@
+// PUCT search kernels: one warp per game, structure-of-arrays node slabs in HBM.
+//
+// Restates the reference search (mcts/new_mcts_alpha.py:77-185) as the per-game
+// state machine FILL -> EVAL -> COMMIT described in DESIGN.md:
+//   azg_fill_kernel    runs simulations until the game's leaf queue holds
+//                      queue_len nodes (the parked simulation is resumed later,
+//                      new_mcts_alpha.py:121-135) or the simulation budget is spent;
+//   azg_commit_kernel  stores masked priors, zeroes N and W of every queued node
+//                      (new_mcts_alpha.py:163-185) and re-arms the game;
+//   azg_finish_kernel  root visit counts -> pi (new_mcts_alpha.py:88-97);
+//   azg_advance_kernel plays the chosen move on the root and reclaims nodes that
+//                      can never be looked up again.
+// Arithmetic of the selection rule is float32 in the reference's exact operation
+// order (new_mcts_alpha.py:136-140); float64 at a Dirichlet-noised root.
+#include "common.cuh"
+#include "rules.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// transposition table: per-game open addressing in windows of 32 slots (one coalesced probe)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool key_equal(const azg_dev& e, int g, int node, const WPos& p) {
+  const int l = lane_id();
+  const size_t off = azg_node_off(e, g, node);
+  const uint32_t x0 = __shfl_sync(AZG_FULL, p.w0, (l & 7) << 2);
+  const uint32_t x1 = __shfl_sync(AZG_FULL, p.w1, (l & 7) << 2);
+  bool ok = true;
+  if (l < 16) ok = __ldcg(&e.key[off * 16 + l]) == (l < 8 ? x0 : x1);
+  else if (l == 16) ok = ((__ldcg(&e.meta[off]) >> 1) & 3u) == (uint32_t)p.player;
+  return __all_sync(AZG_FULL, ok);
+}
+
+__device__ __forceinline__ int table_find(const azg_dev& e, int g, const WPos& p, unsigned long long h, int* ins) {
+  const unsigned long long* tab = e.slots + (size_t)g * (size_t)e.hcap;
+  const uint32_t tag = (uint32_t)(h >> 32);
+  const int nwin = e.hcap >> 5;
+  int win = (int)((uint32_t)h & (uint32_t)(nwin - 1));
+  const int l = lane_id();
+  for (int t = 0; t < nwin; ++t) {
+    const unsigned long long s = __ldcg(&tab[(win << 5) + l]);
+    uint32_t mm = __ballot_sync(AZG_FULL, s != 0ULL && (uint32_t)(s >> 32) == tag);
+    while (mm) {
+      const int src = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const int node = (int)__shfl_sync(AZG_FULL, (uint32_t)s, src) - 1;
+      if (key_equal(e, g, node, p)) return node;
+    }
+    const uint32_t em = __ballot_sync(AZG_FULL, s == 0ULL);
+    if (em) { *ins = (win << 5) + __ffs(em) - 1; return -1; }
+    win = (win + 1) & (nwin - 1);
+  }
+  *ins = -1;
+  return -1;
+}
+
+__device__ __forceinline__ void table_put(const azg_dev& e, int g, int slot, unsigned long long h, int node) {
+  if (lane_id() == 0)
+    e.slots[(size_t)g * (size_t)e.hcap + slot] = ((h >> 32) << 32) | (unsigned long long)(uint32_t)(node + 1);
+}
+
+__device__ __forceinline__ void node_write_key(const azg_dev& e, int g, int node, const WPos& p) {
+  const int l = lane_id();
+  const size_t off = azg_node_off(e, g, node);
+  const uint32_t x0 = __shfl_sync(AZG_FULL, p.w0, (l & 7) << 2);
+  const uint32_t x1 = __shfl_sync(AZG_FULL, p.w1, (l & 7) << 2);
+  if (l < 16) e.key[off * 16 + l] = (l < 8 ? x0 : x1);
+  if (l == 16) e.meta[off] = AZG_META_ALIVE | ((uint32_t)p.player << 1);
+}
+
+// children arrays of a node: lane L < 28 owns elements 8L..8L+7, lane 28 owns element 224.
+__device__ __forceinline__ void node_fill(const azg_dev& e, int g, int node, uint32_t legal, float pv) {
+  const int l = lane_id();
+  const size_t base = azg_node_off(e, g, node) * AZG_ROW;
+  if (l < 28) {
+    float4 a, b;
+    a.x = (legal & 1u) ? pv : 0.f;   a.y = (legal & 2u) ? pv : 0.f;   a.z = (legal & 4u) ? pv : 0.f;   a.w = (legal & 8u) ? pv : 0.f;
+    b.x = (legal & 16u) ? pv : 0.f;  b.y = (legal & 32u) ? pv : 0.f;  b.z = (legal & 64u) ? pv : 0.f;  b.w = (legal & 128u) ? pv : 0.f;
+    float4* P = reinterpret_cast<float4*>(e.P + base + 8 * l);
+    P[0] = a; P[1] = b;
+    int4 z = make_int4(0, 0, 0, 0);
+    int4* Nn = reinterpret_cast<int4*>(e.Nv + base + 8 * l);
+    int4* Ww = reinterpret_cast<int4*>(e.W + base + 8 * l);
+    Nn[0] = z; Nn[1] = z; Ww[0] = z; Ww[1] = z;
+  } else if (l == 28) {
+    e.P[base + 224] = (legal & 1u) ? pv : 0.f;
+    e.Nv[base + 224] = 0;
+    e.W[base + 224] = 0;
+  }
+}
+
+// First-index argmax of the reference's PUCT score over legal children.
+__device__ __forceinline__ int puct_select(const azg_dev& e, int g, int node, uint32_t legal) {
+  const int l = lane_id();
+  const size_t off = azg_node_off(e, g, node);
+  const size_t base = off * AZG_ROW;
+  const uint32_t meta = __ldcg(&e.meta[off]);
+  const int slot64 = (int)((meta >> 4) & 15u) - 1;
+  float p[8]; int n[8], w[8];
+  if (l < 28) {
+    const float4* P = reinterpret_cast<const float4*>(e.P + base + 8 * l);
+    const int4* Nn = reinterpret_cast<const int4*>(e.Nv + base + 8 * l);
+    const int4* Ww = reinterpret_cast<const int4*>(e.W + base + 8 * l);
+    const float4 pa = __ldcg(P), pb = __ldcg(P + 1);
+    const int4 na = __ldcg(Nn), nb = __ldcg(Nn + 1);
+    const int4 wa = __ldcg(Ww), wb = __ldcg(Ww + 1);
+    p[0] = pa.x; p[1] = pa.y; p[2] = pa.z; p[3] = pa.w; p[4] = pb.x; p[5] = pb.y; p[6] = pb.z; p[7] = pb.w;
+    n[0] = na.x; n[1] = na.y; n[2] = na.z; n[3] = na.w; n[4] = nb.x; n[5] = nb.y; n[6] = nb.z; n[7] = nb.w;
+    w[0] = wa.x; w[1] = wa.y; w[2] = wa.z; w[3] = wa.w; w[4] = wb.x; w[5] = wb.y; w[6] = wb.z; w[7] = wb.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { p[j] = 0.f; n[j] = 0; w[j] = 0; }
+    if (l == 28) { p[0] = __ldcg(e.P + base + 224); n[0] = __ldcg(e.Nv + base + 224); w[0] = __ldcg(e.W + base + 224); }
+  }
+  int tot = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) tot += n[j];
+  tot = __reduce_add_sync(AZG_FULL, tot);
+
+  int best_i = 0x7fffffff;
+  if (slot64 < 0) {
+    // float32: ucb = W/(1+N) + ((cpuct*P)*sqrt_sum)/(1+N)     (new_mcts_alpha.py:136-137)
+    const float sq = __fsqrt_rn((float)tot);
+    float best = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (legal & (1u << j)) {
+        const float n1 = __fadd_rn(1.0f, (float)n[j]);
+        const float q = __fdiv_rn((float)w[j], n1);
+        const float u = __fdiv_rn(__fmul_rn(__fmul_rn(e.cpuct, p[j]), sq), n1);
+        const float s = __fadd_rn(q, u);
+        if (s > best) { best = s; best_i = 8 * l + j; }
+      }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const float ob = __shfl_xor_sync(AZG_FULL, best, s);
+      const int oi = __shfl_xor_sync(AZG_FULL, best_i, s);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+  } else {
+    // float64 at a noised root: P is float64 there, so numpy promotes the exploration term
+    // (SURVEY 0.6); the W/(1+N) term is still rounded to float32 first.
+    const double* P64 = e.P64 + ((size_t)g * AZG_P64_SLOTS + slot64) * AZG_ROW;
+    const double sq = sqrt((double)tot);
+    double best = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = 8 * l + j;
+      if ((legal & (1u << j)) && idx < AZG_A) {
+        const float n1 = __fadd_rn(1.0f, (float)n[j]);
+        const float q = __fdiv_rn((float)w[j], n1);
+        const double u = __ddiv_rn(__dmul_rn(__dmul_rn(e.cpuct64, __ldcg(P64 + idx)), sq), (double)n1);
+        const double s = __dadd_rn((double)q, u);
+        if (s > best) { best = s; best_i = idx; }
+      }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const double ob = __shfl_xor_sync(AZG_FULL, best, s);
+      const int oi = __shfl_xor_sync(AZG_FULL, best_i, s);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+  }
+  return best_i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FILL
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= e.G) return;
+  const int l = lane_id();
+  azg_ctl* ctl = e.ctl + g;
+  int state = __ldcg(&ctl->state);
+  if (state != AZG_ST_RUN) return;
+
+  int sims_left = __ldcg(&ctl->sims_left);
+  int root_node = __ldcg(&ctl->root_node);
+  int n_pending = __ldcg(&ctl->n_pending);
+  int n_nodes = __ldcg(&ctl->n_nodes);
+  int n_free = __ldcg(&ctl->n_free);
+  int n_live = __ldcg(&ctl->n_live);
+  int err = 0;
+  bool resume = __ldcg(&ctl->susp) != 0;
+  unsigned long long visits = 0, sims = 0;
+  uint32_t* path = e.path + (size_t)g * AZG_MAX_DEPTH;
+  int32_t* freelist = e.freelist + (size_t)g * e.cap;
+  const WPos root = wpos_load(&ctl->root);
+
+  while (true) {
+    WPos pos;
+    int depth, node = -1, v = 0;
+    bool select_here = false;
+    if (resume) {
+      pos = wpos_load(&ctl->scratch);
+      depth = __ldcg(&ctl->depth);
+      node = __ldcg(&ctl->resume_node);
+      select_here = true;                       // fall through to selection at the evaluated leaf
+      resume = false;
+    } else {
+      if (sims_left <= 0) break;
+      pos = root;
+      depth = 0;
+    }
+    bool parked = false;
+    for (;;) {
+      if (!select_here) {
+        ++visits;
+        const int won = wpos_winner(pos, e.rule);            // new_mcts_alpha.py:106-112
+        if (won != 0) { v = -1; break; }
+        if (!wpos_any_empty(pos)) { v = 0; break; }
+        const unsigned long long h = wpos_hash(pos);
+        int ins = -1;
+        node = table_find(e, g, pos, h, &ins);
+        if (node < 0) {                                        // new_mcts_alpha.py:114-132
+          if (ins < 0) { err |= AZG_ERR_HASH; break; }
+          if (n_free > 0) node = __ldcg(&freelist[--n_free]);
+          else if (n_nodes < e.cap) node = n_nodes++;
+          else { err |= AZG_ERR_NODES; break; }
+          ++n_live;
+          node_write_key(e, g, node, pos);
+          table_put(e, g, ins, h, node);
+          if (depth == 0) root_node = node;
+          if (l == 0) ctl->pending[n_pending] = node;
+          ++n_pending;
+          if (n_pending >= e.queue_len) {                     // park: the queue is evaluated first
+            wpos_store(&ctl->scratch, pos);
+            if (l == 0) { ctl->depth = depth; ctl->resume_node = node; ctl->susp = 1; }
+            parked = true;
+            break;
+          }
+          const int cnt = wpos_count_empty(pos);
+          node_fill(e, g, node, wpos_legal_byte(pos), __fdiv_rn(1.0f, (float)cnt));
+          v = 0;
+          break;
+        }
+      }
+      select_here = false;
+      const int a = puct_select(e, g, node, wpos_legal_byte(pos));
+      if (depth >= AZG_MAX_DEPTH) { err |= AZG_ERR_DEPTH; break; }
+      if (l == 0) __stcg(&path[depth], ((uint32_t)node << 8) | (uint32_t)a);
+      ++depth;
+      wpos_play(pos, e.rule, a);
+    }
+    if (parked || err) break;
+    // back-up: the leaf value alternates sign up the path (new_mcts_alpha.py:146-151)
+    __threadfence_block();
+    __syncwarp();
+    for (int d = l; d < depth; d += 32) {
+      const uint32_t pe = __ldcg(&path[d]);
+      const size_t idx = azg_node_off(e, g, (int)(pe >> 8)) * AZG_ROW + (pe & 255u);
+      atomicAdd(&e.Nv[idx], 1);
+      if (v != 0) atomicAdd(&e.W[idx], ((depth - d) & 1) ? -v : v);
+    }
+    __threadfence_block();
+    __syncwarp();
+    --sims_left;
+    ++sims;
+  }
+
+  if (err) state = AZG_ST_ERROR;
+  else if (n_pending >= e.queue_len) state = AZG_ST_NEED_EVAL;
+  else if (sims_left <= 0) state = (n_pending > 0) ? AZG_ST_NEED_FINAL : AZG_ST_DONE;
+  if (l == 0) {
+    ctl->state = state;
+    ctl->err = __ldcg(&ctl->err) | err;
+    ctl->sims_left = sims_left;
+    ctl->root_node = root_node;
+    ctl->n_pending = n_pending;
+    ctl->n_nodes = n_nodes;
+    ctl->n_free = n_free;
+    ctl->n_live = n_live;
+    ctl->visits += visits;
+    ctl->sims += sims;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// leaf batch assembly: exclusive scan of the per-game queue lengths (single block)
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(1024) azg_scan_kernel(azg_dev e) {
+  __shared__ int part[1024];
+  __shared__ int carry, s_active, s_errors;
+  const int t = threadIdx.x;
+  if (t == 0) { carry = 0; s_active = 0; s_errors = 0; }
+  __syncthreads();
+  for (int base = 0; base < e.G; base += 1024) {
+    const int g = base + t;
+    int n = 0, st = AZG_ST_DONE;
+    if (g < e.G) {
+      st = e.ctl[g].state;
+      if (st == AZG_ST_NEED_EVAL || st == AZG_ST_NEED_FINAL) n = e.ctl[g].n_pending;
+      if (st == AZG_ST_RUN || st == AZG_ST_NEED_EVAL || st == AZG_ST_NEED_FINAL) atomicAdd(&s_active, 1);
+      if (st == AZG_ST_ERROR) atomicAdd(&s_errors, 1);
+    }
+    part[t] = n;
+    __syncthreads();
+    for (int s = 1; s < 1024; s <<= 1) {
+      const int x = (t >= s) ? part[t - s] : 0;
+      __syncthreads();
+      part[t] += x;
+      __syncthreads();
+    }
+    const int off = carry + part[t] - n;
+    if (g < e.G) {
+      e.ctl[g].leaf_off = off;
+      for (int i = 0; i < n; ++i) {
+        e.leaf_game[off + i] = g;
+        e.leaf_node[off + i] = e.ctl[g].pending[i];
+      }
+    }
+    __syncthreads();
+    if (t == 1023) carry += part[t];
+    __syncthreads();
+  }
+  if (t == 0) { e.counters[0] = carry; e.counters[1] = s_active; e.counters[2] = s_errors; }
+}
+
+// Encoded planes of every queued leaf, float32 NCHW exactly as get_encoded_state()
+// (games/gomoku.py:130-150): side-to-move stones, opponent stones, ones.
+extern "C" __global__ void azg_leaf_planes_kernel(azg_dev e, float* out) {
+  const int n = e.counters[0];
+  for (int leaf = blockIdx.x; leaf < n; leaf += gridDim.x) {
+    const int g = e.leaf_game[leaf], node = e.leaf_node[leaf];
+    const size_t off = azg_node_off(e, g, node);
+    const int player = (e.meta[off] >> 1) & 3;
+    const uint32_t* k = e.key + off * 16;
+    float* o = out + (size_t)leaf * 3 * AZG_A;
+    for (int a = threadIdx.x; a < AZG_A; a += blockDim.x) {
+      const uint32_t b1 = (k[a >> 5] >> (a & 31)) & 1u, b2 = (k[8 + (a >> 5)] >> (a & 31)) & 1u;
+      o[a] = (float)(player == 1 ? b1 : b2);
+      o[AZG_A + a] = (float)(player == 1 ? b2 : b1);
+      o[2 * AZG_A + a] = 1.0f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// COMMIT
+// ------------------------------------------------------------------------------------------------
+// numpy's pairwise float sum for n = 225 (n > 128: halves of 112 and 113; each half keeps
+// eight running partials; the odd last element is added at the end).  Bit-exact with
+// np.sum on a contiguous vector, which is what new_mcts_alpha.py:167 and :174 call.
+template <typename T>
+__device__ __forceinline__ T numpy_sum225(const T* sm) {
+  const int l = lane_id();
+  T r = (T)0;
+  if (l < 16) {
+    const T* a = sm + (l >> 3) * 112 + (l & 7);
+    r = a[0];
+#pragma unroll
+    for (int i = 1; i < 14; ++i) r = r + a[8 * i];
+  }
+  // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) inside each group of 8 lanes
+  r = r + __shfl_down_sync(AZG_FULL, r, 1);
+  r = r + __shfl_down_sync(AZG_FULL, r, 2);
+  r = r + __shfl_down_sync(AZG_FULL, r, 4);
+  T lo = __shfl_sync(AZG_FULL, r, 0);
+  T hi = __shfl_sync(AZG_FULL, r, 8);
+  hi = hi + sm[224];
+  return lo + hi;
+}
+
+extern "C" __global__ void __launch_bounds__(128)
+azg_commit_kernel(azg_dev e, const float* __restrict__ probs, const double* __restrict__ noise) {
+  __shared__ float sm_f[4][AZG_ROW];
+  __shared__ double sm_d[4][AZG_ROW];
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= e.G) return;
+  const int l = lane_id();
+  const int wib = threadIdx.x >> 5;
+  azg_ctl* ctl = e.ctl + g;
+  const int state = ctl->state;
+  if (state != AZG_ST_NEED_EVAL && state != AZG_ST_NEED_FINAL) return;
+  const int n_pending = ctl->n_pending;
+  const int leaf_off = ctl->leaf_off;
+  const int root_node = ctl->root_node;
+  const bool noisy_run = e.noise_on && ctl->ply < e.noise_plies && noise != nullptr;
+  int p64_used = ctl->p64_used;
+  int err = 0;
+  float* smf = sm_f[wib];
+  double* smd = sm_d[wib];
+
+  for (int i = 0; i < n_pending; ++i) {
+    const int node = ctl->pending[i];
+    const size_t off = azg_node_off(e, g, node);
+    const size_t base = off * AZG_ROW;
+    const uint32_t occ = e.key[off * 16 + (l >> 2)] | e.key[off * 16 + 8 + (l >> 2)];
+    const uint32_t empty = ~occ & board_word_mask(l >> 2);
+    const uint32_t legal = (empty >> ((l & 3) * 8)) & 0xffu;
+    const float* row = probs + (size_t)(leaf_off + i) * AZG_A;
+    float p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = 8 * l + j;
+      p[j] = 0.f;
+      if (idx < AZG_A) {
+        p[j] = __fmul_rn(row[idx], (legal & (1u << j)) ? 1.0f : 0.0f);     // p * valid (new_mcts_alpha.py:166)
+        smf[idx] = p[j];
+      }
+    }
+    __syncwarp();
+    const float total = numpy_sum225<float>(smf);
+    __syncwarp();
+    if (total < 1e-8f) {                                                    // uniform-legal fallback (:167-168)
+      int c = (l & 3) == 0 ? __popc(empty) : 0;
+      c = __reduce_add_sync(AZG_FULL, c);
+      const float u = __fdiv_rn(1.0f, (float)c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p[j] = (legal & (1u << j)) ? u : 0.f;
+    }
+    uint32_t meta = AZG_META_ALIVE | (e.meta[off] & 6u);
+    if (noisy_run && node == root_node) {                                   // root Dirichlet mix (:171-174)
+      int slot = -1;
+      for (int s = 0; s < AZG_P64_SLOTS; ++s) if (!(p64_used & (1 << s))) { slot = s; break; }
+      if (slot < 0) { err |= AZG_ERR_P64; }
+      else {
+        p64_used |= 1 << slot;
+        meta |= (uint32_t)(slot + 1) << 4;
+        const double* nz = noise + (size_t)g * AZG_A;
+        const float keep = (float)(1.0 - e.eps);                            // (1-eps)*p stays float32 (NEP 50)
+        double q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = 8 * l + j;
+          q[j] = 0.0;
+          if (idx < AZG_A) {
+            q[j] = __dadd_rn((double)__fmul_rn(keep, p[j]), __dmul_rn(e.eps, nz[idx]));
+            smd[idx] = q[j];
+          }
+        }
+        __syncwarp();
+        const double tot = numpy_sum225<double>(smd);
+        __syncwarp();
+        double* P64 = e.P64 + ((size_t)g * AZG_P64_SLOTS + slot) * AZG_ROW;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = 8 * l + j;
+          if (idx < AZG_A) { P64[idx] = __ddiv_rn(q[j], tot); p[j] = (float)P64[idx]; }
+        }
+      }
+    }
+    if (l < 28) {
+      float4* P = reinterpret_cast<float4*>(e.P + base + 8 * l);
+      P[0] = make_float4(p[0], p[1], p[2], p[3]);
+      P[1] = make_float4(p[4], p[5], p[6], p[7]);
+      const int4 z = make_int4(0, 0, 0, 0);
+      int4* Nn = reinterpret_cast<int4*>(e.Nv + base + 8 * l);
+      int4* Ww = reinterpret_cast<int4*>(e.W + base + 8 * l);
+      Nn[0] = z; Nn[1] = z; Ww[0] = z; Ww[1] = z;
+    } else if (l == 28) {
+      e.P[base + 224] = p[0]; e.Nv[base + 224] = 0; e.W[base + 224] = 0;
+    }
+    if (l == 0) e.meta[off] = meta;
+  }
+  if (l == 0) {
+    ctl->evals += (unsigned long long)n_pending;
+    ctl->n_pending = 0;
+    ctl->p64_used = p64_used;
+    if (err) { ctl->err |= err; ctl->state = AZG_ST_ERROR; }
+    else ctl->state = (state == AZG_ST_NEED_FINAL) ? AZG_ST_DONE : AZG_ST_RUN;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// run control
+// ------------------------------------------------------------------------------------------------
+// Start a run on every game (new_mcts_alpha.py:77-83): fix the root key, look it up.
+extern "C" __global__ void __launch_bounds__(128) azg_begin_kernel(azg_dev e, const int32_t* __restrict__ plies, int n_sims) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= e.G) return;
+  azg_ctl* ctl = e.ctl + g;
+  const WPos root = wpos_load(&ctl->root);
+  int state = AZG_ST_RUN, err = 0, root_node = -1;
+  if (wpos_winner(root, e.rule) != 0 || !wpos_any_empty(root)) {
+    // the reference would raise KeyError at new_mcts_alpha.py:89; reported as an error status
+    state = AZG_ST_ERROR; err = AZG_ERR_ROOT_TERMINAL;
+  } else {
+    int ins;
+    root_node = table_find(e, g, root, wpos_hash(root), &ins);
+  }
+  if (lane_id() == 0) {
+    ctl->state = state; ctl->err = err; ctl->sims_left = n_sims;
+    ctl->ply = plies ? plies[g] : root.plies;
+    ctl->root_node = root_node; ctl->susp = 0; ctl->depth = 0; ctl->resume_node = -1; ctl->n_pending = 0;
+  }
+}
+
+// pi = N[root]/sum(N[root]) in float32, uniform over legal moves when the sum is zero
+// (new_mcts_alpha.py:88-97).  Also exports the raw visit counts.
+extern "C" __global__ void __launch_bounds__(128)
+azg_finish_kernel(azg_dev e, float* __restrict__ pi, int32_t* __restrict__ visits) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= e.G) return;
+  const int l = lane_id();
+  const azg_ctl* ctl = e.ctl + g;
+  const int node = ctl->root_node;
+  if (node < 0 || ctl->state == AZG_ST_ERROR) {
+    for (int a = l; a < AZG_A; a += 32) { if (pi) pi[(size_t)g * AZG_A + a] = 0.f; if (visits) visits[(size_t)g * AZG_A + a] = 0; }
+    return;
+  }
+  const size_t base = azg_node_off(e, g, node) * AZG_ROW;
+  const WPos root = wpos_load(&ctl->root);
+  int n[8], tot = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const int idx = 8 * l + j; n[j] = idx < AZG_A ? e.Nv[base + idx] : 0; tot += n[j]; }
+  tot = __reduce_add_sync(AZG_FULL, tot);
+  const uint32_t legal = wpos_legal_byte(root);
+  const int cnt = wpos_count_empty(root);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = 8 * l + j;
+    if (idx < AZG_A) {
+      float v;
+      if (tot > 0) v = __fdiv_rn((float)n[j], (float)tot);
+      else v = (legal & (1u << j)) ? __fdiv_rn(1.0f, (float)cnt) : 0.f;
+      if (pi) pi[(size_t)g * AZG_A + idx] = v;
+      if (visits) visits[(size_t)g * AZG_A + idx] = n[j];
+    }
+  }
+}
+
+// Play `actions[g]` on the root (skipped when < 0) and reclaim dead nodes.
+//   Gomoku: stones are never removed, so a stored position can be reached again only
+//           if it contains every stone of the new root.
+//   Pente : a root stone missing from a stored position must have been captured on the
+//           way, and no path the search follows lets a player exceed four captured
+//           pairs before the position is terminal (games/pente.py:209), so a stored
+//           position missing more than 2*(4-caps) root stones of a colour is dead.
+// Everything that survives is re-inserted into a cleared table; freed slots go to the
+// free stack.  gc == 0 keeps every node.
+extern "C" __global__ void __launch_bounds__(128)
+azg_advance_kernel(azg_dev e, const int32_t* __restrict__ actions, int gc, int32_t* __restrict__ status) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= e.G) return;
+  const int l = lane_id();
+  azg_ctl* ctl = e.ctl + g;
+  WPos root = wpos_load(&ctl->root);
+  const int a = actions ? actions[g] : -1;
+  int ok = 1;
+  if (a >= 0) {
+    const bool empty = a < AZG_A && wpos_at(root, a < AZG_A ? a : 0) == 0;
+    if (empty) { wpos_play(root, e.rule, a); wpos_store(&ctl->root, root); }
+    else ok = 0;
+  }
+  const int won = wpos_winner(root, e.rule);
+  const bool over = won != 0 || !wpos_any_empty(root);
+  if (status && l == 0) status[g] = (ok ? 0 : 8) | (over ? 4 : 0) | won;
+  if (!gc || a < 0 || !ok) return;
+
+  const int n_nodes = ctl->n_nodes;
+  int n_free = 0, n_live = 0, p64_used = 0;
+  int32_t* freelist = e.freelist + (size_t)g * e.cap;
+  unsigned long long* tab = e.slots + (size_t)g * (size_t)e.hcap;
+  for (int i = l; i < e.hcap; i += 32) __stcg(&tab[i], 0ULL);
+  __threadfence_block();
+  __syncwarp();
+  const int lim1 = e.rule == 1 ? 2 * max(0, 4 - root.cap1) : 0;   // player-1 stones that player 2 may still capture
+  const int lim2 = e.rule == 1 ? 2 * max(0, 4 - root.cap0) : 0;
+  for (int node = 0; node < n_nodes; ++node) {
+    const size_t off = azg_node_off(e, g, node);
+    const uint32_t meta = e.meta[off];
+    // this lane's word of the stored key, same distribution as WPos
+    WPos k;
+    k.w0 = e.key[off * 16 + (l >> 2)];
+    k.w1 = e.key[off * 16 + 8 + (l >> 2)];
+    k.player = (meta >> 1) & 3; k.last = -1; k.cap0 = k.cap1 = 0; k.plies = 0;
+    int d1 = (l & 3) == 0 ? __popc(root.w0 & ~k.w0) : 0;
+    int d2 = (l & 3) == 0 ? __popc(root.w1 & ~k.w1) : 0;
+    d1 = __reduce_add_sync(AZG_FULL, d1);
+    d2 = __reduce_add_sync(AZG_FULL, d2);
+    const bool alive = (meta & AZG_META_ALIVE) && d1 <= lim1 && d2 <= lim2;
+    if (alive) {
+      const unsigned long long h = wpos_hash(k);
+      int ins = -1;
+      // keys are unique, so only the insertion point is needed
+      const int nwin = e.hcap >> 5;
+      int win = (int)((uint32_t)h & (uint32_t)(nwin - 1));
+      for (int t = 0; t < nwin; ++t) {
+        const unsigned long long s = __ldcg(&tab[(win << 5) + l]);
+        const uint32_t em = __ballot_sync(AZG_FULL, s == 0ULL);
+        if (em) { ins = (win << 5) + __ffs(em) - 1; break; }
+        win = (win + 1) & (nwin - 1);
+      }
+      if (ins >= 0 && l == 0) __stcg(&tab[ins], ((h >> 32) << 32) | (unsigned long long)(uint32_t)(node + 1));
+      __threadfence_block();
+      __syncwarp();
+      ++n_live;
+      const int s64 = (int)((meta >> 4) & 15u) - 1;
+      if (s64 >= 0) p64_used |= 1 << s64;
+    } else {
+      if (l == 0) { e.meta[off] = 0u; freelist[n_free] = node; }
+      ++n_free;
+    }
+  }
+  if (l == 0) { ctl->n_free = n_free; ctl->n_live = n_live; ctl->p64_used = p64_used; }
+}
+
+// Forget every node of the selected games (MCTS.clear_tree, new_mcts_alpha.py:58-72)
+// and optionally load new root positions.
+extern "C" __global__ void __launch_bounds__(128)
+azg_reset_kernel(azg_dev e, const int32_t* __restrict__ mask, const azg_pos* __restrict__ roots, int clear_tree) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= e.G) return;
+  if (mask && !mask[g]) return;
+  const int l = lane_id();
+  azg_ctl* ctl = e.ctl + g;
+  if (roots) {
+    const WPos p = wpos_load(roots + g);
+    wpos_store(&ctl->root, p);
+  }
+  if (clear_tree) {
+    unsigned long long* tab = e.slots + (size_t)g * (size_t)e.hcap;
+    for (int i = l; i < e.hcap; i += 32) tab[i] = 0ULL;
+    if (l == 0) {
+      ctl->n_nodes = 0; ctl->n_free = 0; ctl->n_live = 0; ctl->p64_used = 0; ctl->n_pending = 0; ctl->susp = 0;
+      ctl->root_node = -1; ctl->state = AZG_ST_IDLE; ctl->err = 0;
+    }
+  }
+}

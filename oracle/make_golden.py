@@ -1,0 +1,407 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference and pin the oracle to it.
+
+Run in the build container only (needs /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden
+
+For every fixture the reference's own classes (games/gomoku.py, games/pente.py,
+mcts/new_mcts_alpha.py, network.py, train.py helpers) produce the expected
+values; the oracle restatement is run on the same inputs and must agree bit for
+bit (asserted here) before anything is written.  The GPU box has no
+/root/reference: tests there compare against these committed files and against
+the oracle.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("AZG_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+
+from games.gomoku import Gomoku          # noqa: E402  (reference)
+from games.pente import Pente            # noqa: E402  (reference)
+from mcts.new_mcts_alpha import MCTS     # noqa: E402  (reference)
+
+from oracle import fakes, rules          # noqa: E402
+from oracle.search import Search, dihedral8   # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+REF_GAME = {rules.GOMOKU: Gomoku, rules.PENTE: Pente}
+
+
+def ref_caps(g):
+    return [g.captures[1], g.captures[2]] if hasattr(g, "captures") else [0, 0]
+
+
+def check_same(g, pos, where):
+    assert np.array_equal(g.board.reshape(-1), pos.cells), where
+    assert g.current_player == pos.player, where
+    assert ref_caps(g) == pos.caps, where
+    assert g.check_winner() == rules.winner(pos), where
+    assert bool(g.is_game_over()) == rules.game_over(pos), where
+    assert np.array_equal(g.get_valid_moves(), rules.legal_mask(pos)), where
+    assert np.array_equal(g.get_encoded_state(), rules.encode(pos)), where
+
+
+# --------------------------------------------------------------------------- rules
+def scripted_traces():
+    """Hand-built move lists (r, c) that hit the edge cases SURVEY section 4 lists."""
+    T = []
+    # horizontal five on the top edge, player 1
+    T.append(("gomoku_edge_row", rules.GOMOKU, [(0, 0), (5, 5), (0, 1), (5, 6), (0, 2), (5, 7), (0, 3), (9, 9), (0, 4)]))
+    # vertical five in the last column, player 2
+    T.append(("gomoku_edge_col", rules.GOMOKU, [(7, 7), (14, 14), (7, 8), (13, 14), (1, 1), (12, 14), (2, 2), (11, 14), (9, 3), (10, 14)]))
+    # overline (six) completed in the middle wins
+    T.append(("gomoku_overline", rules.GOMOKU, [(3, 3), (9, 0), (3, 4), (9, 1), (3, 5), (9, 2), (3, 7), (12, 0), (3, 8), (12, 1), (3, 6)]))
+    # both diagonals
+    T.append(("gomoku_diag", rules.GOMOKU, [(4, 4), (0, 9), (5, 5), (1, 9), (6, 6), (2, 9), (7, 7), (5, 9), (8, 8)]))
+    T.append(("gomoku_antidiag", rules.GOMOKU, [(0, 0), (4, 10), (1, 1), (5, 9), (2, 2), (6, 8), (9, 9), (7, 7), (10, 10), (8, 6)]))
+    # illegal attempts: occupied, off board (do_move must return False and change nothing)
+    T.append(("gomoku_illegal", rules.GOMOKU, [(7, 7), (7, 7), (-1, 0), (15, 0), (0, 15), (0, -1), (7, 8)]))
+    # SURVEY 8c Pente fact: capture along (0,-1) from the new stone
+    T.append(("pente_capture_kat", rules.PENTE, [(7, 7), (7, 8), (0, 0), (7, 9), (7, 10)]))
+    # double capture with one stone (two rays)
+    T.append(("pente_double", rules.PENTE, [(7, 4), (7, 5), (4, 7), (7, 6), (0, 0), (5, 7), (0, 1), (6, 7), (7, 7)]))
+    # capture on the edge rays / no capture when the far cell is off board
+    T.append(("pente_edge", rules.PENTE, [(0, 3), (0, 1), (9, 9), (0, 2), (5, 5), (14, 14), (0, 0)]))
+    # five pairs captured by player 1 -> capture win
+    seq = []
+    for i in range(5):
+        r = 2 * i + 1
+        seq += [(r, 3), (r, 1), (r + 1, 9 + (i % 2)), (r, 2), (r, 0)]
+        if i < 4:
+            seq += [(14, i)]
+    T.append(("pente_capture_win", rules.PENTE, seq))
+    T.append(("pente_illegal", rules.PENTE, [(7, 7), (7, 7), (20, 3), (3, -2), (7, 8)]))
+    return T
+
+
+def run_trace(rule, moves):
+    """Play (r,c) moves on reference and oracle; return per-ply arrays."""
+    g = REF_GAME[rule](15)
+    pos = rules.Position(rule)
+    boards, players, caps, wins, overs, oks, lasts = [], [], [], [], [], [], []
+    for i, (r, c) in enumerate(moves):
+        ok_ref = g.do_move((r, c))
+        ok_or = rules.play_rc(pos, r, c)
+        assert ok_ref == ok_or, (rule, i, r, c)
+        check_same(g, pos, (rule, i))
+        assert (g.last_move is None and pos.last < 0) or (g.last_move[0] * 15 + g.last_move[1] == pos.last)
+        boards.append(g.board.reshape(-1).astype(np.int8).copy())
+        players.append(g.current_player)
+        caps.append(ref_caps(g))
+        wins.append(g.check_winner())
+        overs.append(bool(g.is_game_over()))
+        oks.append(bool(ok_ref))
+        lasts.append(pos.last)
+    return dict(moves=np.array(moves, dtype=np.int16).reshape(-1, 2), boards=np.array(boards, dtype=np.int8),
+                players=np.array(players, dtype=np.int8), caps=np.array(caps, dtype=np.int16),
+                winners=np.array(wins, dtype=np.int8), overs=np.array(overs, dtype=np.bool_),
+                oks=np.array(oks, dtype=np.bool_), lasts=np.array(lasts, dtype=np.int16))
+
+
+def random_trace(rule, rng, p_illegal=0.03, dense=False):
+    """Random playout to the end.  ``dense`` biases moves towards existing stones
+    so that captures and lines actually occur."""
+    g = REF_GAME[rule](15)
+    moves = []
+    while not g.is_game_over():
+        if rng.random() < p_illegal:
+            moves.append((int(rng.integers(-2, 17)), int(rng.integers(-2, 17))))
+            if g.clone().do_move(moves[-1]):
+                g.do_move(moves[-1])
+            continue
+        empties = np.flatnonzero(g.board.reshape(-1) == 0)
+        if dense and len(g.move_history) > 0 and rng.random() < 0.85:
+            pr, pc = g.move_history[int(rng.integers(0, len(g.move_history)))]
+            cand = [(pr + dr) * 15 + (pc + dc) for dr in range(-3, 4) for dc in range(-3, 4)
+                    if 0 <= pr + dr < 15 and 0 <= pc + dc < 15 and g.board[pr + dr, pc + dc] == 0]
+            a = int(cand[int(rng.integers(0, len(cand)))]) if cand else int(empties[int(rng.integers(0, len(empties)))])
+        else:
+            a = int(empties[int(rng.integers(0, len(empties)))])
+        moves.append(divmod(a, 15))
+        g.do_move(moves[-1])
+    return moves
+
+
+def build_rules():
+    out = {}
+    names = []
+    for name, rule, moves in scripted_traces():
+        t = run_trace(rule, moves)
+        names.append((name, rule))
+        for k, v in t.items():
+            out[f"{name}/{k}"] = v
+    rng = np.random.default_rng(20261018)
+    for rule, tag in ((rules.GOMOKU, "gomoku"), (rules.PENTE, "pente")):
+        for i in range(12):
+            moves = random_trace(rule, rng, dense=(i % 2 == 1))
+            t = run_trace(rule, moves)
+            name = f"{tag}_random{i}"
+            names.append((name, rule))
+            for k, v in t.items():
+                out[f"{name}/{k}"] = v
+    # board-full draw: fill the board in an order that never makes five in a row
+    g = Gomoku(15)
+    moves = draw_fill_order()
+    t = run_trace(rules.GOMOKU, moves)
+    assert t["winners"][-1] == 0 and t["overs"][-1] and not t["overs"][-2], "draw fill must end in a draw"
+    names.append(("gomoku_full_draw", rules.GOMOKU))
+    for k, v in t.items():
+        out[f"gomoku_full_draw/{k}"] = v
+    out["names"] = np.array([n for n, _ in names])
+    out["rules"] = np.array([r for _, r in names], dtype=np.int8)
+    # the SURVEY 8c facts, asserted on the reference itself
+    t = {k.split("/", 1)[1]: v for k, v in out.items() if k.startswith("pente_capture_kat/")}
+    assert t["caps"][-1].tolist() == [1, 0] and t["boards"][-1].reshape(15, 15)[7, 6:12].tolist() == [0, 1, 0, 0, 1, 0]
+    np.savez_compressed(os.path.join(OUT, "rules_traces.npz"), **out)
+    plies = sum(len(v) for k, v in out.items() if k.endswith("/players"))
+    print(f"rules_traces.npz: {len(names)} traces, {plies} plies, caps max {max(int(v.max()) for k, v in out.items() if k.endswith('/caps'))}")
+
+
+def draw_fill_order():
+    """A full 225-move game with no five in a row: colour(r,c) = ((c + 2r) mod 4) // 2
+    gives runs of at most two in every direction, 113 cells for player 1 and 112 for
+    player 2; the moves are interleaved to respect turn order."""
+    want = np.array([[((c + 2 * r) % 4) // 2 + 1 for c in range(15)] for r in range(15)], dtype=np.int8)
+    ones = [tuple(x) for x in np.argwhere(want == 1)]
+    twos = [tuple(x) for x in np.argwhere(want == 2)]
+    assert len(ones) == 113 and len(twos) == 112
+    order = []
+    for i in range(112):
+        order += [ones[i], twos[i]]
+    order.append(ones[112])
+    return [(int(r), int(c)) for r, c in order]
+
+
+# --------------------------------------------------------------------------- search
+class RefGameFactory:
+    """Build a reference game object from an oracle Position (for MCTS.run)."""
+
+    @staticmethod
+    def make(pos):
+        g = REF_GAME[pos.rule](15)
+        g.board = pos.cells.reshape(15, 15).copy()
+        g.current_player = pos.player
+        g.last_move = None if pos.last < 0 else divmod(pos.last, 15)
+        g.move_history = [(0, 0)] * pos.plies          # only its length is read (train.py:371)
+        if pos.rule == rules.PENTE:
+            g.captures = {1: pos.caps[0], 2: pos.caps[1]}
+        return g
+
+
+def search_case(rule, model_name, n_sims, queue_len, n_moves, cpuct=1.0, opening=()):
+    """Play ``n_moves`` argmax moves with tree reuse on reference and oracle; record
+    N[root] (int32), pi (f32), eval counts and the chosen move for every run."""
+    ref_model = fakes.BY_NAME[model_name]()
+    orc_model = fakes.BY_NAME[model_name]()
+    ref = MCTS(REF_GAME[rule], n_sims, ref_model, cpuct=cpuct, batch_size=queue_len, add_dirichlet_noise=False)
+    orc = Search(rule, n_sims, orc_model, cpuct=cpuct, queue_len=queue_len, noise=False)
+    g = REF_GAME[rule](15)
+    pos = rules.Position(rule)
+    for mv in opening:
+        assert g.do_move(divmod(mv, 15)) and rules.play(pos, mv)
+    Ns, pis, evals, moves, nodes = [], [], [], [], []
+    for _ in range(n_moves):
+        if g.is_game_over():
+            break
+        pi_ref = ref.run(g, len(g.move_history))
+        pi_orc = orc.run(pos, pos.plies)
+        key = ref._state_key(g)
+        assert key == pos.key()
+        assert pi_ref.dtype == np.float32 and np.array_equal(pi_ref, pi_orc), (rule, model_name, n_sims, queue_len)
+        assert np.array_equal(ref.N[key], orc.Nv[key])
+        assert len(ref.P) == len(orc.P) and ref_model.rows == orc_model.rows and ref_model.calls == orc_model.calls
+        Ns.append(ref.N[key].astype(np.int32))
+        pis.append(pi_ref.copy())
+        evals.append((ref_model.rows, ref_model.calls))
+        nodes.append(len(ref.P))
+        a = int(np.argmax(pi_ref))
+        moves.append(a)
+        g.do_move(divmod(a, 15))
+        rules.play(pos, a)
+    return dict(N=np.array(Ns, dtype=np.int32), pi=np.array(pis, dtype=np.float32),
+                evals=np.array(evals, dtype=np.int64), moves=np.array(moves, dtype=np.int16),
+                nodes=np.array(nodes, dtype=np.int64), opening=np.array(opening, dtype=np.int16))
+
+
+SEARCH_CASES = [
+    # (name, rule, model, n_sims, queue_len, n_moves, cpuct, opening)
+    ("kat_uniform_100", rules.GOMOKU, "uniform", 100, 32, 1, 1.0, ()),
+    ("kat_uniform_400", rules.GOMOKU, "uniform", 400, 32, 1, 1.0, ()),
+    ("kat_uniform_800", rules.GOMOKU, "uniform", 800, 32, 1, 1.0, ()),
+    ("kat_uniform_400_pente", rules.PENTE, "uniform", 400, 32, 1, 1.0, ()),
+    ("g_hashed_1", rules.GOMOKU, "hashed", 1, 32, 3, 1.0, ()),
+    ("g_hashed_31", rules.GOMOKU, "hashed", 31, 32, 4, 1.0, ()),
+    ("g_hashed_32", rules.GOMOKU, "hashed", 32, 32, 4, 1.0, ()),
+    ("g_hashed_33", rules.GOMOKU, "hashed", 33, 32, 4, 1.0, ()),
+    ("g_hashed_100_q8", rules.GOMOKU, "hashed", 100, 8, 6, 1.0, ()),
+    ("g_hashed_60_q1", rules.GOMOKU, "hashed", 60, 1, 3, 1.0, ()),
+    ("g_hashed_400", rules.GOMOKU, "hashed", 400, 32, 30, 1.0, ()),
+    ("g_hashed_800", rules.GOMOKU, "hashed", 800, 32, 6, 1.0, ()),
+    ("g_hashed_400_c25", rules.GOMOKU, "hashed", 400, 32, 8, 2.5, ()),
+    ("g_spiky_400", rules.GOMOKU, "spiky", 400, 32, 40, 1.0, ()),
+    ("g_fixedspike_200", rules.GOMOKU, "fixedspike", 200, 32, 12, 1.0, ()),
+    ("p_hashed_400", rules.PENTE, "hashed", 400, 32, 30, 1.0, ()),
+    ("p_spiky_300", rules.PENTE, "spiky", 300, 32, 40, 1.0, ()),
+    ("p_hashed_100_q8", rules.PENTE, "hashed", 100, 8, 10, 1.0, ()),
+    # terminal-heavy: an opening where both sides hold open fours / capture threats
+    ("g_endgame_400", rules.GOMOKU, "hashed", 400, 32, 12, 1.0,
+     (112, 97, 113, 98, 114, 99, 115, 100, 7 * 15 + 2, 6 * 15 + 2)),
+    ("p_endgame_300", rules.PENTE, "hashed", 300, 32, 12, 1.0,
+     (112, 113, 0, 114, 115, 128, 1, 143, 158, 127, 2, 142)),
+]
+
+
+def build_search():
+    out = {"names": np.array([c[0] for c in SEARCH_CASES])}
+    for name, rule, model, n_sims, q, n_moves, cpuct, opening in SEARCH_CASES:
+        r = search_case(rule, model, n_sims, q, n_moves, cpuct, opening)
+        for k, v in r.items():
+            out[f"{name}/{k}"] = v
+        out[f"{name}/cfg"] = np.array([rule, n_sims, q, n_moves], dtype=np.int64)
+        out[f"{name}/cpuct"] = np.array([cpuct], dtype=np.float64)
+        out[f"{name}/model"] = np.array([model])
+        print(f"  {name}: {len(r['moves'])} runs, evals {r['evals'][-1].tolist()}, nodes {int(r['nodes'][-1])}, sumN0 {int(r['N'][0].sum())}")
+    # SURVEY 8c known answers, re-derived from the reference here
+    for n, (tot, nnz, mx, sha) in {100: (69, 69, 1, "7bbbd774cfe75043"), 400: (369, 225, 2, "7c21360da2a20891"),
+                                   800: (769, 225, 4, "06859f65f08731e8")}.items():
+        N0 = out[f"kat_uniform_{n}/N"][0]
+        got = hashlib.sha256(N0.astype(np.int32).tobytes()).hexdigest()[:16]
+        assert (int(N0.sum()), int((N0 > 0).sum()), int(N0.max()), got) == (tot, nnz, mx, sha), (n, got)
+    np.savez_compressed(os.path.join(OUT, "search_visits.npz"), **out)
+    print("search_visits.npz written")
+
+
+# --------------------------------------------------------------------------- noise (f64 root)
+def build_noise():
+    """Root Dirichlet mixing with an injected noise vector: the reference draws from
+    numpy's global generator (:172), so seed it, capture the draw, and feed the same
+    vector to the oracle.  Pins the float64 PUCT path at a noised root."""
+    out = {}
+    for tag, rule in (("g", rules.GOMOKU), ("p", rules.PENTE)):
+        ref_model, orc_model = fakes.Hashed(), fakes.Hashed()
+        ref = MCTS(REF_GAME[rule], 300, ref_model, cpuct=1.0, batch_size=32, dirichlet_alpha=0.05, epsilon=0.25,
+                   apply_dirichlet_n_first_moves=10, add_dirichlet_noise=True)
+        draws = []
+        rs = np.random.RandomState(99)
+
+        def noise_fn(n, rs=rs, draws=draws):
+            d = rs.dirichlet([0.05] * n)
+            draws.append(d)
+            return d
+        orc = Search(rule, 300, orc_model, cpuct=1.0, queue_len=32, alpha=0.05, eps=0.25, noise_plies=10, noise=True,
+                     noise_fn=noise_fn)
+        np.random.seed(99)
+        g = REF_GAME[rule](15)
+        pos = rules.Position(rule)
+        Ns, pis, moves = [], [], []
+        for _ in range(4):
+            state = np.random.get_state()
+            pi_ref = ref.run(g, len(g.move_history))
+            after = np.random.get_state()
+            np.random.set_state(state)
+            rs.set_state(state)
+            pi_orc = orc.run(pos, pos.plies)
+            np.random.set_state(after)
+            assert np.array_equal(pi_ref, pi_orc)
+            key = pos.key()
+            Ns.append(ref.N[key].astype(np.int32))
+            pis.append(pi_ref.astype(np.float32))
+            a = int(np.argmax(pi_ref))
+            moves.append(a)
+            g.do_move(divmod(a, 15))
+            rules.play(pos, a)
+        out[f"{tag}/N"] = np.array(Ns)
+        out[f"{tag}/pi"] = np.array(pis)
+        out[f"{tag}/moves"] = np.array(moves, dtype=np.int16)
+        out[f"{tag}/draws"] = np.array(draws, dtype=np.float64)
+        print(f"  noise {tag}: {len(draws)} draws, sumN {[int(n.sum()) for n in Ns]}")
+    np.savez_compressed(os.path.join(OUT, "search_noise.npz"), **out)
+
+
+# --------------------------------------------------------------------------- symmetries / sampling
+def build_misc():
+    import train as ref_train        # reference train.py (imports torch)
+    rng = np.random.default_rng(5)
+    planes = (rng.random((3, 15, 15)) < 0.3).astype(np.float32)
+    pi = rng.random(225).astype(np.float32)
+    pi /= pi.sum()
+    ref = MCTS(Gomoku, 1, None).symmetries(planes, pi)
+    mine = dihedral8(planes, pi)
+    for (a, b), (c, d) in zip(ref, mine):
+        assert np.array_equal(a, c) and np.array_equal(b, d)
+    from oracle import selfplay
+    temps = [0.0, 1.0, 0.7, 0.1]
+    tp = []
+    for t in temps:
+        r = ref_train.softmax_temperature(pi, t)
+        m = selfplay.temper(pi, t)
+        assert np.array_equal(r, m)
+        tp.append(np.asarray(r, dtype=np.float64))
+    assert ref_train.sample_action_from_pi(pi, 0) == selfplay.pick(pi, 0)
+    np.savez_compressed(os.path.join(OUT, "symmetry_sampling.npz"), planes=planes, pi=pi,
+                        sym_planes=np.array([np.ascontiguousarray(a) for a, _ in ref]),
+                        sym_pi=np.array([b for _, b in ref]), temps=np.array(temps), tempered=np.array(tp))
+    print("symmetry_sampling.npz written")
+
+
+# --------------------------------------------------------------------------- network
+def build_net():
+    import torch
+    import network as ref_net          # reference network.py
+    from oracle import net as onet
+    out = {}
+    rng = np.random.default_rng(11)
+    # 24 positions from random legal playouts of 0..120 plies (SURVEY 8d recipe)
+    X = []
+    for i in range(24):
+        pos = rules.Position(rules.GOMOKU)
+        for _ in range(int(rng.integers(0, 121))):
+            e = np.flatnonzero(pos.cells == 0)
+            rules.play(pos, int(e[int(rng.integers(0, len(e)))]))
+        X.append(rules.encode(pos))
+    X = np.stack(X).astype(np.float32)
+    out["X"] = X
+    torch.set_num_threads(1)
+    for tag, blocks, ch in (("3x64", 3, 64), ("6x128", 6, 128)):
+        torch.manual_seed(0)
+        m = ref_net.PyTorchModel(board_size=15, n_res_blocks=blocks, channels=ch, device="cpu")
+        sd = m.net.state_dict()
+        probs, values = m.predict(X)
+        with torch.no_grad():
+            m.net.eval()
+            logits, _ = m.net(torch.from_numpy(X))
+        lo, va = onet.forward(sd, torch.from_numpy(X))
+        assert torch.equal(lo, logits), "oracle forward differs from reference forward"
+        cm = onet.CpuModel(sd)
+        p2, v2 = cm.predict(X)
+        assert np.array_equal(p2, probs) and np.array_equal(v2, values)
+        out[f"{tag}/logits"] = logits.numpy()
+        out[f"{tag}/probs"] = probs
+        out[f"{tag}/values"] = values
+        # per-tensor checksums so tests can prove "same seed -> same weights" without shipping them
+        names = sorted(k for k, v in sd.items() if v.dtype.is_floating_point)
+        out[f"{tag}/param_names"] = np.array(names)
+        out[f"{tag}/param_sums"] = np.array([float(sd[k].double().sum()) for k in names])
+        out[f"{tag}/param_abs"] = np.array([float(sd[k].double().abs().sum()) for k in names])
+        out[f"{tag}/n_params"] = np.array([sum(p.numel() for p in m.net.parameters())])
+        print(f"  net {tag}: params {int(out[f'{tag}/n_params'][0])}, logit std {float(logits.std()):.2f}")
+    np.savez_compressed(os.path.join(OUT, "net_outputs.npz"), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["rules", "search", "noise", "misc", "net"]
+    for w in which:
+        print(f"== {w}")
+        {"rules": build_rules, "search": build_search, "noise": build_noise, "misc": build_misc, "net": build_net}[w]()
+
+
+if __name__ == "__main__":
+    main()

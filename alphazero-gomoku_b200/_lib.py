@@ -1,0 +1,93 @@
+"""ctypes binding of libazgomoku_b200.so (the C ABI in include/azgomoku_b200.h).
+
+The library is built in-tree by ``make -C alphazero-gomoku_b200/csrc`` (or
+``__graft_entry__.build()``).  There is no fallback of any kind: a missing
+library raises at import time and every compute call fails when no sm_100
+device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libazgomoku_b200.so")
+
+
+class AzgError(RuntimeError):
+    pass
+
+
+class azg_pos(C.Structure):
+    _fields_ = [("stones", (C.c_uint32 * 8) * 2), ("player", C.c_int32), ("last", C.c_int32),
+                ("caps", C.c_int32 * 2), ("plies", C.c_int32), ("pad", C.c_int32 * 3)]
+
+
+class azg_config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("rule", C.c_int32), ("n_games", C.c_int32), ("queue_len", C.c_int32),
+                ("node_capacity", C.c_int32), ("noise_on", C.c_int32), ("noise_plies", C.c_int32),
+                ("reserved", C.c_int32), ("cpuct", C.c_double), ("alpha", C.c_double), ("eps", C.c_double),
+                ("seed", C.c_uint64)]
+
+
+assert C.sizeof(azg_pos) == 96
+
+_P = C.c_void_p
+_I = C.c_int
+# name -> (restype, argtypes); must list every symbol the header declares (tests check this)
+PROTOTYPES = {
+    "azg_last_error": (C.c_char_p, []),
+    "azg_abi_version": (_I, []),
+    "azg_device_count": (_I, []),
+    "azg_rules_pack": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
+    "azg_rules_unpack": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
+    "azg_rules_play": (_I, [_I, _P, _P, _P, _I, _P]),
+    "azg_rules_status": (_I, [_I, _P, _P, _I, _P]),
+    "azg_rules_legal": (_I, [_P, _P, _I, _P]),
+    "azg_rules_encode": (_I, [_P, _P, _I, _P]),
+    "azg_rules_play_host": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _I]),
+    "azg_create": (_I, [C.POINTER(azg_config), C.POINTER(_P)]),
+    "azg_destroy": (_I, [_P]),
+    "azg_set_stream": (_I, [_P, _P]),
+    "azg_memory_bytes": (C.c_int64, [_P]),
+    "azg_set_roots": (_I, [_P, _P, _P, _I]),
+    "azg_get_roots": (_I, [_P, _P]),
+    "azg_search_begin": (_I, [_P, _P, _I]),
+    "azg_search_fill": (_I, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "azg_search_counters": (_P, [_P]),
+    "azg_search_leaf_planes": (_I, [_P, _P]),
+    "azg_search_commit": (_I, [_P, _P, _P]),
+    "azg_search_result": (_I, [_P, _P, _P]),
+    "azg_search_advance": (_I, [_P, _P, _I, _P]),
+    "azg_search_stats": (_I, [_P, _P]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+            "(this package has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise AzgError(f"azgomoku_b200 error {rc}: {lib.azg_last_error().decode()}")
+
+
+def ptr(t) -> C.c_void_p:
+    """Device (or host) address of a torch tensor / numpy array / None."""
+    if t is None:
+        return C.c_void_p(0)
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include "../../include/azgomoku_b200.h"
 
 #define AZG_N 15
 #define AZG_A 225
@@ -16,15 +17,7 @@
 #define AZG_P64_SLOTS 8          // float64 prior rows per game (noised roots)
 #define AZG_FULL 0xffffffffu
 
-// Packed position: stones[colour-1][word] bit a&31 of word a>>5 is cell a.
-struct azg_pos {
-  uint32_t stones[2][8];
-  int32_t player;      // side to move, 1 or 2
-  int32_t last;        // action index of the last stone, -1 == None
-  int32_t caps[2];     // Pente captured pairs of player 1 / 2
-  int32_t plies;       // len(move_history)
-  int32_t pad[3];
-};
+// Packed position (azg_pos) comes from the public header: stones[colour-1][word], bit a&31 of word a>>5 is cell a.
 static_assert(sizeof(azg_pos) == 96, "azg_pos layout is part of the C ABI");
 
 // Per-game search control block (device resident).

@@ -14,6 +14,7 @@
 // order (new_mcts_alpha.py:136-140); float64 at a Dirichlet-noised root.
 #include "common.cuh"
 #include "rules.cuh"
+#include "kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // transposition table: per-game open addressing in windows of 32 slots (one coalesced probe)
@@ -280,9 +281,9 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
 // ------------------------------------------------------------------------------------------------
 extern "C" __global__ void __launch_bounds__(1024) azg_scan_kernel(azg_dev e) {
   __shared__ int part[1024];
-  __shared__ int carry, s_active, s_errors;
+  __shared__ int carry, s_active, s_errors, s_roots;
   const int t = threadIdx.x;
-  if (t == 0) { carry = 0; s_active = 0; s_errors = 0; }
+  if (t == 0) { carry = 0; s_active = 0; s_errors = 0; s_roots = 0; }
   __syncthreads();
   for (int base = 0; base < e.G; base += 1024) {
     const int g = base + t;
@@ -290,8 +291,10 @@ extern "C" __global__ void __launch_bounds__(1024) azg_scan_kernel(azg_dev e) {
     if (g < e.G) {
       st = e.ctl[g].state;
       if (st == AZG_ST_NEED_EVAL || st == AZG_ST_NEED_FINAL) n = e.ctl[g].n_pending;
-      if (st == AZG_ST_RUN || st == AZG_ST_NEED_EVAL || st == AZG_ST_NEED_FINAL) atomicAdd(&s_active, 1);
+      if (st == AZG_ST_RUN || st == AZG_ST_NEED_EVAL) atomicAdd(&s_active, 1);   // needs another fill after the commit
       if (st == AZG_ST_ERROR) atomicAdd(&s_errors, 1);
+      const int rn = e.ctl[g].root_node;
+      for (int i = 0; i < n; ++i) if (e.ctl[g].pending[i] == rn) atomicAdd(&s_roots, 1);
     }
     part[t] = n;
     __syncthreads();
@@ -313,7 +316,7 @@ extern "C" __global__ void __launch_bounds__(1024) azg_scan_kernel(azg_dev e) {
     if (t == 1023) carry += part[t];
     __syncthreads();
   }
-  if (t == 0) { e.counters[0] = carry; e.counters[1] = s_active; e.counters[2] = s_errors; }
+  if (t == 0) { e.counters[0] = carry; e.counters[1] = s_active; e.counters[2] = s_errors; e.counters[3] = s_roots; }
 }
 
 // Encoded planes of every queued leaf, float32 NCHW exactly as get_encoded_state()
@@ -546,7 +549,7 @@ azg_advance_kernel(azg_dev e, const int32_t* __restrict__ actions, int gc, int32
   const int won = wpos_winner(root, e.rule);
   const bool over = won != 0 || !wpos_any_empty(root);
   if (status && l == 0) status[g] = (ok ? 0 : 8) | (over ? 4 : 0) | won;
-  if (!gc || a < 0 || !ok) return;
+  if (!gc || !ok) return;
 
   const int n_nodes = ctl->n_nodes;
   int n_free = 0, n_live = 0, p64_used = 0;
@@ -617,4 +620,23 @@ azg_reset_kernel(azg_dev e, const int32_t* __restrict__ mask, const azg_pos* __r
       ctl->root_node = -1; ctl->state = AZG_ST_IDLE; ctl->err = 0;
     }
   }
+}
+
+// Aggregate counters over all games (single block).
+extern "C" __global__ void __launch_bounds__(256) azg_stats_kernel(azg_dev e, unsigned long long* out) {
+  __shared__ unsigned long long acc[8];
+  if (threadIdx.x < 8) acc[threadIdx.x] = 0ULL;
+  __syncthreads();
+  for (int g = threadIdx.x; g < e.G; g += blockDim.x) {
+    const azg_ctl* c = e.ctl + g;
+    atomicAdd(&acc[0], c->sims);
+    atomicAdd(&acc[1], c->visits);
+    atomicAdd(&acc[2], c->evals);
+    atomicAdd(&acc[3], (unsigned long long)c->n_live);
+    atomicMax(&acc[4], (unsigned long long)c->n_nodes);
+    if (c->state == AZG_ST_ERROR || c->err) atomicAdd(&acc[5], 1ULL);
+    atomicOr(&acc[6], (unsigned long long)c->err);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) out[threadIdx.x] = acc[threadIdx.x];
 }

@@ -1,0 +1,161 @@
+"""Drop-in ``PyTorchModel`` / ``AlphaZeroNet`` whose inference runs in the sm_100a CUDA library.
+
+Mirrors network.py of the reference (network.py:29-73 module layout and initialisation,
+:132-264 wrapper): the ``state_dict`` keys, constructor arguments, ``predict`` /
+``predict_batch`` / ``train_batch`` / ``save`` / ``load`` signatures and the checkpoint
+dictionary (``net``, ``opt``, ``board_size``, ``action_size``) are the same, so reference
+snapshots load here and vice versa.
+
+``predict`` (the search's leaf evaluator, network.py:168-183) is the hot path: it goes
+through ``azg_net_forward`` - folded BatchNorm, bf16 tensor-core trunk, fused heads - and
+raises if the CUDA library or a B200 is missing (no eager PyTorch fallback).
+``train_batch`` keeps the reference's loss and optimiser definitions and uses torch
+autograd on the same parameters (SURVEY 8f "next" row).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+class ResidualBlock(nn.Module):
+    """Two 3x3 conv + BN with a skip connection (network.py:9-26)."""
+
+    def __init__(self, channels: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(channels, channels, kernel_size=3, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(channels)
+        self.conv2 = nn.Conv2d(channels, channels, kernel_size=3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(channels)
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)))
+        y = self.bn2(self.conv2(y))
+        return F.relu(y + x)
+
+
+class AlphaZeroNet(nn.Module):
+    """Parameter container with the reference's module names, creation order and
+    initialisation (network.py:41-83), so the same seed yields the same weights and
+    checkpoints are interchangeable.  ``forward`` is the autograd path used for training."""
+
+    def __init__(self, in_channels: int = 3, board_size: int = 15, action_size: int = 15 * 15,
+                 n_res_blocks: int = 6, channels: int = 128):
+        super().__init__()
+        self.board_size, self.action_size, self.channels = board_size, action_size, channels
+        self.conv = nn.Conv2d(in_channels, channels, kernel_size=3, padding=1, bias=False)
+        self.bn = nn.BatchNorm2d(channels)
+        self.res_blocks = nn.ModuleList([ResidualBlock(channels) for _ in range(n_res_blocks)])
+        self.policy_conv = nn.Conv2d(channels, 2, kernel_size=1, bias=False)
+        self.policy_bn = nn.BatchNorm2d(2)
+        self.policy_fc = nn.Linear(2 * board_size * board_size, action_size)
+        self.value_conv = nn.Conv2d(channels, 1, kernel_size=1, bias=False)
+        self.value_bn = nn.BatchNorm2d(1)
+        self.value_fc1 = nn.Linear(board_size * board_size, 64)
+        self.value_fc2 = nn.Linear(64, 1)
+        for m in self.modules():                       # network.py:75-83
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, nonlinearity="relu")
+            elif isinstance(m, nn.Linear):
+                nn.init.kaiming_uniform_(m.weight, nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        h = F.relu(self.bn(self.conv(x)))
+        for blk in self.res_blocks:
+            h = blk(h)
+        p = F.relu(self.policy_bn(self.policy_conv(h)))
+        logits = self.policy_fc(p.view(p.shape[0], -1))
+        v = F.relu(self.value_bn(self.value_conv(h)))
+        v = F.relu(self.value_fc1(v.view(v.shape[0], -1)))
+        return logits, torch.tanh(self.value_fc2(v))
+
+
+class PyTorchModel:
+    def __init__(self, board_size: int = 15, action_size: Optional[int] = None, device: Optional[str] = None,
+                 n_res_blocks: int = 3, channels: int = 64, lr: float = 1e-3, weight_decay: float = 1e-4):
+        if board_size != 15:
+            raise ValueError("azgomoku_b200 kernels are specialised for the 15x15 board")
+        self.board_size = board_size
+        self.action_size = action_size if action_size is not None else board_size * board_size
+        self.device = device or "cuda"
+        if not str(self.device).startswith("cuda") or not torch.cuda.is_available():
+            raise _lib.AzgError("PyTorchModel needs a CUDA device: azgomoku_b200 has no CPU fallback")
+        self.net = AlphaZeroNet(3, board_size, self.action_size, n_res_blocks, channels).to(self.device)
+        self.optimizer = torch.optim.Adam(self.net.parameters(), lr=lr, weight_decay=weight_decay)
+        self.value_loss_fn = nn.MSELoss()
+        self.policy_loss_fn = nn.KLDivLoss(reduction="batchmean")
+        self._engine = None
+        self._packed_version = None
+
+    # ------------------------------------------------------------------ CUDA inference engine
+    def _ensure_engine(self):
+        from .nn_engine import NetEngine
+        if self._engine is None:
+            self._engine = NetEngine(len(self.net.res_blocks), self.net.channels, torch.device(self.device))
+        version = tuple(p._version for p in self.net.parameters()) + tuple(b._version for b in self.net.buffers())
+        if version != self._packed_version:
+            self._engine.load_state_dict(self.net.state_dict())
+            self._packed_version = version
+        return self._engine
+
+    def predict_device(self, planes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """planes float32[B,3,15,15] on the device -> (probs f32[B,225], values f32[B,1]) on the device."""
+        return self._ensure_engine().forward(planes)
+
+    def predict(self, encoded_states: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """network.py:168-183: eval-mode forward + softmax over all 225 logits, numpy in / numpy out."""
+        x = torch.from_numpy(np.ascontiguousarray(encoded_states, dtype=np.float32)).to(self.device)
+        probs, values = self.predict_device(x)
+        return probs.cpu().numpy(), values.cpu().numpy()
+
+    def predict_batch(self, states_list: list) -> Tuple[np.ndarray, np.ndarray]:
+        return self.predict(self.make_batch_from_states(states_list))
+
+    # ------------------------------------------------------------------ training step (network.py:199-235)
+    def train_batch(self, states: np.ndarray, target_pis: np.ndarray, target_vs: np.ndarray, epochs: int = 1) -> dict:
+        self.net.train()
+        to = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.asarray(a, dtype=np.float32))).to(self.device, torch.float32)
+        states_t, pis_t, vs_t = to(states), to(target_pis), to(target_vs)
+        tp = tv = tl = 0.0
+        for _ in range(epochs):
+            self.optimizer.zero_grad()
+            logits, values = self.net(states_t)
+            policy_loss = self.policy_loss_fn(F.log_softmax(logits, dim=1), pis_t)
+            value_loss = self.value_loss_fn(values, vs_t)
+            loss = policy_loss + value_loss
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(self.net.parameters(), 3.0)
+            self.optimizer.step()
+            tp += float(policy_loss.item()); tv += float(value_loss.item()); tl += float(loss.item())
+        ne = float(epochs)
+        return {"policy_loss": tp / ne, "value_loss": tv / ne, "total_loss": tl / ne}
+
+    # ------------------------------------------------------------------ checkpoints (network.py:240-258)
+    def save(self, path: str) -> None:
+        d = os.path.dirname(path)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        torch.save({"net": self.net.state_dict(), "opt": self.optimizer.state_dict(),
+                    "board_size": self.board_size, "action_size": self.action_size}, path)
+
+    def load(self, path: str, map_location: Optional[str] = None) -> None:
+        state = torch.load(path, map_location=map_location or self.device)
+        self.net.load_state_dict(state["net"])
+        if state.get("opt") is not None:
+            try:
+                self.optimizer.load_state_dict(state["opt"])
+            except Exception:
+                pass
+
+    @staticmethod
+    def make_batch_from_states(list_of_encoded_states: list) -> np.ndarray:
+        return np.stack(list_of_encoded_states, axis=0).astype(np.float32)

@@ -1,0 +1,140 @@
+/* azgomoku_b200 - C ABI of the B200-native AlphaZero Gomoku/Pente self-play engine.
+ *
+ * This is the drop-in boundary for the hot path of shirongcan/AlphaZero-Gomoku.
+ * The reference is pure Python and has no FFI of its own; each entry point below
+ * names the reference interface (file:line under the reference tree) whose work
+ * it replaces.  INTEGRATION.md shows the ctypes stubs a maintainer of the
+ * reference would add.
+ *
+ * Conventions: every function returns 0 on success and a negative code on error
+ * (azg_last_error() gives the text, per host thread); all `*_dev` / unmarked data
+ * pointers are DEVICE memory owned by the caller unless the name ends in `_host`;
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream); no hidden
+ * global state; one host thread per engine.  There is no CPU fallback: every call
+ * fails with AZG_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef AZGOMOKU_B200_H
+#define AZGOMOKU_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZG_ABI_VERSION 1
+#define AZG_BOARD 15
+#define AZG_ACTIONS 225
+
+enum { AZG_OK = 0, AZG_E_ARG = -1, AZG_E_CUDA = -2, AZG_E_NOMEM = -3, AZG_E_STATE = -4, AZG_E_SEARCH = -5 };
+enum { AZG_RULE_GOMOKU = 0, AZG_RULE_PENTE = 1 };
+
+/* Packed position, 96 bytes.  Bit (a & 31) of stones[c][a >> 5] is cell a = r*15+c of
+ * colour c+1.  Mirrors the state of games/gomoku.py:20-25 and games/pente.py:12-23:
+ * board, current_player, last_move (-1 == None), captures, len(move_history). */
+typedef struct azg_pos {
+  uint32_t stones[2][8];
+  int32_t player;
+  int32_t last;
+  int32_t caps[2];
+  int32_t plies;
+  int32_t pad[3];
+} azg_pos;
+
+const char* azg_last_error(void);
+int azg_abi_version(void);
+/* Number of usable sm_100 devices (0 when none: every other call then fails). */
+int azg_device_count(void);
+
+/* ------------------------------------------------------------------ rules (batched, n positions)
+ * status bits written by azg_rules_play / azg_rules_status:
+ *   bits 0-1 winner (0/1/2), bit 2 game over, bit 3 move rejected (off board / occupied). */
+#define AZG_STATUS_WINNER(s) ((s) & 3)
+#define AZG_STATUS_OVER(s) (((s) >> 2) & 1)
+#define AZG_STATUS_REJECTED(s) (((s) >> 3) & 1)
+
+/* boards int8[n][225] (0/1/2) + scalars -> packed positions.  lasts/caps/plies may be NULL. */
+int azg_rules_pack(const int8_t* boards, const int32_t* players, const int32_t* lasts, const int32_t* caps,
+                   const int32_t* plies, azg_pos* out, int n, void* stream);
+/* packed -> boards int8[n][225]; players/lasts/caps/plies outputs may be NULL. */
+int azg_rules_unpack(const azg_pos* pos, int8_t* boards, int32_t* players, int32_t* lasts, int32_t* caps,
+                     int32_t* plies, int n, void* stream);
+/* Gomoku.do_move / Pente.do_move + _handle_captures (games/gomoku.py:60-78,
+ * games/pente.py:57-79,114-152), then check_winner / is_game_over
+ * (gomoku.py:155-197, pente.py:199-236).  actions[i] = r*15+c, or any value outside
+ * 0..224 for an off-board move; rejected moves leave the position unchanged. */
+int azg_rules_play(int rule, azg_pos* pos, const int32_t* actions, int32_t* status, int n, void* stream);
+int azg_rules_status(int rule, const azg_pos* pos, int32_t* status, int n, void* stream);
+/* get_valid_moves (gomoku.py:109-121): float32[n][225]. */
+int azg_rules_legal(const azg_pos* pos, float* mask, int n, void* stream);
+/* get_encoded_state (gomoku.py:130-150): float32[n][3][15][15]. */
+int azg_rules_encode(const azg_pos* pos, float* planes, int n, void* stream);
+/* Host-buffer form of azg_rules_play used by the Python game shims: boards int8[n][225],
+ * players/lasts/caps[n][2]/plies are updated in place; status_host receives the bits. */
+int azg_rules_play_host(int rule, int device, int8_t* boards_host, int32_t* players_host, int32_t* lasts_host,
+                        int32_t* caps_host, int32_t* plies_host, const int32_t* actions_host,
+                        int32_t* status_host, int n);
+
+/* ------------------------------------------------------------------ search engine
+ * One engine = G concurrent games of one rule on one device, each with its own
+ * HBM-resident tree slab.  Replaces MCTS.__init__/run/search/_predict_batch/clear_tree
+ * (mcts/new_mcts_alpha.py:12-37, 58-72, 77-185) for G games at once. */
+typedef struct azg_engine azg_engine;
+
+typedef struct azg_config {
+  int32_t device;          /* CUDA ordinal */
+  int32_t rule;            /* AZG_RULE_* (game_class) */
+  int32_t n_games;         /* G */
+  int32_t queue_len;       /* reference batch_size, 1..64 (default 32) */
+  int32_t node_capacity;   /* nodes per game slab */
+  int32_t noise_on;        /* add_dirichlet_noise */
+  int32_t noise_plies;     /* apply_dirichlet_n_first_moves */
+  int32_t reserved;
+  double cpuct;            /* cpuct */
+  double alpha;            /* dirichlet_alpha */
+  double eps;              /* epsilon */
+  uint64_t seed;           /* Philox key for on-device noise / sampling */
+} azg_config;
+
+int azg_create(const azg_config* cfg, azg_engine** out);
+int azg_destroy(azg_engine* e);
+int azg_set_stream(azg_engine* e, void* stream);
+/* Bytes of device memory held by the engine. */
+int64_t azg_memory_bytes(const azg_engine* e);
+
+/* Load root positions (roots[g] for every g with mask[g] != 0; mask NULL = all) and, when
+ * clear_tree != 0, forget those games' trees (MCTS.clear_tree, new_mcts_alpha.py:58-72). */
+int azg_set_roots(azg_engine* e, const azg_pos* roots, const int32_t* mask, int clear_tree);
+int azg_get_roots(azg_engine* e, azg_pos* roots_out);
+
+/* MCTS.run, first half (new_mcts_alpha.py:77-83): fix the root keys and the budget.
+ * plies[g] is the reference's move_number (NULL = the root's own ply count). */
+int azg_search_begin(azg_engine* e, const int32_t* plies, int n_sims);
+/* Run simulations on every game until its leaf queue is full or its budget is spent
+ * (MCTS.search, new_mcts_alpha.py:102-151), then assemble the leaf batch.
+ * The outputs (each may be NULL) receive the batch size, the number of games that need
+ * another fill after this batch is committed, and the number of games whose root is
+ * in the batch (the only case in which the reference draws Dirichlet noise,
+ * new_mcts_alpha.py:171); passing all NULL skips the host synchronisation. */
+int azg_search_fill(azg_engine* e, int32_t* n_leaves_host, int32_t* n_active_host, int32_t* n_roots_host);
+/* Device address of int32 {n_leaves, n_active, n_errors, n_roots, ...} for on-device consumers. */
+const int32_t* azg_search_counters(const azg_engine* e);
+/* Encoded planes of the current leaf batch, float32[n_leaves][3][15][15] - what the
+ * reference stacks into X at new_mcts_alpha.py:160. */
+int azg_search_leaf_planes(azg_engine* e, float* planes);
+/* MCTS._predict_batch after the network call (new_mcts_alpha.py:163-185): probs is the
+ * unmasked softmax float32[n_leaves][225] in leaf order.  noise (may be NULL) is
+ * float64[G][225]: the Dirichlet draw used if game g's root is in its queue. */
+int azg_search_commit(azg_engine* e, const float* probs, const double* noise);
+/* MCTS.run, second half (new_mcts_alpha.py:88-97): pi float32[G][225] and the raw root
+ * visit counts int32[G][225] (either may be NULL). */
+int azg_search_result(azg_engine* e, float* pi, int32_t* visits);
+/* Play actions[g] (>= 0) on game g's root, report azg_rules status bits, and with
+ * gc != 0 reclaim tree nodes that can no longer be reached (DESIGN.md "tree memory"). */
+int azg_search_advance(azg_engine* e, const int32_t* actions, int gc, int32_t* status);
+/* out_host[0..7] = completed sims, node visits, leaf evaluations, live nodes (sum),
+ * high-water nodes (max over games), games in error, OR of error bits, reserved. */
+int azg_search_stats(azg_engine* e, uint64_t* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,142 @@
+"""GPU: the tree kernels reproduce the reference's visit counts exactly.
+
+Priors are injected through the reference's own ``nn_model`` protocol (oracle/fakes.py);
+expected N[root] / pi / evaluation counts come from tests/golden/search_visits.npz, which
+oracle/make_golden.py produced by running the UNMODIFIED reference MCTS."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import fakes, rules as orules
+from oracle.search import Search
+
+pytestmark = pytest.mark.gpu
+
+
+class _Game:
+    """Reference-style game object built from an oracle position (duck typing)."""
+
+    def __init__(self, pos):
+        self.size = 15
+        self.board = pos.cells.reshape(15, 15).copy()
+        self.current_player = pos.player
+        self.last_move = None if pos.last < 0 else divmod(pos.last, 15)
+        self.move_history = [None] * pos.plies
+        if pos.rule == orules.PENTE:
+            self.captures = {1: pos.caps[0], 2: pos.caps[1]}
+
+
+class Gomoku:      # names the MCTS shim maps to rule ids (game_class argument)
+    pass
+
+
+class Pente:
+    pass
+
+
+def cases():
+    z = load_golden("search_visits.npz")
+    return [str(n) for n in z["names"]]
+
+
+@pytest.mark.parametrize("name", cases())
+def test_visit_counts_match_reference(name):
+    import alphazero_gomoku_b200 as m
+    z = load_golden("search_visits.npz")
+    rule, n_sims, q, _ = (int(x) for x in z[f"{name}/cfg"])
+    model = fakes.BY_NAME[str(z[f"{name}/model"][0])]()
+    mcts = m.MCTS(Pente if rule else Gomoku, n_sims, model, cpuct=float(z[f"{name}/cpuct"][0]), batch_size=q,
+                  add_dirichlet_noise=False)
+    pos = orules.Position(rule)
+    for a in z[f"{name}/opening"]:
+        assert orules.play(pos, int(a))
+    for i in range(len(z[f"{name}/moves"])):
+        pi = mcts.run(_Game(pos), pos.plies)
+        assert pi.dtype == np.float32
+        assert np.array_equal(mcts.last_visits, z[f"{name}/N"][i]), (name, i, int(np.abs(mcts.last_visits - z[f'{name}/N'][i]).sum()))
+        assert np.array_equal(pi, z[f"{name}/pi"][i]), (name, i)
+        assert (model.rows, model.calls) == tuple(z[f"{name}/evals"][i]), (name, i)
+        a = int(np.argmax(pi))
+        assert a == z[f"{name}/moves"][i]
+        orules.play(pos, a)
+    mcts.engine.close()
+
+
+def test_survey_known_answers():
+    import alphazero_gomoku_b200 as m
+    for n, (tot, sha, evals) in {100: (69, "7bbbd774cfe75043", 103), 400: (369, "7c21360da2a20891", 412),
+                                 800: (769, "06859f65f08731e8", 825)}.items():
+        model = fakes.Uniform()
+        mcts = m.MCTS(Gomoku, n, model, add_dirichlet_noise=False)
+        mcts.run(_Game(orules.Position(0)), 0)
+        assert int(mcts.last_visits.sum()) == tot and model.rows == evals
+        assert hashlib.sha256(mcts.last_visits.astype(np.int32).tobytes()).hexdigest()[:16] == sha
+        mcts.engine.close()
+
+
+@pytest.mark.parametrize("tag,rule", [("g", 0), ("p", 1)])
+def test_noised_root_float64_path(tag, rule):
+    """Dirichlet noise injected from the golden draws: float64 priors and PUCT at that root."""
+    import alphazero_gomoku_b200 as m
+    z = load_golden("search_noise.npz")
+    draws = list(z[f"{tag}/draws"])
+    mcts = m.MCTS(Pente if rule else Gomoku, 300, fakes.Hashed(), cpuct=1.0, batch_size=32, dirichlet_alpha=0.05,
+                  epsilon=0.25, apply_dirichlet_n_first_moves=10, add_dirichlet_noise=True)
+    orig = np.random.dirichlet
+    np.random.dirichlet = lambda a: draws.pop(0)
+    try:
+        pos = orules.Position(rule)
+        for i in range(len(z[f"{tag}/moves"])):
+            pi = mcts.run(_Game(pos), pos.plies)
+            assert np.array_equal(mcts.last_visits, z[f"{tag}/N"][i]), (tag, i)
+            assert np.array_equal(pi, z[f"{tag}/pi"][i])
+            orules.play(pos, int(np.argmax(pi)))
+    finally:
+        np.random.dirichlet = orig
+    assert len(draws) == 0, "noise must be drawn exactly as often as the reference draws it"
+    mcts.engine.close()
+
+
+@pytest.mark.parametrize("rule", [0, 1])
+def test_many_games_vs_oracle(rule):
+    """64 concurrent games with different openings in ONE engine, against the oracle search
+    run game by game (sharing nothing): lock-step batching must not change any count."""
+    import alphazero_gomoku_b200 as m
+    G, n_sims = 64, 150
+    rng = np.random.default_rng(7 + rule)
+    eng = m.SearchEngine(rule, G, cpuct=1.3, queue_len=32, node_capacity=4096)
+    starts = []
+    for g in range(G):
+        p = orules.Position(rule)
+        for _ in range(int(rng.integers(0, 30))):
+            e = np.flatnonzero(p.cells == 0)
+            orules.play(p, int(e[int(rng.integers(0, len(e)))]))
+            if orules.game_over(p):
+                p = orules.Position(rule)
+        starts.append(p)
+    pos = eng.rules.pack(np.stack([p.cells for p in starts]), [p.player for p in starts], [p.last for p in starts],
+                         [p.caps for p in starts], [p.plies for p in starts])
+    eng.set_roots(pos)
+    model = fakes.Hashed()
+    ev = lambda planes: torch.from_numpy(model.predict(planes.cpu().numpy())[0]).cuda()
+    searches = [Search(rule, n_sims, fakes.Hashed(), cpuct=1.3, queue_len=32, noise=False) for _ in range(G)]
+    for move in range(3):
+        pi, visits = eng.run(n_sims, ev)
+        pi, visits = pi.cpu().numpy(), visits.cpu().numpy()
+        acts = np.zeros(G, np.int32)
+        for g in range(G):
+            want = searches[g].run(starts[g], starts[g].plies)
+            assert np.array_equal(visits[g], searches[g].Nv[starts[g].key()].astype(np.int32)), (g, move)
+            assert np.array_equal(pi[g], want)
+            acts[g] = int(np.argmax(want))
+            orules.play(starts[g], int(acts[g]))
+        st = eng.advance(torch.from_numpy(acts).cuda(), gc=True).cpu().numpy()
+        if any(orules.game_over(p) for p in starts):
+            break
+        assert not (st & 8).any()
+    s = eng.stats()
+    assert s["games_in_error"] == 0 and s["sims"] >= G * n_sims
+    eng.close()

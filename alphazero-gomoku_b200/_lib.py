@@ -30,6 +30,18 @@ class azg_config(C.Structure):
                 ("seed", C.c_uint64)]
 
 
+MAX_LAYERS = 80
+
+
+class azg_net_weights(C.Structure):
+    _fields_ = [("conv_w", C.c_void_p), ("bn", C.c_void_p * 4),
+                ("res_conv_w", C.c_void_p * MAX_LAYERS), ("res_bn", (C.c_void_p * 4) * MAX_LAYERS),
+                ("policy_conv_w", C.c_void_p), ("policy_bn", C.c_void_p * 4), ("policy_fc_w", C.c_void_p),
+                ("policy_fc_b", C.c_void_p), ("value_conv_w", C.c_void_p), ("value_bn", C.c_void_p * 4),
+                ("value_fc1_w", C.c_void_p), ("value_fc1_b", C.c_void_p), ("value_fc2_w", C.c_void_p),
+                ("value_fc2_b", C.c_void_p)]
+
+
 assert C.sizeof(azg_pos) == 96
 
 _P = C.c_void_p
@@ -60,6 +72,14 @@ PROTOTYPES = {
     "azg_search_result": (_I, [_P, _P, _P]),
     "azg_search_advance": (_I, [_P, _P, _I, _P]),
     "azg_search_stats": (_I, [_P, _P]),
+    "azg_net_create": (_I, [_I, _I, _I, _I, C.POINTER(_P)]),
+    "azg_net_destroy": (_I, [_P]),
+    "azg_net_memory_bytes": (C.c_int64, [_P]),
+    "azg_net_load": (_I, [_P, C.POINTER(azg_net_weights), _P]),
+    "azg_net_forward_planes": (_I, [_P, _P, _I, _P, _P, _P, _P]),
+    "azg_net_forward_leaves": (_I, [_P, _P, _P, _P]),
+    "azg_net_trunk_debug": (_I, [_P, _P, _I, _I, _P, _P]),
+    "azg_net_check": (_I, [_P, _P]),
 }
 
 

@@ -1,0 +1,65 @@
+// Leaf-evaluation network: shared declarations of the CUDA translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "host.h"
+
+#define AZG_NET_FRONT 32          // zero rows in front of the first board of an activation buffer
+#define AZG_NET_BACK 32           // zero rows behind the last board
+#define AZG_NET_MAX_BLOCKS 40
+#define AZG_HIDDEN_TILE (676 * 32)   // floats per 32-board tile of head features
+
+struct ConvArgs {
+  const int* n_boards;            // device: positions in this batch
+  int max_boards;                 // capacity of the activation buffers
+  int layer;                      // index into the packed 3x3 weights (tap-major blocks of C x C)
+  int relu;
+  const float* scale;             // [C] folded BatchNorm scale of this layer
+  const float* shift;             // [C]
+  const __nv_bfloat16* residual;  // padded activation buffer added before the ReLU, or null
+  __nv_bfloat16* out;             // padded activation buffer
+  int* error;                     // device flag set by the pipeline watchdogs
+};
+
+int azg_conv3x3_launch(int C, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm,
+                       cudaStream_t stream);
+
+// net_aux.cu
+struct StemArgs {
+  const int* n_boards; int max_boards;
+  const uint32_t* keys;           // leaf stones: [n][16] words (player-1 words 0-7, player-2 words 8-15) ...
+  const uint32_t* meta;           // ... and the side to move in bits 1-2 of meta (tree node layout), or
+  const int32_t* leaf_game;       // leaf -> (game, node) indirection into the engine slabs (null: keys are dense [n][16], meta [n])
+  const int32_t* leaf_node;
+  long long slab_stride;          // nodes per game in the slab
+  const float* w;                 // [27][C] folded stem weights (tap-major, plane, then channel)
+  const float* shift;             // [C]
+  __nv_bfloat16* out;
+};
+int azg_stem_launch(int C, const StemArgs& a, int n_sm, cudaStream_t stream);
+int azg_planes_to_keys_launch(const float* planes, int n, uint32_t* keys, uint32_t* meta, cudaStream_t stream);
+
+struct HeadArgs {
+  const int* n_boards; int max_boards;
+  const __nv_bfloat16* act;       // final trunk activations (padded layout)
+  const float* w1;                // [3][C]: policy conv rows 0-1, value conv row 2 (1x1)
+  const float* scale1;            // [3] folded BN of the two head convs
+  const float* shift1;            // [3]
+  float* hidden;                  // [max_boards][676]: 450 policy features (ch*225+pixel) then 225 value features
+  const float* pol_wt;            // [450][225] policy_fc.weight transposed
+  const float* pol_b;             // [225]
+  const float* v1_wt;             // [225][64] value_fc1.weight transposed
+  const float* v1_b;              // [64]
+  const float* v2_w;              // [64]
+  const float* v2_b;              // [1]
+  float* probs;                   // [n][225]
+  float* values;                  // [n] (may be null)
+  float* logits;                  // [n][225] optional raw logits (may be null)
+};
+int azg_heads_launch(int C, const HeadArgs& a, int n_sm, cudaStream_t stream);
+
+struct PackArgs {
+  int C, n_blocks;
+};

@@ -1,0 +1,226 @@
+// 3x3 convolution + folded BatchNorm (+ residual) + ReLU as a tcgen05 implicit GEMM (sm_100a).
+//
+// Replaces the trunk of AlphaZeroNet.forward (network.py:94-99, ResidualBlock network.py:17-26)
+// - 99.75 % of the network's FLOPs - for a batch of leaf positions.
+//
+// Data layout (DESIGN.md "leaf evaluation"): activations are bf16 channels-last in a PADDED
+// flat pixel space: every board owns 256 consecutive rows of C channels, row qi = y*16 + x with
+// y = 0 a zero row above the board, x = 15 a zero column; pixel (r, c) lives at (r+1)*16 + c.
+// A 3x3 tap (dr, dc) is then the constant row offset dr*16 + dc, halo reads hit zero rows, and
+// one board is exactly one M = 256 tile of a CTA pair (two M = 128 halves).
+//
+// Kernel shape: persistent, one 2-CTA cluster per SM pair (cta_group::2, UMMA 256 x C x 16).
+//   * the layer's weights (9 taps x C x C bf16) stay RESIDENT in shared memory, split by output
+//     channel across the pair (C = 128: 144 KB per CTA) - no weight traffic per tile;
+//   * activations arrive by TMA as three column-shifted copies (dc = -1, 0, +1) of 160 rows per
+//     64-channel slice; the three row taps (dr) of a copy are 2 KB-aligned offsets of the same
+//     shared-memory tile, so each activation byte is fetched 3x from L2 instead of 9x;
+//   * accumulators live in TMEM (2 x C columns, double buffered) so the epilogue of board i
+//     overlaps the MMAs of board i+1;
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator,
+//     warps 2-5 epilogue (TMEM -> registers -> scale/shift (+residual) -> ReLU -> bf16 -> HBM).
+#include <cuda_bf16.h>
+#include "net.h"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int kStages = 3;
+constexpr int kCopyRows = 160;                 // 128 tile rows + 16 above + 16 below
+constexpr int kStageBytes = kCopyRows * 128;   // one 64-channel slice of one shifted copy
+constexpr int kThreads = 192;
+
+template <int C>
+struct Cfg {
+  static constexpr int KC = C / 64;                       // 64-channel K slices
+  static constexpr int BBLK = (C / 2) * 128;              // one (tap, slice) weight block: C/2 rows x 128 B
+  static constexpr int BBYTES = 9 * KC * BBLK;            // resident weights per CTA
+  static constexpr int TMEM_COLS = 2 * C;                 // two accumulators
+  static constexpr int SMEM = 1024 + BBYTES + kStages * kStageBytes + 256 + 2 * C * 4;
+};
+
+enum { ERR_BFULL = 1, ERR_EMPTY = 2, ERR_FULL = 3, ERR_TEMPTY = 4, ERR_TFULL = 5 };
+
+template <int C>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w, ConvArgs p) {
+  using K = Cfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + K::BBYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kStages * kStageBytes);
+  uint64_t* full = bars;                // [kStages]  leader: both CTAs' copies landed
+  uint64_t* empty = bars + kStages;     // [kStages]  each CTA: MMAs reading the stage retired
+  uint64_t* tfull = bars + 2 * kStages; // [2]        each CTA: accumulator complete
+  uint64_t* tempty = tfull + 2;         // [2]        leader: both epilogues drained the accumulator
+  uint64_t* bfull = tempty + 2;         // leader: both weight halves resident
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  float* s_scale = reinterpret_cast<float*>(bars + 32);
+  float* s_shift = s_scale + C;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int cid = (int)ptx::cluster_id_x(), ncl = (int)ptx::ncluster_x();
+  int n_boards = *p.n_boards;
+  if (n_boards > p.max_boards) n_boards = p.max_boards;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_act);
+    ptx::prefetch_tmap(&tm_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+      for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 8); }
+      ptx::mbar_init(bfull, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<2>(tmem_slot, K::TMEM_COLS);
+    ptx::tmem_relinquish<2>();
+  }
+  for (int i = threadIdx.x; i < C; i += kThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer (both CTAs) ==============================
+    if (lane == 0) {
+      if (rank == 0) ptx::mbar_arrive_expect_tx(bfull, 2u * K::BBYTES);
+      for (int blk = 0; blk < 9 * K::KC; ++blk) {
+        const int tap = blk / K::KC, kc = blk % K::KC;
+        ptx::tma_load_2d_pair(sB + blk * K::BBLK, &tm_w, bfull, kc * 64, (p.layer * 9 + tap) * C + (int)rank * (C / 2));
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int b = cid; b < n_boards && ok; b += ncl) {
+        const int row0 = AZG_NET_FRONT + (b * 2 + (int)rank) * 128 - 16;
+        for (int kc = 0; kc < K::KC && ok; ++kc)
+          for (int dci = 0; dci < 3; ++dci) {
+            if (!ptx::mbar_wait(&empty[stage], phase ^ 1u)) { atomicExch(p.error, ERR_EMPTY); ok = false; break; }
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2u * kStageBytes);
+            ptx::tma_load_2d_pair(sA + stage * kStageBytes, &tm_act, &full[stage], kc * 64, row0 + dci - 1);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer (leader CTA, one thread) ==============================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16(256, C);
+      const uint32_t a_base = ptx::smem_u32(sA), b_base = ptx::smem_u32(sB);
+      bool ok = ptx::mbar_wait(bfull, 0);
+      if (!ok) atomicExch(p.error, ERR_BFULL);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
+        const int acc = it & 1;
+        if (!ptx::mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u)) { atomicExch(p.error, ERR_TEMPTY); ok = false; break; }
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C);
+        for (int kc = 0; kc < K::KC && ok; ++kc)
+          for (int dci = 0; dci < 3; ++dci) {
+            if (!ptx::mbar_wait(&full[stage], phase)) { atomicExch(p.error, ERR_FULL); ok = false; break; }
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int dri = 0; dri < 3; ++dri) {
+              const int tap = dri * 3 + dci;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = ptx::smem_desc_sw128(a_base + stage * kStageBytes + dri * 2048 + k * 32);
+                const uint64_t bd = ptx::smem_desc_sw128(b_base + (tap * K::KC + kc) * K::BBLK + k * 32);
+                ptx::umma_bf16<2>(tmem_d, ad, bd, idesc, (kc | dci | dri | k) != 0 ? 1u : 0u);
+              }
+            }
+            ptx::umma_commit_pair(&empty[stage], 3);        // frees the stage in both CTAs
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        if (ok) ptx::umma_commit_pair(&tfull[acc], 3);       // accumulator ready in both CTAs
+      }
+    }
+  } else {
+    // ============================== epilogue (warps 2..5, both CTAs) ==============================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int qi = (int)rank * 128 + row;
+    const bool pad = (qi < 16) || ((qi & 15) == 15);
+    int it = 0;
+    bool ok = true;
+    for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
+      const int acc = it & 1;
+      if (!ptx::mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u)) { atomicExch(p.error, ERR_TFULL); ok = false; break; }
+      ptx::tc_fence_after();
+      const size_t grow = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)qi;
+      __nv_bfloat16* orow = p.out + grow * C;
+      const __nv_bfloat16* rrow = p.residual ? p.residual + grow * C : nullptr;
+#pragma unroll 1
+      for (int ch = 0; ch < C; ch += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * C + ch), v);
+        ptx::tmem_ld_wait();
+        uint4 res[4];
+        if (rrow) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rrow + ch + 8 * j);
+        }
+        uint4 outv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t packed[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int c0 = ch + 8 * j + 2 * h;
+            float y0 = fmaf(__uint_as_float(v[8 * j + 2 * h]), s_scale[c0], s_shift[c0]);
+            float y1 = fmaf(__uint_as_float(v[8 * j + 2 * h + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
+            if (rrow) {
+              const uint32_t rw = (&res[j].x)[h];
+              y0 += __uint_as_float(rw << 16);
+              y1 += __uint_as_float(rw & 0xffff0000u);
+            }
+            if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            if (pad) { y0 = 0.f; y1 = 0.f; }
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
+            packed[h] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
+          outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + ch + 8 * j) = outv[j];
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 1) ptx::tmem_dealloc<2>(tmem_base, K::TMEM_COLS);
+}
+
+template <int C>
+int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm, cudaStream_t stream) {
+  using K = Cfg<C>;
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+  if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
+  int grid = n_sm & ~1;
+  const int want = 2 * args.max_boards;
+  if (grid > want) grid = want < 2 ? 2 : want;
+  conv3x3_pair_kernel<C><<<grid, kThreads, K::SMEM, stream>>>(tm_act, tm_w, args);
+  return azg_check_launch("conv3x3_pair_kernel");
+}
+
+}  // namespace
+
+int azg_conv3x3_launch(int C, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm,
+                       cudaStream_t stream) {
+  if (C == 128) return launch_conv<128>(tm_act, tm_w, args, n_sm, stream);
+  if (C == 64) return launch_conv<64>(tm_act, tm_w, args, n_sm, stream);
+  return azg_fail(AZG_E_ARG, "conv3x3: resident-weight kernel supports 64 or 128 channels");
+}

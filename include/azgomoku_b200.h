@@ -134,6 +134,51 @@ int azg_search_advance(azg_engine* e, const int32_t* actions, int gc, int32_t* s
  * high-water nodes (max over games), games in error, OR of error bits, reserved. */
 int azg_search_stats(azg_engine* e, uint64_t* out_host);
 
+/* ------------------------------------------------------------------ leaf evaluator (policy/value ResNet)
+ * Replaces AlphaZeroNet.forward + PyTorchModel.predict (network.py:85-117, 168-183): stem conv,
+ * n_blocks residual blocks of two 3x3 convs (tcgen05 implicit GEMM, bf16 in / fp32 accumulate,
+ * eval-mode BatchNorm folded into the epilogue), fused policy / value heads. */
+typedef struct azg_net azg_net;
+#define AZG_NET_MAX_LAYERS 80
+
+/* Device pointers to float32 tensors in the reference's state_dict layout (network.py:54-71).
+ * bn arrays are {weight, bias, running_mean, running_var}. */
+typedef struct azg_net_weights {
+  const float* conv_w;                          /* conv.weight [C,3,3,3] */
+  const float* bn[4];                           /* bn.* */
+  const float* res_conv_w[AZG_NET_MAX_LAYERS];  /* res_blocks.i.conv1.weight, res_blocks.i.conv2.weight, ... [C,C,3,3] */
+  const float* res_bn[AZG_NET_MAX_LAYERS][4];   /* res_blocks.i.bn1.*, res_blocks.i.bn2.*, ... */
+  const float* policy_conv_w;                   /* [2,C,1,1] */
+  const float* policy_bn[4];
+  const float* policy_fc_w;                     /* [225,450] */
+  const float* policy_fc_b;                     /* [225] */
+  const float* value_conv_w;                    /* [1,C,1,1] */
+  const float* value_bn[4];
+  const float* value_fc1_w;                     /* [64,225] */
+  const float* value_fc1_b;                     /* [64] */
+  const float* value_fc2_w;                     /* [1,64] */
+  const float* value_fc2_b;                     /* [1] */
+} azg_net_weights;
+
+/* channels: 64 or 128; max_batch: positions per forward pass the activation buffers hold. */
+int azg_net_create(int device, int n_blocks, int channels, int max_batch, azg_net** out);
+int azg_net_destroy(azg_net* n);
+int64_t azg_net_memory_bytes(const azg_net* n);
+/* Repack weights (fold BatchNorm, bf16 tap-major conv weights, transposed FC weights). */
+int azg_net_load(azg_net* n, const azg_net_weights* w, void* stream);
+/* PyTorchModel.predict on device buffers: planes float32[count][3][15][15] ->
+ * probs float32[count][225] (softmax over all 225), values float32[count] (may be NULL),
+ * logits float32[count][225] (may be NULL). */
+int azg_net_forward_planes(azg_net* n, const float* planes, int count, float* probs, float* values, float* logits,
+                           void* stream);
+/* Evaluate the engine's current leaf batch (azg_search_fill) without leaving the device:
+ * probs float32[n_leaves][225] in leaf order, values float32[n_leaves] (may be NULL). */
+int azg_net_forward_leaves(azg_net* n, azg_engine* e, float* probs, float* values);
+/* Test hook: activations after the stem and the first n_layers 3x3 layers, float32[count][C][15][15]. */
+int azg_net_trunk_debug(azg_net* n, const float* planes, int count, int n_layers, float* out, void* stream);
+/* Synchronise and report the tcgen05 pipeline watchdog (0 = healthy). */
+int azg_net_check(azg_net* n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

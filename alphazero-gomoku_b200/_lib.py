@@ -70,8 +70,12 @@ PROTOTYPES = {
     "azg_search_leaf_planes": (_I, [_P, _P]),
     "azg_search_commit": (_I, [_P, _P, _P]),
     "azg_search_result": (_I, [_P, _P, _P]),
-    "azg_search_advance": (_I, [_P, _P, _I, _P]),
+    "azg_search_advance": (_I, [_P, _P, _I, _I, _P]),
     "azg_search_stats": (_I, [_P, _P]),
+    "azg_selfplay_enable": (_I, [_P, _I]),
+    "azg_selfplay_noise": (_I, [_P, C.c_uint64, _P]),
+    "azg_selfplay_choose": (_I, [_P, _P, C.c_float, C.c_uint64, _P]),
+    "azg_selfplay_finish": (_I, [_P, _P, _I, _I, _P, C.c_int64, _P, _P, _P]),
     "azg_net_create": (_I, [_I, _I, _I, _I, C.POINTER(_P)]),
     "azg_net_destroy": (_I, [_P]),
     "azg_net_memory_bytes": (C.c_int64, [_P]),
@@ -79,6 +83,8 @@ PROTOTYPES = {
     "azg_net_forward_planes": (_I, [_P, _P, _I, _P, _P, _P, _P]),
     "azg_net_forward_leaves": (_I, [_P, _P, _P, _P]),
     "azg_net_trunk_debug": (_I, [_P, _P, _I, _I, _P, _P]),
+    "azg_net_profile": (_I, [_P, _I]),
+    "azg_net_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "azg_net_check": (_I, [_P, _P]),
 }
 

@@ -41,7 +41,8 @@ struct azg_ctl {
   int32_t n_live;
   int32_t p64_used;             // bit mask of float64 prior rows in use
   int32_t leaf_off;             // offset of this game's queue in the leaf batch
-  int32_t pad0[2];
+  int32_t resets;               // trees dropped because the slab could not hold another run
+  int32_t pad0;
   unsigned long long visits;    // node visits (search() entries in the reference)
   unsigned long long evals;     // rows sent to the evaluator
   unsigned long long sims;      // completed simulations

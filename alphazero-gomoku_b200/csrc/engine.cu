@@ -115,6 +115,7 @@ extern "C" int azg_destroy(azg_engine* e) {
   cudaFree(d.ctl); cudaFree(d.P); cudaFree(d.Nv); cudaFree(d.W); cudaFree(d.key); cudaFree(d.meta); cudaFree(d.slots);
   cudaFree(d.freelist); cudaFree(d.path); cudaFree(d.P64); cudaFree(d.leaf_game); cudaFree(d.leaf_node);
   cudaFree(d.counters); cudaFree(e->stats_dev);
+  cudaFree(e->sp.ex_key); cudaFree(e->sp.ex_player); cudaFree(e->sp.ex_pi); cudaFree(e->sp.n_plies);
   if (e->pinned) cudaFreeHost(e->pinned);
   delete e;
   return AZG_OK;
@@ -186,9 +187,9 @@ extern "C" int azg_search_result(azg_engine* e, float* pi, int32_t* visits) {
   return azg_check_launch("azg_search_result");
 }
 
-extern "C" int azg_search_advance(azg_engine* e, const int32_t* actions, int gc, int32_t* status) {
+extern "C" int azg_search_advance(azg_engine* e, const int32_t* actions, int gc, int reserve, int32_t* status) {
   if (!e) return azg_fail(AZG_E_ARG, "null engine");
-  azg_advance_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, actions, gc, status);
+  azg_advance_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, actions, gc, reserve, status);
   return azg_check_launch("azg_search_advance");
 }
 

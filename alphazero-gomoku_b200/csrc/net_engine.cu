@@ -27,6 +27,11 @@ struct azg_net {
   int *n_dev = nullptr, *error_dev = nullptr;
   int* pinned = nullptr;
   CUtensorMap tm_act[3], tm_w;
+  // optional timing of the 3x3 trunk (one CUDA-event pair per forward pass, on the launch stream)
+  int profiling = 0;
+  std::vector<cudaEvent_t> ev;          // start/stop pairs
+  size_t ev_used = 0;
+  long long prof_launches = 0;
 };
 
 typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -74,6 +79,7 @@ extern "C" int azg_net_destroy(azg_net* n) {
   for (int i = 0; i < 3; ++i) cudaFree(n->act[i]);
   cudaFree(n->hidden); cudaFree(n->keys); cudaFree(n->meta); cudaFree(n->n_dev); cudaFree(n->error_dev);
   if (n->pinned) cudaFreeHost(n->pinned);
+  for (cudaEvent_t ev : n->ev) cudaEventDestroy(ev);
   delete n;
   return AZG_OK;
 }
@@ -166,6 +172,19 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
   stem.n_boards = n_ptr; stem.max_boards = max_boards; stem.w = n->stem_w; stem.shift = n->stem_shift; stem.out = n->act[0];
   if ((rc = azg_stem_launch(C, stem, n->n_sm, s))) return rc;
   int x = 0, t = 1, y = 2;
+  cudaEvent_t ev_stop = nullptr;
+  if (n->profiling && n_layers > 0) {
+    if (n->ev_used + 2 > n->ev.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) { n->ev.push_back(a); n->ev.push_back(b); }
+    }
+    if (n->ev_used + 2 <= n->ev.size()) {
+      cudaEventRecord(n->ev[n->ev_used], s);
+      ev_stop = n->ev[n->ev_used + 1];
+      n->ev_used += 2;
+      n->prof_launches += n_layers;
+    }
+  }
   for (int l = 0; l < n_layers; ++l) {
     ConvArgs a;
     a.n_boards = n_ptr; a.max_boards = max_boards; a.layer = l; a.relu = 1;
@@ -174,6 +193,7 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
     else { a.residual = n->act[x]; a.out = n->act[y]; rc = azg_conv3x3_launch(C, n->tm_act[t], n->tm_w, a, n->n_sm, s); int tmp = x; x = y; y = tmp; }
     if (rc) return rc;
   }
+  if (ev_stop) cudaEventRecord(ev_stop, s);
   const int last = (n_layers & 1) ? t : x;
   if (out_buf) *out_buf = last;
   if (heads) {
@@ -259,6 +279,31 @@ extern "C" int azg_net_forward_leaves(azg_net* n, azg_engine* e, float* probs, f
   st.keys = e->dev.key; st.meta = e->dev.meta; st.leaf_game = e->dev.leaf_game; st.leaf_node = e->dev.leaf_node;
   st.slab_stride = e->dev.cap;
   return run_network(n, st, e->dev.counters, cap, 2 * n->n_blocks, probs, values, nullptr, true, e->stream, nullptr);
+}
+
+// Trunk timing: enable != 0 starts collecting one event pair around the 3x3 layers of every
+// forward pass; azg_net_profile_read synchronises the device, returns the summed milliseconds and
+// the number of conv3x3 launches they cover, and resets the collection.
+extern "C" int azg_net_profile(azg_net* n, int enable) {
+  if (!n) return azg_fail(AZG_E_ARG, "null network");
+  n->profiling = enable ? 1 : 0;
+  return AZG_OK;
+}
+
+extern "C" int azg_net_profile_read(azg_net* n, double* trunk_ms, int64_t* launches) {
+  if (!n || !trunk_ms || !launches) return azg_fail(AZG_E_ARG, "null argument");
+  AZG_CUDA(cudaSetDevice(n->device));
+  AZG_CUDA(cudaDeviceSynchronize());
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < n->ev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, n->ev[i], n->ev[i + 1]) == cudaSuccess) total += ms;
+  }
+  *trunk_ms = total;
+  *launches = n->prof_launches;
+  n->ev_used = 0;
+  n->prof_launches = 0;
+  return AZG_OK;
 }
 
 // Watchdog status of the tcgen05 pipeline (0 = healthy); synchronises the stream.

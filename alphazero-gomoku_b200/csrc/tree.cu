@@ -533,7 +533,7 @@ azg_finish_kernel(azg_dev e, float* __restrict__ pi, int32_t* __restrict__ visit
 // Everything that survives is re-inserted into a cleared table; freed slots go to the
 // free stack.  gc == 0 keeps every node.
 extern "C" __global__ void __launch_bounds__(128)
-azg_advance_kernel(azg_dev e, const int32_t* __restrict__ actions, int gc, int32_t* __restrict__ status) {
+azg_advance_kernel(azg_dev e, const int32_t* __restrict__ actions, int gc, int reserve, int32_t* __restrict__ status) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= e.G) return;
   const int l = lane_id();
@@ -596,6 +596,15 @@ azg_advance_kernel(azg_dev e, const int32_t* __restrict__ actions, int gc, int32
       ++n_free;
     }
   }
+  // Not enough room for the next run (it can add up to `reserve` nodes): drop the whole tree
+  // rather than fail mid-run.  This loses tree reuse for this game (a deviation from the
+  // reference, which never frees) and is counted in azg_search_stats.
+  if (reserve > 0 && e.cap - n_live < reserve) {
+    for (int i = l; i < e.hcap; i += 32) __stcg(&tab[i], 0ULL);
+    for (int i = l; i < n_nodes; i += 32) e.meta[azg_node_off(e, g, i)] = 0u;
+    if (l == 0) { ctl->n_nodes = 0; ctl->n_free = 0; ctl->n_live = 0; ctl->p64_used = 0; ctl->resets += 1; }
+    return;
+  }
   if (l == 0) { ctl->n_free = n_free; ctl->n_live = n_live; ctl->p64_used = p64_used; }
 }
 
@@ -636,6 +645,7 @@ extern "C" __global__ void __launch_bounds__(256) azg_stats_kernel(azg_dev e, un
     atomicMax(&acc[4], (unsigned long long)c->n_nodes);
     if (c->state == AZG_ST_ERROR || c->err) atomicAdd(&acc[5], 1ULL);
     atomicOr(&acc[6], (unsigned long long)c->err);
+    atomicAdd(&acc[7], (unsigned long long)c->resets);
   }
   __syncthreads();
   if (threadIdx.x < 8) out[threadIdx.x] = acc[threadIdx.x];

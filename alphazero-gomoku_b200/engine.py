@@ -186,18 +186,20 @@ class SearchEngine:
         check(lib.azg_search_result(self._h, ptr(pi), ptr(visits)))
         return pi, visits
 
-    def advance(self, actions: torch.Tensor, gc: bool = True) -> torch.Tensor:
+    def advance(self, actions: torch.Tensor, gc: bool = True, reserve: int = 0) -> torch.Tensor:
+        """Play actions (>= 0) on the roots and sweep dead nodes; ``reserve`` > 0 drops the tree of
+        any game that could not hold another run of that many new nodes."""
         self._sync_stream()
         a = actions.to(self.device, torch.int32).contiguous()
         status = torch.empty(self.G, dtype=torch.int32, device=self.device)
-        check(lib.azg_search_advance(self._h, ptr(a), int(gc), ptr(status)))
+        check(lib.azg_search_advance(self._h, ptr(a), int(gc), int(reserve), ptr(status)))
         return status
 
     def stats(self) -> dict:
         self._sync_stream()
         out = (C.c_uint64 * 8)()
         check(lib.azg_search_stats(self._h, out))
-        keys = ("sims", "visits", "evals", "live_nodes", "max_nodes", "games_in_error", "error_bits")
+        keys = ("sims", "visits", "evals", "live_nodes", "max_nodes", "games_in_error", "error_bits", "dropped_trees")
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     # -- the reference's run() for all games, evaluator supplied by the caller

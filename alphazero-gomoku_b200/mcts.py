@@ -92,7 +92,8 @@ class MCTS:
         pos = eng.rules.pack(board[None, :], [player], [last], [list(caps)], [plies])
         eng.set_roots(pos, clear_tree=False)
         if self.gc and not self._fresh:
-            eng.advance(torch.full((1,), -1, dtype=torch.int32, device=self.device), gc=True)
+            eng.advance(torch.full((1,), -1, dtype=torch.int32, device=self.device), gc=True,
+                        reserve=self.n_simulations + self.n_simulations // max(self.batch_size, 1) + 8)
         self._fresh = False
         eng.begin(self.n_simulations, torch.tensor([int(move_number)], dtype=torch.int32, device=self.device))
         while True:

@@ -86,5 +86,14 @@ class NetEngine:
             check(lib.azg_net_trunk_debug(self._h, ptr(x), x.shape[0], n_layers, ptr(out), _stream()))
         return out
 
+    def profile(self, enable: bool):
+        check(lib.azg_net_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """-> (milliseconds spent in the 3x3 trunk, conv3x3 launches covered) since the last read."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(lib.azg_net_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def check(self):
         check(lib.azg_net_check(self._h, _stream()))

@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched self-play MCTS simulations per second (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): Gomoku 15x15, 2048 concurrent self-play games per GPU,
+800 simulations per move, random-init 6x128 ResNet (torch.manual_seed(0)), cpuct 1.0, leaf queue
+32, Dirichlet alpha 0.05 / eps 0.15 on the first 10 plies, temperature threshold 10.  A "step" is
+one ply of every game: 2048 x 800 simulations, i.e. 26+ rounds of FILL -> leaf evaluation ->
+COMMIT.  Synthetic data: games start from seeded random legal positions of 0..39 plies so that
+the batch is a steady-state mix of game phases; weights are random-init.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA engine)
+    python bench.py --impl reference ...                      # the reference's CPU algorithm (oracle port)
+
+Prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = the same
+metric through host buffers (boards up, pi/actions/boards down every step), roofline = the
+conv3x3 tcgen05 kernel against the measured bf16 peak, cpu_baseline = the oracle port on one core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "self-play MCTS sims/sec (Gomoku 15x15, 6x128 ResNet)"
+UNIT = "sims/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=2048)
+    ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--blocks", type=int, default=6)
+    ap.add_argument("--channels", type=int, default=128)
+    ap.add_argument("--rule", default="gomoku", choices=["gomoku", "pente"])
+    ap.add_argument("--node-capacity", type=int, default=16384)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    return {"workload": f"{args.rule} 15x15 batched self-play, {args.games} concurrent games/GPU x {args.sims} sims/move, "
+                        f"{args.blocks}x{args.channels} ResNet, leaf queue 32",
+            "games_per_gpu": args.games, "sims_per_move": args.sims, "net": f"{args.blocks}x{args.channels}",
+            "rule": args.rule, "cache": "working set (tree slabs + activations, >10 GB) exceeds the 126 MB L2",
+            "parallelism": f"independent games per GPU x{args.gpus}"}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if mx and x > 0.3 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs (oracle)
+def _oracle_model(blocks, channels):
+    import torch
+    from oracle import net as onet
+    import alphazero_gomoku_b200.network as mynet
+    torch.manual_seed(0)
+    return onet.CpuModel(mynet.AlphaZeroNet(n_res_blocks=blocks, channels=channels).state_dict())
+
+
+def _cpu_worker(job):
+    """One process of the reference's parallel mode (train.py:62-129): own model, one torch thread,
+    one MCTS.run of `sims` simulations from the empty board with root noise."""
+    blocks, channels, rule, sims, seed = job
+    import torch
+    torch.set_num_threads(1)
+    from oracle import rules
+    from oracle.search import Search
+    np.random.seed(seed)
+    model = _oracle_model(blocks, channels)
+    s = Search(rule, sims, model, cpuct=1.0, queue_len=32, alpha=0.05, eps=0.15, noise_plies=10, noise=True)
+    t0 = time.perf_counter()
+    s.run(rules.Position(rule), 0)
+    return sims, s.n_evals, time.perf_counter() - t0
+
+
+def cpu_baseline(args, seconds):
+    """Oracle port (numpy tree + fp32 torch-CPU network, one thread) for ~`seconds` of self-play:
+    successive MCTS.run calls of one game with tree reuse, 400 sims per move."""
+    import torch
+    torch.set_num_threads(1)
+    from oracle import rules
+    from oracle.search import Search
+    rule = 1 if args.rule == "pente" else 0
+    np.random.seed(12345)
+    model = _oracle_model(args.blocks, args.channels)
+    s = Search(rule, 400, model, cpuct=1.0, queue_len=32, alpha=0.05, eps=0.15, noise_plies=10, noise=True)
+    pos = rules.Position(rule)
+    sims = moves = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds and not rules.game_over(pos):
+        pi = s.run(pos, pos.plies)
+        rules.play(pos, int(np.argmax(pi)))
+        sims += 400
+        moves += 1
+    dt = time.perf_counter() - t0
+    return {"value": sims / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle port of mcts/new_mcts_alpha.py + network.py, one game, {moves} moves x 400 sims, "
+                      f"{s.n_evals} leaf evals, 1 torch thread, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python and
+    is not present on the GPU box) in the reference's own parallel mode: one process per host core
+    minus one, one torch thread each (train.py:695-742)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    workers = max(1, (os.cpu_count() or 2) - 1)
+    workers = min(workers, 64)
+    rule = 1 if args.rule == "pente" else 0
+    sims = 100
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        for w in range(args.warmup):
+            pool.map(_cpu_worker, [(args.blocks, args.channels, rule, 32, 1000 + i) for i in range(workers)])
+        t0 = time.perf_counter()
+        total = evals = 0
+        for k in range(args.steps):
+            out = pool.map(_cpu_worker, [(args.blocks, args.channels, rule, sims, 12345 + k * workers + i) for i in range(workers)])
+            total += sum(o[0] for o in out)
+            evals += sum(o[1] for o in out)
+        dt = time.perf_counter() - t0
+    value = total / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                             "sample": f"{workers} processes x {args.steps} MCTS.run of {sims} sims from the empty board "
+                                       f"(oracle port, 1 torch thread each), {evals} leaf evals"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU engine
+def scatter_start(sp, rng_seed):
+    """Advance game g by (g mod 40) uniformly random legal plies so the batch mixes game phases."""
+    import torch
+    eng = sp.engine
+    G = sp.G
+    gen = torch.Generator(device=sp.device).manual_seed(rng_seed)
+    pos = eng.roots()
+    target = torch.arange(G, device=sp.device, dtype=torch.int32) % 40
+    for t in range(39):
+        legal = eng.rules.legal(pos)
+        a = torch.multinomial(legal, 1, generator=gen).squeeze(1).to(torch.int32)
+        a = torch.where(target > t, a, torch.full_like(a, -1))
+        before = pos.clone()
+        st = eng.rules.play(pos, a)
+        over = (st & 4) != 0
+        pos = torch.where(over[:, None], before, pos)          # never start from a finished game
+    eng.set_roots(pos, clear_tree=True)
+    return pos
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import alphazero_gomoku_b200 as m
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import SelfPlay, TRUNK_FLOPS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rule = 1 if args.rule == "pente" else 0
+
+    torch.manual_seed(0)
+    model = PyTorchModel(board_size=15, n_res_blocks=args.blocks, channels=args.channels, device=str(dev))
+    sp = SelfPlay(model, rule=rule, n_games=args.games, n_sims=args.sims, cpuct=1.0, queue_len=32,
+                  node_capacity=args.node_capacity, noise=True, alpha=0.05, eps=0.15, noise_plies=10, temp_threshold=10.0,
+                  example_capacity=1 << 18, seed=12345 + rank * args.games, device=str(dev))
+    scatter_start(sp, 777 + rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sp.step()
+        sp.cursor.zero_()
+
+    # ---- timed region A: device-resident self-play
+    clocks = ClockSampler(local)
+    sims0, evals0, launches0, rounds0 = sp.total_sims, sp.total_evals, sp.total_launches, sp.total_rounds
+    sp.net.profile(True)
+    sp.net.profile_read()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sp.step()
+        sp.cursor.zero_()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    trunk_ms, conv_launches = sp.net.profile_read()
+    sp.net.profile(False)
+    sims, evals = sp.total_sims - sims0, sp.total_evals - evals0
+    launches, rounds = sp.total_launches - launches0, sp.total_rounds - rounds0
+    clk = clocks.stop()
+    stats = sp.engine.stats()
+
+    # ---- timed region B: the same step driven through HOST buffers
+    G = args.games
+    h_boards = torch.empty((G, 225), dtype=torch.int8).pin_memory()
+    h_meta = torch.empty((G, 5), dtype=torch.int32).pin_memory()          # player, last, caps0, caps1, plies
+    h_pi = torch.empty((G, 225), dtype=torch.float32).pin_memory()
+    h_act = torch.empty((G, 2), dtype=torch.int32).pin_memory()           # action, status
+    R = sp.engine.rules
+
+    def download():
+        boards, players, lasts, caps, plies = R.unpack(sp.engine.roots())
+        h_boards.copy_(boards, non_blocking=True)
+        h_meta.copy_(torch.stack([players, lasts, caps[:, 0], caps[:, 1], plies], dim=1), non_blocking=True)
+
+    download()
+    torch.cuda.synchronize()
+    h2d = h_boards.numel() + h_meta.numel() * 4
+    d2h = h_pi.numel() * 4 + h_act.numel() * 4 + h2d
+
+    def e2e_step():
+        d_boards = h_boards.to(dev, non_blocking=True)
+        d_meta = h_meta.to(dev, non_blocking=True)
+        pos = R.pack(d_boards, d_meta[:, 0].contiguous(), d_meta[:, 1].contiguous(), d_meta[:, 2:4].contiguous(), d_meta[:, 4].contiguous())
+        sp.engine.set_roots(pos, clear_tree=False)
+        status = sp.step()
+        h_pi.copy_(sp.last_pi, non_blocking=True)
+        h_act.copy_(torch.stack([sp.actions, status], dim=1), non_blocking=True)
+        download()
+        torch.cuda.synchronize()
+        sp.cursor.zero_()
+
+    e2e_step()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms, ms_e2e, float(sims), float(evals)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, ms_e2e = float(mx[0]), float(mx[1])
+        tot_sims, tot_evals = float(sm[2]), float(sm[3])
+    else:
+        tot_sims, tot_evals = float(sims), float(evals)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
+        flops = float(evals) * TRUNK_FLOPS[args.channels] * 2 * args.blocks
+        achieved = flops / (trunk_ms * 1e-3) / 1e12 if trunk_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": tot_sims / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload(args),
+            "leaf_evals_per_s": tot_evals / (ms * 1e-3), "evals_per_sim": tot_evals / max(tot_sims, 1.0),
+            "node_visits_per_sim": stats["visits"] / max(stats["sims"], 1),
+            "e2e": {"value": tot_sims / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_pair_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "launches": int(conv_launches), "avg_launch_ms": trunk_ms / max(conv_launches, 1),
+                         "trunk_share_of_step": trunk_ms / ms if ms else None,
+                         "algorithmic_flops_per_position_per_launch": TRUNK_FLOPS[args.channels]},
+            "clocks": clk,
+            "search": {"rounds": int(rounds), "games_in_error": stats["games_in_error"], "error_bits": stats["error_bits"],
+                       "max_nodes_per_game": stats["max_nodes"], "dropped_trees": stats["dropped_trees"], "engine_gb": sp.engine.memory_bytes / 1e9,
+                       "net_gb": sp.net.memory_bytes / 1e9},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -128,11 +128,32 @@ int azg_search_commit(azg_engine* e, const float* probs, const double* noise);
  * visit counts int32[G][225] (either may be NULL). */
 int azg_search_result(azg_engine* e, float* pi, int32_t* visits);
 /* Play actions[g] (>= 0) on game g's root, report azg_rules status bits, and with
- * gc != 0 reclaim tree nodes that can no longer be reached (DESIGN.md "tree memory"). */
-int azg_search_advance(azg_engine* e, const int32_t* actions, int gc, int32_t* status);
+ * gc != 0 reclaim tree nodes that can no longer be reached (DESIGN.md "tree memory").
+ * reserve > 0: a game whose slab has fewer than `reserve` free nodes after the sweep drops
+ * its whole tree (counted in azg_search_stats) instead of overflowing during the next run. */
+int azg_search_advance(azg_engine* e, const int32_t* actions, int gc, int reserve, int32_t* status);
 /* out_host[0..7] = completed sims, node visits, leaf evaluations, live nodes (sum),
- * high-water nodes (max over games), games in error, OR of error bits, reserved. */
+ * high-water nodes (max over games), games in error, OR of error bits, dropped trees. */
 int azg_search_stats(azg_engine* e, uint64_t* out_host);
+
+/* ------------------------------------------------------------------ self-play driver
+ * play_game_and_collect for G games at once (train.py:360-412) with on-device Philox. */
+/* Allocate example capture for games of up to max_plies moves (train.py max_moves). */
+int azg_selfplay_enable(azg_engine* e, int max_plies);
+/* noise float64[G][225] ~ Dirichlet(alpha) over all 225 actions (new_mcts_alpha.py:172);
+ * `draw` distinguishes successive draws. */
+int azg_selfplay_noise(azg_engine* e, uint64_t draw, double* noise);
+/* sample_action_from_pi with temperature max(0, 1 - ply/temp_threshold) (train.py:252-266,
+ * 647-648), illegal-pick fallback to argmax (train.py:380-382); records (position, pi) as the
+ * ply's example (train.py:384).  pi float32[G][225] -> actions int32[G]. */
+int azg_selfplay_choose(azg_engine* e, const float* pi, float temp_threshold, uint64_t draw, int32_t* actions);
+/* After azg_search_advance: games that are over (status bit 2) or reached max_moves plies get
+ * their examples labelled with z and expanded by the 8 symmetries (train.py:392-410,
+ * new_mcts_alpha.py:42-56) into out[row][901] = planes[3][225], pi[225], z, rows reserved at
+ * *cursor (device counter; rows >= capacity are dropped).  done_mask int32[G] marks the games
+ * to restart; winners int32[G] (may be NULL) receives 0/1/2 or -1 for unfinished games. */
+int azg_selfplay_finish(azg_engine* e, const int32_t* status, int max_moves, int use_symmetries, float* out,
+                        int64_t capacity, uint64_t* cursor, int32_t* done_mask, int32_t* winners);
 
 /* ------------------------------------------------------------------ leaf evaluator (policy/value ResNet)
  * Replaces AlphaZeroNet.forward + PyTorchModel.predict (network.py:85-117, 168-183): stem conv,
@@ -176,6 +197,10 @@ int azg_net_forward_planes(azg_net* n, const float* planes, int count, float* pr
 int azg_net_forward_leaves(azg_net* n, azg_engine* e, float* probs, float* values);
 /* Test hook: activations after the stem and the first n_layers 3x3 layers, float32[count][C][15][15]. */
 int azg_net_trunk_debug(azg_net* n, const float* planes, int count, int n_layers, float* out, void* stream);
+/* Measurement hooks used by bench.py: time the 3x3 trunk of every forward pass with CUDA events
+ * on the launch stream; read returns the summed milliseconds and the conv3x3 launches covered. */
+int azg_net_profile(azg_net* n, int enable);
+int azg_net_profile_read(azg_net* n, double* trunk_ms, int64_t* launches);
 /* Synchronise and report the tcgen05 pipeline watchdog (0 = healthy). */
 int azg_net_check(azg_net* n, void* stream);
 

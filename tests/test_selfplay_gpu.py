@@ -1,0 +1,139 @@
+"""GPU: self-play driver kernels - Philox Dirichlet noise and temperature sampling (statistical),
+argmax at T = 0, outcome labels and the 8 symmetries in the reference's order (exact)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import rules as orules
+from oracle.search import dihedral8
+
+pytestmark = pytest.mark.gpu
+
+
+def test_dirichlet_moments():
+    """Marginals of Dirichlet(alpha * 1_225): mean 1/225, var = (1/225)(1-1/225)/(225*alpha+1)."""
+    import alphazero_gomoku_b200 as m
+    from alphazero_gomoku_b200._lib import check, lib, ptr
+    G, alpha = 4096, 0.05
+    eng = m.SearchEngine(0, G, noise=True, alpha=alpha, eps=0.25, node_capacity=64)
+    noise = torch.empty((G, 225), dtype=torch.float64, device="cuda")
+    draws = []
+    for d in range(4):
+        eng._sync_stream()
+        check(lib.azg_selfplay_noise(eng._h, d, ptr(noise)))
+        draws.append(noise.cpu().numpy().copy())
+    x = np.concatenate(draws)                         # 16384 samples of a 225-vector
+    assert np.allclose(x.sum(1), 1.0, atol=1e-12) and (x >= 0).all()
+    mean, var = 1 / 225, (1 / 225) * (1 - 1 / 225) / (225 * alpha + 1)
+    assert abs(x.mean() - mean) < 1e-9
+    assert np.abs(x.mean(0) - mean).max() < 6 * np.sqrt(var / len(x))
+    assert abs(x.var(0).mean() / var - 1) < 0.03
+    assert not np.array_equal(draws[0], draws[1])
+    # same (seed, draw) -> same numbers
+    eng._sync_stream()
+    check(lib.azg_selfplay_noise(eng._h, 0, ptr(noise)))
+    assert np.array_equal(noise.cpu().numpy(), draws[0])
+    eng.close()
+
+
+def test_choose_argmax_and_sampling():
+    import alphazero_gomoku_b200 as m
+    from alphazero_gomoku_b200._lib import check, lib, ptr
+    G = 8192
+    eng = m.SearchEngine(0, G, node_capacity=64)
+    check(lib.azg_selfplay_enable(eng._h, 225))
+    pi = torch.zeros((G, 225), dtype=torch.float32, device="cuda")
+    pi[:, 10] = 0.5; pi[:, 20] = 0.3; pi[:, 200] = 0.2
+    acts = torch.empty(G, dtype=torch.int32, device="cuda")
+    # ply 0, threshold 10 -> temperature 1: frequencies follow pi
+    eng._sync_stream()
+    check(lib.azg_selfplay_choose(eng._h, ptr(pi), C.c_float(10.0), 1, ptr(acts)))
+    a = acts.cpu().numpy()
+    f = np.array([(a == 10).mean(), (a == 20).mean(), (a == 200).mean()])
+    assert f.sum() == 1.0 and np.abs(f - [0.5, 0.3, 0.2]).max() < 0.02
+    # ply 1 with threshold 1 -> temperature 0 -> first argmax even with ties
+    pi2 = torch.zeros((G, 225), dtype=torch.float32, device="cuda")
+    pi2[:, 37] = 0.4; pi2[:, 99] = 0.4; pi2[:, 5] = 0.2
+    check(lib.azg_selfplay_choose(eng._h, ptr(pi2), C.c_float(1.0), 2, ptr(acts)))
+    assert (acts.cpu().numpy() == 37).all()
+    eng.close()
+
+
+def test_examples_labels_and_symmetries():
+    """Play two short scripted games to the end; exported rows must equal the oracle's
+    play_game_and_collect output format: 8 symmetries per ply in reference order, z per player."""
+    import alphazero_gomoku_b200 as m
+    from alphazero_gomoku_b200._lib import check, lib, ptr
+    G = 2
+    eng = m.SearchEngine(0, G, node_capacity=64)
+    check(lib.azg_selfplay_enable(eng._h, 225))
+    # game 0: player 1 wins on the top row; game 1: same moves shifted down (still player 1 wins)
+    moves0 = [0, 30, 1, 31, 2, 32, 3, 33, 4]
+    moves1 = [m_ + 45 for m_ in moves0]
+    rng = np.random.default_rng(0)
+    pis, pos = [], [orules.Position(0), orules.Position(0)]
+    out = torch.zeros((4096, 901), dtype=torch.float32, device="cuda")
+    cursor = torch.zeros(1, dtype=torch.int64, device="cuda")
+    done = torch.zeros(G, dtype=torch.int32, device="cuda")
+    winners = torch.zeros(G, dtype=torch.int32, device="cuda")
+    expected = [[], []]
+    for t in range(len(moves0)):
+        pi = np.zeros((G, 225), np.float32)
+        for g, mv in enumerate((moves0[t], moves1[t])):
+            pi[g] = rng.random(225).astype(np.float32) * 0.001
+            pi[g, mv] = 5.0                                   # argmax = the scripted move
+            pi[g] /= pi[g].sum()
+            expected[g].append((orules.encode(pos[g]), pi[g].copy(), pos[g].player))
+            orules.play(pos[g], mv)
+        acts = torch.empty(G, dtype=torch.int32, device="cuda")
+        eng._sync_stream()
+        check(lib.azg_selfplay_choose(eng._h, ptr(torch.from_numpy(pi).cuda()), C.c_float(1e-9), 7, ptr(acts)))   # T = 0 after ply 0
+        if t > 0:
+            assert acts.cpu().tolist() == [moves0[t], moves1[t]]
+        else:
+            acts = torch.tensor([moves0[0], moves1[0]], dtype=torch.int32, device="cuda")
+        status = eng.advance(acts, gc=True)
+        check(lib.azg_selfplay_finish(eng._h, ptr(status), 225, 1, ptr(out), 4096, ptr(cursor), ptr(done), ptr(winners)))
+    assert done.cpu().tolist() == [1, 1] and winners.cpu().tolist() == [1, 1]
+    n = int(cursor.item())
+    assert n == 2 * len(moves0) * 8
+    rows = out[:n].cpu().numpy()
+    # rows of a game are contiguous (one reservation per game); find each game's block by its first plane
+    blocks = [rows[:n // 2], rows[n // 2:]]
+    if not np.array_equal(blocks[0][0, :675].reshape(3, 15, 15), expected[0][0][0]):
+        blocks = blocks[::-1]
+    for g in range(G):
+        k = 0
+        for planes, pi, player in expected[g]:
+            z = 1.0 if player == 1 else -1.0
+            for s, p in dihedral8(planes, pi):
+                assert np.array_equal(blocks[g][k, :675].reshape(3, 15, 15), s), (g, k)
+                assert np.array_equal(blocks[g][k, 675:900], p)
+                assert blocks[g][k, 900] == z
+                k += 1
+    eng.close()
+
+
+def test_selfplay_runs_games_to_completion():
+    import alphazero_gomoku_b200 as m
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import SelfPlay
+    torch.manual_seed(0)
+    model = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    sp = SelfPlay(model, n_games=32, n_sims=48, node_capacity=2048, example_capacity=1 << 16, max_moves=60)
+    finished = 0
+    for _ in range(70):
+        sp.step()
+        finished += int(sp.done.sum().item())
+    st = sp.engine.stats()
+    assert st["games_in_error"] == 0 and finished >= 32
+    rows = sp.drain_examples()
+    states, pis, zs = SelfPlay.split(rows)
+    assert rows.shape[0] > 0 and rows.shape[0] % 8 == 0
+    assert torch.all((zs == 0) | (zs == 1) | (zs == -1))
+    assert torch.allclose(pis.sum(1), torch.ones_like(pis[:, 0]), atol=1e-4)
+    assert torch.all(states[:, 2] == 1.0) and torch.all((states[:, 0] * states[:, 1]) == 0)
+    sp.close()

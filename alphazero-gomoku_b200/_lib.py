@@ -85,6 +85,7 @@ PROTOTYPES = {
     "azg_net_trunk_debug": (_I, [_P, _P, _I, _I, _P, _P]),
     "azg_net_profile": (_I, [_P, _I]),
     "azg_net_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "azg_net_profile_counters": (_I, [_P, _P]),
     "azg_net_check": (_I, [_P, _P]),
 }
 

@@ -16,11 +16,11 @@ struct ConvArgs {
   int max_boards;                 // capacity of the activation buffers
   int layer;                      // index into the packed 3x3 weights (tap-major blocks of C x C)
   int relu;
-  const float* scale;             // [C] folded BatchNorm scale of this layer
-  const float* shift;             // [C]
+  const float* shift_host;        // HOST [C]: folded BatchNorm shift of this layer (the scale lives in the weights)
   const __nv_bfloat16* residual;  // padded activation buffer added before the ReLU, or null
   __nv_bfloat16* out;             // padded activation buffer
   int* error;                     // device flag set by the pipeline watchdogs
+  unsigned long long* prof;       // optional device counters [8] (cycles spent waiting per role), or null
 };
 
 int azg_conv3x3_launch(int C, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm,

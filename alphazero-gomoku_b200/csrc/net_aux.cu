@@ -17,12 +17,13 @@ __global__ void fold_bn_kernel(const float* g, const float* b, const float* mean
   shift[i] = b[i] - mean[i] * s;
 }
 
-// conv weight [Cout][Cin][3][3] fp32 -> bf16 rows (layer*9 + tap)*C + cout, columns cin (K-major B operand).
-__global__ void pack_conv3_kernel(const float* w, int C, int layer, __nv_bfloat16* out) {
+// conv weight [Cout][Cin][3][3] fp32, times the folded BatchNorm scale of its output channel ->
+// bf16 rows (layer*9 + tap)*C + cout, columns cin (K-major B operand).
+__global__ void pack_conv3_kernel(const float* w, const float* scale, int C, int layer, __nv_bfloat16* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 9 * C * C) return;
   const int ci = i % C, co = (i / C) % C, tap = i / (C * C);
-  out[((size_t)(layer * 9 + tap) * C + co) * C + ci] = __float2bfloat16(w[((size_t)co * C + ci) * 9 + tap]);
+  out[((size_t)(layer * 9 + tap) * C + co) * C + ci] = __float2bfloat16(w[((size_t)co * C + ci) * 9 + tap] * scale[co]);
 }
 
 // stem weight [C][3][3][3] -> fp32 [(tap*3 + plane)][C], BatchNorm scale folded in.
@@ -45,8 +46,8 @@ int azg_pack_launch_fold(const float* g, const float* b, const float* m, const f
   fold_bn_kernel<<<(n + 127) / 128, 128, 0, s>>>(g, b, m, v, n, scale, shift);
   return azg_check_launch("fold_bn");
 }
-int azg_pack_launch_conv3(const float* w, int C, int layer, __nv_bfloat16* out, cudaStream_t s) {
-  pack_conv3_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(w, C, layer, out);
+int azg_pack_launch_conv3(const float* w, const float* scale, int C, int layer, __nv_bfloat16* out, cudaStream_t s) {
+  pack_conv3_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(w, scale, C, layer, out);
   return azg_check_launch("pack_conv3");
 }
 int azg_pack_launch_stem(const float* w, const float* scale, int C, float* out, cudaStream_t s) {

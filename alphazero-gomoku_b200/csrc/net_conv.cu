@@ -25,7 +25,6 @@
 
 namespace {
 
-constexpr int kStages = 3;
 constexpr int kCopyRows = 160;                 // 128 tile rows + 16 above + 16 below
 constexpr int kStageBytes = kCopyRows * 128;   // one 64-channel slice of one shifted copy
 constexpr int kThreads = 192;
@@ -36,15 +35,25 @@ struct Cfg {
   static constexpr int BBLK = (C / 2) * 128;              // one (tap, slice) weight block: C/2 rows x 128 B
   static constexpr int BBYTES = 9 * KC * BBLK;            // resident weights per CTA
   static constexpr int TMEM_COLS = 2 * C;                 // two accumulators
-  static constexpr int SMEM = 1024 + BBYTES + kStages * kStageBytes + 256 + 2 * C * 4;
+  static constexpr int STAGES = C == 128 ? 4 : 6;         // activation copies in flight
+  static constexpr int SMEM = 1024 + BBYTES + STAGES * kStageBytes + 256;
+};
+
+// Folded BatchNorm shift of the layer, passed by value so the epilogue reads it from the constant
+// bank (no shared-memory or LSU traffic).  The BatchNorm scale is folded into the bf16 weights.
+template <int C>
+struct ConvShift {
+  float v[C];
 };
 
 enum { ERR_BFULL = 1, ERR_EMPTY = 2, ERR_FULL = 3, ERR_TEMPTY = 4, ERR_TFULL = 5 };
 
 template <int C>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w, ConvArgs p) {
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w, ConvArgs p,
+                    const __grid_constant__ ConvShift<C> shift) {
   using K = Cfg<C>;
+  constexpr int kStages = K::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;
@@ -56,8 +65,6 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   uint64_t* tempty = tfull + 2;         // [2]        leader: both epilogues drained the accumulator
   uint64_t* bfull = tempty + 2;         // leader: both weight halves resident
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
-  float* s_scale = reinterpret_cast<float*>(bars + 32);
-  float* s_shift = s_scale + C;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -80,7 +87,6 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     ptx::tmem_alloc<2>(tmem_slot, K::TMEM_COLS);
     ptx::tmem_relinquish<2>();
   }
-  for (int i = threadIdx.x; i < C; i += kThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();
@@ -98,15 +104,23 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
+      long long t_wait = 0;
+      const long long t_begin = clock64();
       for (int b = cid; b < n_boards && ok; b += ncl) {
         const int row0 = AZG_NET_FRONT + (b * 2 + (int)rank) * 128 - 16;
         for (int kc = 0; kc < K::KC && ok; ++kc)
           for (int dci = 0; dci < 3; ++dci) {
+            const long long t0 = clock64();
             if (!ptx::mbar_wait(&empty[stage], phase ^ 1u)) { atomicExch(p.error, ERR_EMPTY); ok = false; break; }
+            t_wait += clock64() - t0;
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2u * kStageBytes);
             ptx::tma_load_2d_pair(sA + stage * kStageBytes, &tm_act, &full[stage], kc * 64, row0 + dci - 1);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
+      }
+      if (p.prof && rank == 0) {
+        atomicAdd(p.prof + 3, (unsigned long long)t_wait);
+        atomicAdd(p.prof + 4, (unsigned long long)(clock64() - t_begin));
       }
     }
   } else if (warp == 1) {
@@ -118,14 +132,20 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       if (!ok) atomicExch(p.error, ERR_BFULL);
       int stage = 0, it = 0;
       uint32_t phase = 0;
+      long long t_full = 0, t_tempty = 0;
+      const long long t_begin = clock64();
       for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
         const int acc = it & 1;
+        long long t0 = clock64();
         if (!ptx::mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u)) { atomicExch(p.error, ERR_TEMPTY); ok = false; break; }
+        t_tempty += clock64() - t0;
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C);
         for (int kc = 0; kc < K::KC && ok; ++kc)
           for (int dci = 0; dci < 3; ++dci) {
+            t0 = clock64();
             if (!ptx::mbar_wait(&full[stage], phase)) { atomicExch(p.error, ERR_FULL); ok = false; break; }
+            t_full += clock64() - t0;
             ptx::tc_fence_after();
 #pragma unroll
             for (int dri = 0; dri < 3; ++dri) {
@@ -142,6 +162,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
           }
         if (ok) ptx::umma_commit_pair(&tfull[acc], 3);       // accumulator ready in both CTAs
       }
+      if (p.prof) {
+        atomicAdd(p.prof + 0, (unsigned long long)t_full);
+        atomicAdd(p.prof + 1, (unsigned long long)t_tempty);
+        atomicAdd(p.prof + 2, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(p.prof + 7, (unsigned long long)it);
+      }
     }
   } else {
     // ============================== epilogue (warps 2..5, both CTAs) ==============================
@@ -151,50 +177,48 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     const bool pad = (qi < 16) || ((qi & 15) == 15);
     int it = 0;
     bool ok = true;
+    long long t_tfull = 0;
+    const long long t_begin = clock64();
     for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
       const int acc = it & 1;
+      const long long t0 = clock64();
       if (!ptx::mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u)) { atomicExch(p.error, ERR_TFULL); ok = false; break; }
+      t_tfull += clock64() - t0;
       ptx::tc_fence_after();
       const size_t grow = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)qi;
       __nv_bfloat16* orow = p.out + grow * C;
       const __nv_bfloat16* rrow = p.residual ? p.residual + grow * C : nullptr;
-#pragma unroll 1
+#pragma unroll
       for (int ch = 0; ch < C; ch += 32) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * C + ch), v);
+        uint32_t res[16];
+        if (rrow) { ptx::ldg256(rrow + ch, &res[0]); ptx::ldg256(rrow + ch + 16, &res[8]); }
         ptx::tmem_ld_wait();
-        uint4 res[4];
-        if (rrow) {
+        uint32_t outv[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rrow + ch + 8 * j);
-        }
-        uint4 outv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t packed[4];
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int c0 = ch + 8 * j + 2 * h;
-            float y0 = fmaf(__uint_as_float(v[8 * j + 2 * h]), s_scale[c0], s_shift[c0]);
-            float y1 = fmaf(__uint_as_float(v[8 * j + 2 * h + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
-            if (rrow) {
-              const uint32_t rw = (&res[j].x)[h];
-              y0 += __uint_as_float(rw << 16);
-              y1 += __uint_as_float(rw & 0xffff0000u);
-            }
-            if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-            if (pad) { y0 = 0.f; y1 = 0.f; }
-            const __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
-            packed[h] = *reinterpret_cast<const uint32_t*>(&pk);
+        for (int h = 0; h < 16; ++h) {
+          float y0 = __uint_as_float(v[2 * h]) + shift.v[ch + 2 * h];
+          float y1 = __uint_as_float(v[2 * h + 1]) + shift.v[ch + 2 * h + 1];
+          if (rrow) {
+            y0 += __uint_as_float(res[h] << 16);
+            y1 += __uint_as_float(res[h] & 0xffff0000u);
           }
-          outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+          if (pad) { y0 = 0.f; y1 = 0.f; }
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
+          outv[h] = *reinterpret_cast<const uint32_t*>(&pk);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + ch + 8 * j) = outv[j];
+        ptx::stg256(orow + ch, &outv[0]);
+        ptx::stg256(orow + ch + 16, &outv[8]);
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
+    }
+    if (p.prof && rank == 0 && warp == 2 && lane == 0) {
+      atomicAdd(p.prof + 5, (unsigned long long)t_tfull);
+      atomicAdd(p.prof + 6, (unsigned long long)(clock64() - t_begin));
     }
   }
 
@@ -212,7 +236,9 @@ int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvAr
   int grid = n_sm & ~1;
   const int want = 2 * args.max_boards;
   if (grid > want) grid = want < 2 ? 2 : want;
-  conv3x3_pair_kernel<C><<<grid, kThreads, K::SMEM, stream>>>(tm_act, tm_w, args);
+  ConvShift<C> shift;
+  for (int i = 0; i < C; ++i) shift.v[i] = args.shift_host[i];
+  conv3x3_pair_kernel<C><<<grid, kThreads, K::SMEM, stream>>>(tm_act, tm_w, args, shift);
   return azg_check_launch("conv3x3_pair_kernel");
 }
 

@@ -8,7 +8,7 @@
 #include "net.h"
 
 int azg_pack_launch_fold(const float*, const float*, const float*, const float*, int, float*, float*, cudaStream_t);
-int azg_pack_launch_conv3(const float*, int, int, __nv_bfloat16*, cudaStream_t);
+int azg_pack_launch_conv3(const float*, const float*, int, int, __nv_bfloat16*, cudaStream_t);
 int azg_pack_launch_stem(const float*, const float*, int, float*, cudaStream_t);
 int azg_pack_launch_transpose(const float*, int, int, float*, cudaStream_t);
 
@@ -25,11 +25,13 @@ struct azg_net {
   float* hidden = nullptr;
   uint32_t *keys = nullptr, *meta = nullptr;
   int *n_dev = nullptr, *error_dev = nullptr;
+  unsigned long long* prof_dev = nullptr;
   int* pinned = nullptr;
   CUtensorMap tm_act[3], tm_w;
   // optional timing of the 3x3 trunk (one CUDA-event pair per forward pass, on the launch stream)
   int profiling = 0;
   std::vector<cudaEvent_t> ev;          // start/stop pairs
+  std::vector<float> shift_host;        // [2*n_blocks][C] folded BatchNorm shifts of the 3x3 layers
   size_t ev_used = 0;
   long long prof_launches = 0;
 };
@@ -77,7 +79,7 @@ extern "C" int azg_net_destroy(azg_net* n) {
   cudaFree(n->head_w1); cudaFree(n->head_scale1); cudaFree(n->head_shift1); cudaFree(n->pol_wt); cudaFree(n->pol_b);
   cudaFree(n->v1_wt); cudaFree(n->v1_b); cudaFree(n->v2_w); cudaFree(n->v2_b);
   for (int i = 0; i < 3; ++i) cudaFree(n->act[i]);
-  cudaFree(n->hidden); cudaFree(n->keys); cudaFree(n->meta); cudaFree(n->n_dev); cudaFree(n->error_dev);
+  cudaFree(n->hidden); cudaFree(n->keys); cudaFree(n->meta); cudaFree(n->n_dev); cudaFree(n->error_dev); cudaFree(n->prof_dev);
   if (n->pinned) cudaFreeHost(n->pinned);
   for (cudaEvent_t ev : n->ev) cudaEventDestroy(ev);
   delete n;
@@ -114,13 +116,15 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
       (rc = nalloc(n, &n->act[2], n->rows * C)) ||
       (rc = nalloc(n, &n->hidden, (size_t)((max_batch + 31) / 32) * AZG_HIDDEN_TILE)) ||
       (rc = nalloc(n, &n->keys, (size_t)max_batch * 16)) || (rc = nalloc(n, &n->meta, (size_t)max_batch)) ||
-      (rc = nalloc(n, &n->n_dev, (size_t)4)) || (rc = nalloc(n, &n->error_dev, (size_t)4))) {
+      (rc = nalloc(n, &n->n_dev, (size_t)4)) || (rc = nalloc(n, &n->error_dev, (size_t)4)) ||
+      (rc = nalloc(n, &n->prof_dev, (size_t)16))) {
     azg_net_destroy(n);
     return rc;
   }
   if (cudaMallocHost((void**)&n->pinned, 64) != cudaSuccess) { azg_net_destroy(n); return azg_fail(AZG_E_NOMEM, "pinned allocation failed"); }
   for (int i = 0; i < 3; ++i) cudaMemset(n->act[i], 0, n->rows * C * 2);      // pad rows must read as zero
   cudaMemset(n->error_dev, 0, 16);
+  cudaMemset(n->prof_dev, 0, 128);
   cudaMemset(n->hidden, 0, (size_t)((max_batch + 31) / 32) * AZG_HIDDEN_TILE * 4);
   for (int i = 0; i < 3; ++i)
     if ((rc = make_map(&n->tm_act[i], n->act[i], n->rows, C, 160))) { azg_net_destroy(n); return rc; }
@@ -143,9 +147,9 @@ extern "C" int azg_net_load(azg_net* n, const azg_net_weights* w, void* stream_)
   if ((rc = azg_pack_launch_stem(w->conv_w, n->stem_scale, C, n->stem_w, s))) return rc;
   for (int l = 0; l < 2 * n->n_blocks; ++l) {
     if (!w->res_conv_w[l]) return azg_fail(AZG_E_ARG, "azg_net_load: missing residual-block weights");
-    if ((rc = azg_pack_launch_conv3(w->res_conv_w[l], C, l, n->w3, s))) return rc;
     if ((rc = azg_pack_launch_fold(w->res_bn[l][0], w->res_bn[l][1], w->res_bn[l][2], w->res_bn[l][3], C,
                                    n->scale3 + (size_t)l * C, n->shift3 + (size_t)l * C, s))) return rc;
+    if ((rc = azg_pack_launch_conv3(w->res_conv_w[l], n->scale3 + (size_t)l * C, C, l, n->w3, s))) return rc;
   }
   // head 1x1 convs: rows 0-1 policy_conv.weight [2][C], row 2 value_conv.weight [1][C]
   AZG_CUDA(cudaMemcpyAsync(n->head_w1, w->policy_conv_w, 2 * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -158,6 +162,11 @@ extern "C" int azg_net_load(azg_net* n, const azg_net_weights* w, void* stream_)
   AZG_CUDA(cudaMemcpyAsync(n->v1_b, w->value_fc1_b, 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   AZG_CUDA(cudaMemcpyAsync(n->v2_w, w->value_fc2_w, 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   AZG_CUDA(cudaMemcpyAsync(n->v2_b, w->value_fc2_b, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  // the epilogue takes the shifts as kernel arguments (constant bank): keep a host copy
+  n->shift_host.resize((size_t)2 * n->n_blocks * C + 1);
+  if (n->n_blocks > 0)
+    AZG_CUDA(cudaMemcpyAsync(n->shift_host.data(), n->shift3, (size_t)2 * n->n_blocks * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+  AZG_CUDA(cudaStreamSynchronize(s));
   n->loaded = 1;
   return AZG_OK;
 }
@@ -188,7 +197,7 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
   for (int l = 0; l < n_layers; ++l) {
     ConvArgs a;
     a.n_boards = n_ptr; a.max_boards = max_boards; a.layer = l; a.relu = 1;
-    a.scale = n->scale3 + (size_t)l * C; a.shift = n->shift3 + (size_t)l * C; a.error = n->error_dev;
+    a.shift_host = n->shift_host.data() + (size_t)l * C; a.error = n->error_dev; a.prof = n->profiling ? n->prof_dev : nullptr;
     if ((l & 1) == 0) { a.residual = nullptr; a.out = n->act[t]; rc = azg_conv3x3_launch(C, n->tm_act[x], n->tm_w, a, n->n_sm, s); }
     else { a.residual = n->act[x]; a.out = n->act[y]; rc = azg_conv3x3_launch(C, n->tm_act[t], n->tm_w, a, n->n_sm, s); int tmp = x; x = y; y = tmp; }
     if (rc) return rc;
@@ -303,6 +312,18 @@ extern "C" int azg_net_profile_read(azg_net* n, double* trunk_ms, int64_t* launc
   *launches = n->prof_launches;
   n->ev_used = 0;
   n->prof_launches = 0;
+  return AZG_OK;
+}
+
+// Pipeline wait counters of the conv3x3 kernel accumulated while profiling is enabled (cycles,
+// summed over clusters): {mma wait-full, mma wait-tmem-empty, mma total, producer wait-empty,
+// producer total, epilogue wait-tmem-full, epilogue total, boards}; reading resets them.
+extern "C" int azg_net_profile_counters(azg_net* n, uint64_t* out8) {
+  if (!n || !out8) return azg_fail(AZG_E_ARG, "null argument");
+  AZG_CUDA(cudaSetDevice(n->device));
+  AZG_CUDA(cudaDeviceSynchronize());
+  AZG_CUDA(cudaMemcpy(out8, n->prof_dev, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  AZG_CUDA(cudaMemset(n->prof_dev, 0, 128));
   return AZG_OK;
 }
 

@@ -95,5 +95,12 @@ class NetEngine:
         check(lib.azg_net_profile_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def profile_counters(self) -> dict:
+        out = (C.c_uint64 * 8)()
+        check(lib.azg_net_profile_counters(self._h, out))
+        keys = ("mma_wait_full", "mma_wait_tmem_empty", "mma_total", "producer_wait_empty", "producer_total",
+                "epilogue_wait_tmem_full", "epilogue_total", "boards")
+        return {k: int(out[i]) for i, k in enumerate(keys)}
+
     def check(self):
         check(lib.azg_net_check(self._h, _stream()))

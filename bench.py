@@ -253,6 +253,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     trunk_ms, conv_launches = sp.net.profile_read()
+    pipe = sp.net.profile_counters()
     sp.net.profile(False)
     sims, evals = sp.total_sims - sims0, sp.total_evals - evals0
     launches, rounds = sp.total_launches - launches0, sp.total_rounds - rounds0
@@ -332,7 +333,8 @@ def run_ours(args):
                          "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
                          "launches": int(conv_launches), "avg_launch_ms": trunk_ms / max(conv_launches, 1),
                          "trunk_share_of_step": trunk_ms / ms if ms else None,
-                         "algorithmic_flops_per_position_per_launch": TRUNK_FLOPS[args.channels]},
+                         "algorithmic_flops_per_position_per_launch": TRUNK_FLOPS[args.channels],
+                         "pipeline_cycles_per_board": {k: round(v / max(pipe["boards"], 1), 1) for k, v in pipe.items() if k != "boards"}},
             "clocks": clk,
             "search": {"rounds": int(rounds), "games_in_error": stats["games_in_error"], "error_bits": stats["error_bits"],
                        "max_nodes_per_game": stats["max_nodes"], "dropped_trees": stats["dropped_trees"], "engine_gb": sp.engine.memory_bytes / 1e9,

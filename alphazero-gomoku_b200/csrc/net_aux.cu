@@ -94,11 +94,23 @@ int azg_planes_to_keys_launch(const float* planes, int n, uint32_t* keys, uint32
 template <int C>
 __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
   constexpr int CPL = C / 32;
-  __shared__ float s_w[27 * C];
-  __shared__ float s_shift[C];
-  __shared__ uint8_t s_state[256];
-  for (int i = threadIdx.x; i < 27 * C; i += 256) s_w[i] = a.w[i];
-  for (int i = threadIdx.x; i < C; i += 256) s_shift[i] = a.shift[i];
+  __shared__ __align__(16) float s_t[27 * C];   // [tap][state-1]: ones-plane weight (+ mover / opponent weight)
+  __shared__ __align__(16) float s_empty[C];    // shift + all nine taps on empty in-board cells
+  __shared__ __align__(16) float s_shift[C];
+  __shared__ uint8_t s_state[256];              // 0 off-board / pad, 1 empty, 2 mover stone, 3 opponent stone
+  __shared__ uint32_t s_code[256];              // the nine neighbour states of each padded pixel, 2 bits per tap
+  for (int i = threadIdx.x; i < 27 * C; i += 256) {
+    const int c = i % C, st = (i / C) % 3, tap = i / (3 * C);
+    float v = a.w[(tap * 3 + 2) * C + c];
+    if (st >= 1) v += a.w[(tap * 3 + (st - 1)) * C + c];
+    s_t[i] = v;
+  }
+  for (int i = threadIdx.x; i < C; i += 256) {
+    float e = a.shift[i];
+    for (int tap = 0; tap < 9; ++tap) e += a.w[(tap * 3 + 2) * C + i];
+    s_empty[i] = e;
+    s_shift[i] = a.shift[i];
+  }
   int n = *a.n_boards;
   if (n > a.max_boards) n = a.max_boards;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -120,30 +132,40 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
       s_state[qi] = st;
     }
     __syncthreads();
+    {
+      const int qi = threadIdx.x;
+      uint32_t code = 0;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int q2 = qi + (tap / 3 - 1) * 16 + (tap % 3 - 1);
+        const uint32_t st = (q2 >= 0 && q2 < 256) ? s_state[q2] : 0;
+        code |= st << (2 * tap);
+      }
+      s_code[qi] = s_state[qi] ? code : 0xffffffffu;      // pad rows/columns are written as zeros
+    }
+    __syncthreads();
     __nv_bfloat16* out = a.out + ((size_t)AZG_NET_FRONT + (size_t)b * 256) * C;
+#pragma unroll 2
     for (int i = 0; i < 32; ++i) {
       const int qi = warp * 32 + i;
+      const uint32_t code = s_code[qi];
       float acc[CPL];
-      const int st0 = s_state[qi];
-      if (st0 == 0) {
+      if (code == 0xffffffffu) {
 #pragma unroll
         for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
+      } else if (code == 0x15555u) {                       // nine empty in-board neighbours
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) acc[j] = fmaxf(s_empty[lane * CPL + j], 0.f);
       } else {
 #pragma unroll
         for (int j = 0; j < CPL; ++j) acc[j] = s_shift[lane * CPL + j];
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const int q2 = qi + (tap / 3 - 1) * 16 + (tap % 3 - 1);
-          const int st = (q2 >= 0 && q2 < 256) ? s_state[q2] : 0;
+          const uint32_t st = (code >> (2 * tap)) & 3u;
           if (st == 0) continue;
-          const float* w1 = s_w + (tap * 3 + 2) * C + lane * CPL;
+          const float* w = s_t + (tap * 3 + (int)st - 1) * C + lane * CPL;
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) acc[j] += w1[j];
-          if (st >= 2) {
-            const float* w2 = s_w + (tap * 3 + (st - 2)) * C + lane * CPL;
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) acc[j] += w2[j];
-          }
+          for (int j = 0; j < CPL; ++j) acc[j] += w[j];
         }
 #pragma unroll
         for (int j = 0; j < CPL; ++j) acc[j] = fmaxf(acc[j], 0.f);
@@ -198,34 +220,43 @@ __global__ void __launch_bounds__(256) head1_kernel(HeadArgs a) {
   for (int b = blockIdx.x; b < n; b += gridDim.x) {
     const __nv_bfloat16* act = a.act + ((size_t)AZG_NET_FRONT + (size_t)b * 256) * C;
     float* hid = a.hidden + (size_t)(b >> 5) * (AZG_HID * 32) + (b & 31);
-    for (int pix = warp; pix < 225; pix += 8) {
-      const int r = pix / 15, c = pix - r * 15;
-      const __nv_bfloat16* row = act + (size_t)((r + 1) * 16 + c) * C + lane * CPL;
-      float x[CPL];
-      if constexpr (CPL == 2) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row));
-        x[0] = f.x; x[1] = f.y;
-      } else {
+    // four pixels per iteration so that four row loads are in flight per warp
+    for (int p0 = warp * 4; p0 < 225; p0 += 32) {
+      float x[4][CPL];
 #pragma unroll
-        for (int j = 0; j < CPL; j += 4) {
-          const uint2 v = *reinterpret_cast<const uint2*>(row + j);
-          x[j] = __uint_as_float(v.x << 16); x[j + 1] = __uint_as_float(v.x & 0xffff0000u);
-          x[j + 2] = __uint_as_float(v.y << 16); x[j + 3] = __uint_as_float(v.y & 0xffff0000u);
+      for (int u = 0; u < 4; ++u) {
+        const int pix = min(p0 + u, 224);
+        const int r = pix / 15, c = pix - r * 15;
+        const __nv_bfloat16* row = act + (size_t)((r + 1) * 16 + c) * C + lane * CPL;
+        if constexpr (CPL == 2) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row));
+          x[u][0] = f.x; x[u][1] = f.y;
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPL; j += 4) {
+            const uint2 v = *reinterpret_cast<const uint2*>(row + j);
+            x[u][j] = __uint_as_float(v.x << 16); x[u][j + 1] = __uint_as_float(v.x & 0xffff0000u);
+            x[u][j + 2] = __uint_as_float(v.y << 16); x[u][j + 3] = __uint_as_float(v.y & 0xffff0000u);
+          }
         }
       }
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < CPL; ++j) { d0 = fmaf(x[j], w[0][j], d0); d1 = fmaf(x[j], w[1][j], d1); d2 = fmaf(x[j], w[2][j], d2); }
+      for (int u = 0; u < 4; ++u) {
+        const int pix = p0 + u;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) {
-        d0 += __shfl_xor_sync(0xffffffffu, d0, s);
-        d1 += __shfl_xor_sync(0xffffffffu, d1, s);
-        d2 += __shfl_xor_sync(0xffffffffu, d2, s);
-      }
-      if (lane == 0) {
-        hid[(size_t)pix * 32] = fmaxf(fmaf(d0, sc0, sh0), 0.f);
-        hid[(size_t)(225 + pix) * 32] = fmaxf(fmaf(d1, sc1, sh1), 0.f);
-        hid[(size_t)(450 + pix) * 32] = fmaxf(fmaf(d2, sc2, sh2), 0.f);
+        for (int j = 0; j < CPL; ++j) { d0 = fmaf(x[u][j], w[0][j], d0); d1 = fmaf(x[u][j], w[1][j], d1); d2 = fmaf(x[u][j], w[2][j], d2); }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+          d0 += __shfl_xor_sync(0xffffffffu, d0, s);
+          d1 += __shfl_xor_sync(0xffffffffu, d1, s);
+          d2 += __shfl_xor_sync(0xffffffffu, d2, s);
+        }
+        if (lane == 0 && pix < 225) {
+          hid[(size_t)pix * 32] = fmaxf(fmaf(d0, sc0, sh0), 0.f);
+          hid[(size_t)(225 + pix) * 32] = fmaxf(fmaf(d1, sc1, sh1), 0.f);
+          hid[(size_t)(450 + pix) * 32] = fmaxf(fmaf(d2, sc2, sh2), 0.f);
+        }
       }
     }
   }
@@ -257,14 +288,20 @@ __global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
       const float bias = a.pol_b[tid];
 #pragma unroll
       for (int b = 0; b < 32; ++b) acc[b] = bias;
-      for (int k = 0; k < 450; ++k) {
-        const float w = __ldg(a.pol_wt + (size_t)k * 225 + tid);
-        const float4* h = reinterpret_cast<const float4*>(s_h + k * 32);
+      for (int k0 = 0; k0 < 450; k0 += 10) {
+        float wv[10];                                   // ten weight loads in flight per thread
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 hv = h[q];
-          acc[4 * q] = fmaf(w, hv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(w, hv.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(w, hv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, hv.w, acc[4 * q + 3]);
+        for (int u = 0; u < 10; ++u) wv[u] = __ldg(a.pol_wt + (size_t)(k0 + u) * 225 + tid);
+#pragma unroll
+        for (int u = 0; u < 10; ++u) {
+          const float w = wv[u];
+          const float4* h = reinterpret_cast<const float4*>(s_h + (k0 + u) * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 hv = h[q];
+            acc[4 * q] = fmaf(w, hv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(w, hv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(w, hv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, hv.w, acc[4 * q + 3]);
+          }
         }
       }
 #pragma unroll

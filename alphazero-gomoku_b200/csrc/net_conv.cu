@@ -18,7 +18,7 @@
 //   * accumulators live in TMEM (2 x C columns, double buffered) so the epilogue of board i
 //     overlaps the MMAs of board i+1;
 //   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator,
-//     warps 2-5 epilogue (TMEM -> registers -> scale/shift (+residual) -> ReLU -> bf16 -> HBM).
+//     warps 2-9 epilogue (TMEM -> registers -> shift (+residual) -> ReLU -> bf16 -> HBM).
 #include <cuda_bf16.h>
 #include "net.h"
 #include "ptx.cuh"
@@ -27,7 +27,7 @@ namespace {
 
 constexpr int kCopyRows = 160;                 // 128 tile rows + 16 above + 16 below
 constexpr int kStageBytes = kCopyRows * 128;   // one 64-channel slice of one shifted copy
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 
 template <int C>
 struct Cfg {
@@ -79,7 +79,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-      for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 8); }
+      for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 16); }
       ptx::mbar_init(bfull, 1);
       ptx::fence_barrier_init();
     }
@@ -124,12 +124,16 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer (leader CTA, one thread) ==============================
-    if (rank == 0 && lane == 0) {
+    // ============================== MMA issuer (leader CTA) ==============================
+    // The whole warp runs this loop so that every descriptor / stage / phase value is provably
+    // warp-uniform (kept in uniform registers, no per-MMA R2UR round trips); one elected lane
+    // issues the tcgen05 instructions and the commits.
+    if (rank == 0) {
       constexpr uint32_t idesc = ptx::idesc_bf16(256, C);
-      const uint32_t a_base = ptx::smem_u32(sA), b_base = ptx::smem_u32(sB);
+      const uint64_t a_desc0 = ptx::smem_desc_sw128(ptx::smem_u32(sA));
+      const uint64_t b_desc0 = ptx::smem_desc_sw128(ptx::smem_u32(sB));
       bool ok = ptx::mbar_wait(bfull, 0);
-      if (!ok) atomicExch(p.error, ERR_BFULL);
+      if (!ok && lane == 0) atomicExch(p.error, ERR_BFULL);
       int stage = 0, it = 0;
       uint32_t phase = 0;
       long long t_full = 0, t_tempty = 0;
@@ -137,32 +141,37 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
         const int acc = it & 1;
         long long t0 = clock64();
-        if (!ptx::mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u)) { atomicExch(p.error, ERR_TEMPTY); ok = false; break; }
+        if (!ptx::mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u)) { if (lane == 0) atomicExch(p.error, ERR_TEMPTY); ok = false; break; }
         t_tempty += clock64() - t0;
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C);
         for (int kc = 0; kc < K::KC && ok; ++kc)
           for (int dci = 0; dci < 3; ++dci) {
             t0 = clock64();
-            if (!ptx::mbar_wait(&full[stage], phase)) { atomicExch(p.error, ERR_FULL); ok = false; break; }
+            if (!ptx::mbar_wait(&full[stage], phase)) { if (lane == 0) atomicExch(p.error, ERR_FULL); ok = false; break; }
             t_full += clock64() - t0;
             ptx::tc_fence_after();
+            const uint64_t a_stage = a_desc0 + (uint64_t)((stage * kStageBytes) >> 4);
+            const uint64_t b_slice = b_desc0 + (uint64_t)(((dci * K::KC + kc) * K::BBLK) >> 4);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int dri = 0; dri < 3; ++dri) {
-              const int tap = dri * 3 + dci;
+              for (int dri = 0; dri < 3; ++dri) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = ptx::smem_desc_sw128(a_base + stage * kStageBytes + dri * 2048 + k * 32);
-                const uint64_t bd = ptx::smem_desc_sw128(b_base + (tap * K::KC + kc) * K::BBLK + k * 32);
-                ptx::umma_bf16<2>(tmem_d, ad, bd, idesc, (kc | dci | dri | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = a_stage + (uint64_t)((dri * 2048 + k * 32) >> 4);
+                  const uint64_t bd = b_slice + (uint64_t)((dri * 3 * K::KC * K::BBLK + k * 32) >> 4);
+                  ptx::umma_bf16<2>(tmem_d, ad, bd, idesc, (kc | dci | dri | k) != 0 ? 1u : 0u);
+                }
               }
+              ptx::umma_commit_pair(&empty[stage], 3);        // frees the stage in both CTAs
             }
-            ptx::umma_commit_pair(&empty[stage], 3);        // frees the stage in both CTAs
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-        if (ok) ptx::umma_commit_pair(&tfull[acc], 3);       // accumulator ready in both CTAs
+        if (ok && ptx::elect_one()) ptx::umma_commit_pair(&tfull[acc], 3);       // accumulator ready in both CTAs
+        __syncwarp();
       }
-      if (p.prof) {
+      if (p.prof && lane == 0) {
         atomicAdd(p.prof + 0, (unsigned long long)t_full);
         atomicAdd(p.prof + 1, (unsigned long long)t_tempty);
         atomicAdd(p.prof + 2, (unsigned long long)(clock64() - t_begin));
@@ -170,8 +179,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       }
     }
   } else {
-    // ============================== epilogue (warps 2..5, both CTAs) ==============================
+    // ============================== epilogue (warps 2..9, both CTAs) ==============================
+    // Two warps per TMEM lane quadrant; each takes half of the channels of its 32 rows.
     const int quad = warp & 3;
+    const int ch0 = ((warp - 2) >> 2) * (C / 2);
     const int row = quad * 32 + lane;
     const int qi = (int)rank * 128 + row;
     const bool pad = (qi < 16) || ((qi & 15) == 15);
@@ -181,28 +192,33 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     const long long t_begin = clock64();
     for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
       const int acc = it & 1;
+      const size_t grow = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)qi;
+      __nv_bfloat16* orow = p.out + grow * C;
+      const __nv_bfloat16* rrow = p.residual ? p.residual + grow * C : nullptr;
+      // the residual row is fetched while the MMAs of this board are still running
+      uint32_t res[C / 4];
+      if (rrow) {
+#pragma unroll
+        for (int j = 0; j < C / 32; ++j) ptx::ldg256(rrow + ch0 + 16 * j, &res[8 * j]);
+      }
       const long long t0 = clock64();
       if (!ptx::mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u)) { atomicExch(p.error, ERR_TFULL); ok = false; break; }
       t_tfull += clock64() - t0;
       ptx::tc_fence_after();
-      const size_t grow = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)qi;
-      __nv_bfloat16* orow = p.out + grow * C;
-      const __nv_bfloat16* rrow = p.residual ? p.residual + grow * C : nullptr;
 #pragma unroll
-      for (int ch = 0; ch < C; ch += 32) {
+      for (int cc = 0; cc < C / 2; cc += 32) {
+        const int ch = ch0 + cc;
         uint32_t v[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * C + ch), v);
-        uint32_t res[16];
-        if (rrow) { ptx::ldg256(rrow + ch, &res[0]); ptx::ldg256(rrow + ch + 16, &res[8]); }
         ptx::tmem_ld_wait();
         uint32_t outv[16];
 #pragma unroll
         for (int h = 0; h < 16; ++h) {
-          float y0 = __uint_as_float(v[2 * h]) + shift.v[ch + 2 * h];
-          float y1 = __uint_as_float(v[2 * h + 1]) + shift.v[ch + 2 * h + 1];
+          float y0 = __uint_as_float(v[2 * h]) + (ch0 ? shift.v[C / 2 + cc + 2 * h] : shift.v[cc + 2 * h]);
+          float y1 = __uint_as_float(v[2 * h + 1]) + (ch0 ? shift.v[C / 2 + cc + 2 * h + 1] : shift.v[cc + 2 * h + 1]);
           if (rrow) {
-            y0 += __uint_as_float(res[h] << 16);
-            y1 += __uint_as_float(res[h] & 0xffff0000u);
+            y0 += __uint_as_float(res[cc / 2 + h] << 16);
+            y1 += __uint_as_float(res[cc / 2 + h] & 0xffff0000u);
           }
           if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
           if (pad) { y0 = 0.f; y1 = 0.f; }
@@ -216,7 +232,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
     }
-    if (p.prof && rank == 0 && warp == 2 && lane == 0) {
+    if (p.prof && rank == 0 && warp == 2 && lane == 0) {   // one representative epilogue warp
       atomicAdd(p.prof + 5, (unsigned long long)t_tfull);
       atomicAdd(p.prof + 6, (unsigned long long)(clock64() - t_begin));
     }

@@ -88,14 +88,21 @@ __device__ __forceinline__ void node_fill(const azg_dev& e, int g, int node, uin
   }
 }
 
-// First-index argmax of the reference's PUCT score over legal children.
-__device__ __forceinline__ int puct_select(const azg_dev& e, int g, int node, uint32_t legal) {
+// Everything the selection step needs from one node, fetched with ONE round trip: the child
+// arrays (lane L: children 8L..8L+7), the flags, and the stored key for the transposition check.
+struct NodeData {
+  float p[8];
+  int n[8], w[8];
+  uint32_t meta;
+  uint32_t keyw;     // lanes 0..15: key word l of the node
+};
+
+__device__ __forceinline__ void node_load(const azg_dev& e, int g, int node, NodeData& nd) {
   const int l = lane_id();
   const size_t off = azg_node_off(e, g, node);
   const size_t base = off * AZG_ROW;
-  const uint32_t meta = __ldcg(&e.meta[off]);
-  const int slot64 = (int)((meta >> 4) & 15u) - 1;
-  float p[8]; int n[8], w[8];
+  nd.meta = __ldcg(&e.meta[off]);
+  nd.keyw = l < 16 ? __ldcg(&e.key[off * 16 + l]) : 0u;
   if (l < 28) {
     const float4* P = reinterpret_cast<const float4*>(e.P + base + 8 * l);
     const int4* Nn = reinterpret_cast<const int4*>(e.Nv + base + 8 * l);
@@ -103,14 +110,60 @@ __device__ __forceinline__ int puct_select(const azg_dev& e, int g, int node, ui
     const float4 pa = __ldcg(P), pb = __ldcg(P + 1);
     const int4 na = __ldcg(Nn), nb = __ldcg(Nn + 1);
     const int4 wa = __ldcg(Ww), wb = __ldcg(Ww + 1);
-    p[0] = pa.x; p[1] = pa.y; p[2] = pa.z; p[3] = pa.w; p[4] = pb.x; p[5] = pb.y; p[6] = pb.z; p[7] = pb.w;
-    n[0] = na.x; n[1] = na.y; n[2] = na.z; n[3] = na.w; n[4] = nb.x; n[5] = nb.y; n[6] = nb.z; n[7] = nb.w;
-    w[0] = wa.x; w[1] = wa.y; w[2] = wa.z; w[3] = wa.w; w[4] = wb.x; w[5] = wb.y; w[6] = wb.z; w[7] = wb.w;
+    nd.p[0] = pa.x; nd.p[1] = pa.y; nd.p[2] = pa.z; nd.p[3] = pa.w; nd.p[4] = pb.x; nd.p[5] = pb.y; nd.p[6] = pb.z; nd.p[7] = pb.w;
+    nd.n[0] = na.x; nd.n[1] = na.y; nd.n[2] = na.z; nd.n[3] = na.w; nd.n[4] = nb.x; nd.n[5] = nb.y; nd.n[6] = nb.z; nd.n[7] = nb.w;
+    nd.w[0] = wa.x; nd.w[1] = wa.y; nd.w[2] = wa.z; nd.w[3] = wa.w; nd.w[4] = wb.x; nd.w[5] = wb.y; nd.w[6] = wb.z; nd.w[7] = wb.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { p[j] = 0.f; n[j] = 0; w[j] = 0; }
-    if (l == 28) { p[0] = __ldcg(e.P + base + 224); n[0] = __ldcg(e.Nv + base + 224); w[0] = __ldcg(e.W + base + 224); }
+    for (int j = 0; j < 8; ++j) { nd.p[j] = 0.f; nd.n[j] = 0; nd.w[j] = 0; }
+    if (l == 28) { nd.p[0] = __ldcg(e.P + base + 224); nd.n[0] = __ldcg(e.Nv + base + 224); nd.w[0] = __ldcg(e.W + base + 224); }
   }
+}
+
+__device__ __forceinline__ bool node_key_matches(const NodeData& nd, const WPos& p) {
+  const int l = lane_id();
+  const uint32_t x0 = __shfl_sync(AZG_FULL, p.w0, (l & 7) << 2);
+  const uint32_t x1 = __shfl_sync(AZG_FULL, p.w1, (l & 7) << 2);
+  bool ok = ((nd.meta >> 1) & 3u) == (uint32_t)p.player;
+  if (l < 16) ok = ok && nd.keyw == (l < 8 ? x0 : x1);
+  return __all_sync(AZG_FULL, ok);
+}
+
+// Transposition lookup that also fetches the node: the candidate's arrays are requested together
+// with its key, so a hit costs two dependent memory round trips (probe window, node) instead of
+// three.  The full key is always compared (the tag only selects candidates).
+__device__ __forceinline__ int table_find_load(const azg_dev& e, int g, const WPos& p, unsigned long long h, int* ins,
+                                               NodeData& nd) {
+  const unsigned long long* tab = e.slots + (size_t)g * (size_t)e.hcap;
+  const uint32_t tag = (uint32_t)(h >> 32);
+  const int nwin = e.hcap >> 5;
+  int win = (int)((uint32_t)h & (uint32_t)(nwin - 1));
+  const int l = lane_id();
+  for (int t = 0; t < nwin; ++t) {
+    const unsigned long long s = __ldcg(&tab[(win << 5) + l]);
+    uint32_t mm = __ballot_sync(AZG_FULL, s != 0ULL && (uint32_t)(s >> 32) == tag);
+    while (mm) {
+      const int src = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const int node = (int)__shfl_sync(AZG_FULL, (uint32_t)s, src) - 1;
+      node_load(e, g, node, nd);
+      if (node_key_matches(nd, p)) return node;
+    }
+    const uint32_t em = __ballot_sync(AZG_FULL, s == 0ULL);
+    if (em) { *ins = (win << 5) + __ffs(em) - 1; return -1; }
+    win = (win + 1) & (nwin - 1);
+  }
+  *ins = -1;
+  return -1;
+}
+
+// First-index argmax of the reference's PUCT score over legal children.
+__device__ __forceinline__ int puct_select(const azg_dev& e, int g, const NodeData& nd, uint32_t legal) {
+  const int l = lane_id();
+  const int slot64 = (int)((nd.meta >> 4) & 15u) - 1;
+  const float* p = nd.p;
+  const int* n = nd.n;
+  const int* w = nd.w;
   int tot = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) tot += n[j];
@@ -190,12 +243,14 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
 
   while (true) {
     WPos pos;
+    NodeData nd;
     int depth, node = -1, v = 0;
     bool select_here = false;
     if (resume) {
       pos = wpos_load(&ctl->scratch);
       depth = __ldcg(&ctl->depth);
       node = __ldcg(&ctl->resume_node);
+      node_load(e, g, node, nd);
       select_here = true;                       // fall through to selection at the evaluated leaf
       resume = false;
     } else {
@@ -212,7 +267,8 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
         if (!wpos_any_empty(pos)) { v = 0; break; }
         const unsigned long long h = wpos_hash(pos);
         int ins = -1;
-        node = table_find(e, g, pos, h, &ins);
+        if (depth == 0 && root_node >= 0) { node = root_node; node_load(e, g, node, nd); }   // the root key is fixed for the run
+        else node = table_find_load(e, g, pos, h, &ins, nd);
         if (node < 0) {                                        // new_mcts_alpha.py:114-132
           if (ins < 0) { err |= AZG_ERR_HASH; break; }
           if (n_free > 0) node = __ldcg(&freelist[--n_free]);
@@ -237,7 +293,7 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
         }
       }
       select_here = false;
-      const int a = puct_select(e, g, node, wpos_legal_byte(pos));
+      const int a = puct_select(e, g, nd, wpos_legal_byte(pos));
       if (depth >= AZG_MAX_DEPTH) { err |= AZG_ERR_DEPTH; break; }
       if (l == 0) __stcg(&path[depth], ((uint32_t)node << 8) | (uint32_t)a);
       ++depth;

@@ -1,0 +1,308 @@
+"""Self-play -> replay buffer -> train loop on the B200 engine (SURVEY 8f "next" rows).
+
+Keeps the reference's call shapes (train.py of the reference): ``softmax_temperature``,
+``sample_action_from_pi`` (:252-266), ``ReplayBuffer`` (:272-296), ``save_replay_buffer`` /
+``load_replay_buffer`` (:302-354, same pickle dictionary), ``play_game_and_collect`` (:360-412),
+``evaluate_models`` (:418-486) and ``train_alphazero`` with the same keyword arguments (:575-609).
+Self-play inside ``train_alphazero`` runs on the batched device driver (``selfplay.SelfPlay``);
+with ``torch.distributed`` initialised every rank plays its own games, the examples are
+all-gathered and the gradients of ``train_batch`` are all-reduced over NCCL.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import random
+import time
+from collections import deque
+from datetime import datetime
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .games import Gomoku
+from .mcts import MCTS
+from .network import PyTorchModel
+from .selfplay import SelfPlay
+
+GameClass = Gomoku
+
+
+# ------------------------------------------------------------------ sampling helpers (train.py:252-266)
+def softmax_temperature(pi: np.ndarray, temp: float) -> np.ndarray:
+    if temp <= 0:
+        return pi
+    z = np.log(pi + 1e-15) / temp
+    e = np.exp(z - np.max(z))
+    return e / np.sum(e)
+
+
+def sample_action_from_pi(pi: np.ndarray, temp: float) -> int:
+    if temp == 0:
+        return int(np.argmax(pi))
+    p = softmax_temperature(pi, temp)
+    return int(np.random.choice(len(p), p=p))
+
+
+# ------------------------------------------------------------------ replay buffer (train.py:272-354)
+class ReplayBuffer:
+    def __init__(self, capacity: int = 20000):
+        self.capacity = capacity
+        self.buffer = deque(maxlen=capacity)
+
+    def add(self, examples: List[Tuple[np.ndarray, np.ndarray, float]]):
+        for ex in examples:
+            self.buffer.append(ex)
+
+    def add_rows(self, rows: torch.Tensor):
+        """Rows of ``SelfPlay.drain_examples`` (float32[n, 901]) -> (state, pi, z) tuples."""
+        r = rows.detach().cpu().numpy()
+        for x in r:
+            self.buffer.append((x[:675].reshape(3, 15, 15).copy(), x[675:900].copy(), float(x[900])))
+
+    def sample(self, batch_size: int):
+        batch = random.sample(self.buffer, k=batch_size)
+        states, pis, zs = zip(*batch)
+        return (np.stack(states, axis=0).astype(np.float32), np.stack(pis, axis=0).astype(np.float32),
+                np.array(zs, dtype=np.float32).reshape(-1, 1))
+
+    def __len__(self):
+        return len(self.buffer)
+
+
+def save_replay_buffer(buffer: ReplayBuffer, filepath: str):
+    try:
+        with open(filepath, "wb") as f:
+            pickle.dump({"buffer": list(buffer.buffer), "capacity": buffer.capacity}, f, protocol=pickle.HIGHEST_PROTOCOL)
+        print(f"[Buffer] saved: {filepath} ({len(buffer)} samples)")
+        return True
+    except Exception as e:          # the reference prints and carries on
+        print(f"[Buffer] save failed: {e}")
+        return False
+
+
+def load_replay_buffer(filepath: str, capacity: int) -> Optional[ReplayBuffer]:
+    if not os.path.exists(filepath):
+        print(f"[Buffer] no saved buffer: {filepath}")
+        return None
+    try:
+        with open(filepath, "rb") as f:
+            data = pickle.load(f)
+        buf = ReplayBuffer(capacity=capacity)
+        if data.get("capacity", capacity) != capacity:
+            print(f"[Buffer] warning: saved capacity {data.get('capacity')} != configured {capacity}")
+        for item in data["buffer"]:
+            buf.buffer.append(item)
+        print(f"[Buffer] loaded: {filepath} ({len(buf)} samples)")
+        return buf
+    except Exception as e:
+        print(f"[Buffer] load failed: {e}")
+        return None
+
+
+# ------------------------------------------------------------------ one game on the host API (train.py:360-412)
+def play_game_and_collect(mcts: MCTS, game, temp_fn, max_moves=225, use_symmetries=True):
+    examples = []
+    move_number = 0
+    while True:
+        state_enc = game.get_encoded_state()
+        pi = mcts.run(game, len(game.move_history))
+        keep = pi.copy()
+        action = sample_action_from_pi(pi, temp_fn(move_number))
+        if game.get_valid_moves()[action] != 1.0:
+            action = int(np.argmax(pi))
+        examples.append((state_enc, keep, int(game.current_player)))
+        game.do_move(divmod(action, game.size))
+        move_number += 1
+        if game.is_game_over() or move_number >= max_moves:
+            break
+    winner = game.get_winner()
+    out = []
+    for state_enc, pi_vec, player in examples:
+        z = 0.0 if winner == 0 else (1.0 if winner == player else -1.0)
+        if use_symmetries:
+            for s_aug, pi_aug in mcts.symmetries(state_enc, pi_vec):
+                out.append((s_aug.astype(np.float32), pi_aug.astype(np.float32), z))
+        else:
+            out.append((state_enc.astype(np.float32), pi_vec.astype(np.float32), z))
+    return out, winner
+
+
+# ------------------------------------------------------------------ evaluation arena (train.py:418-486)
+def evaluate_models(model_new: PyTorchModel, model_best: PyTorchModel, game_name: str, n_games: int = 20,
+                    n_simulations: int = 100, cpuct: float = 1.0) -> Tuple[int, float, int]:
+    new_wins = draws = 0
+    for i in range(n_games):
+        game = GameClass(size=model_new.board_size)
+        center, radius = model_new.board_size // 2, 4
+        game.do_move((random.randint(center - radius, center + radius), random.randint(center - radius, center + radius)))
+        new_starts = i % 2 == 0
+        move_number = 1
+        mcts_new = MCTS(GameClass, n_simulations, model_new, cpuct=cpuct, add_dirichlet_noise=False)
+        mcts_best = MCTS(GameClass, n_simulations, model_best, cpuct=cpuct, add_dirichlet_noise=False)
+        while not game.is_game_over():
+            mine = (game.current_player == 1 and new_starts) or (game.current_player == 2 and not new_starts)
+            pi = (mcts_new if mine else mcts_best).run(game, len(game.move_history))
+            game.do_move(divmod(int(np.argmax(pi)), game.size))
+            move_number += 1
+            if move_number > game.size * game.size:
+                break
+        winner = game.get_winner()
+        if winner == 0:
+            draws += 1
+        elif (winner == 1 and new_starts) or (winner == 2 and not new_starts):
+            new_wins += 1
+        mcts_new.engine.close()
+        mcts_best.engine.close()
+    return new_wins, new_wins / float(n_games), draws
+
+
+# ------------------------------------------------------------------ data-parallel helpers
+def _world():
+    return (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
+
+
+def gather_rows(rows: torch.Tensor) -> torch.Tensor:
+    """All-gather variable-length example rows [n_r, 901] from every rank (padded, with counts)."""
+    world, _ = _world()
+    if world == 1:
+        return rows
+    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    m = int(max(int(c.item()) for c in counts))
+    pad = torch.zeros((m, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    pad[: rows.shape[0]] = rows
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[: int(c.item())] for p, c in zip(parts, counts)], dim=0)
+
+
+def train_batch_dp(model: PyTorchModel, states, pis, zs) -> dict:
+    """``PyTorchModel.train_batch`` (network.py:199-235: KLDiv(batchmean) + MSE, clip 3.0, Adam) on this
+    rank's micro-batch with the gradients averaged over all ranks before the clip and the step, so
+    every rank applies the identical update."""
+    world, _ = _world()
+    if world == 1:
+        return model.train_batch(states, pis, zs, epochs=1)
+    net, dev = model.net, model.device
+    to = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.asarray(a, dtype=np.float32))).to(dev, torch.float32)
+    net.train()
+    model.optimizer.zero_grad()
+    logits, values = net(to(states))
+    pl = model.policy_loss_fn(F.log_softmax(logits, dim=1), to(pis))
+    vl = model.value_loss_fn(values, to(zs))
+    loss = pl + vl
+    loss.backward()
+    grads = [p.grad for p in net.parameters() if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= world
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+    torch.nn.utils.clip_grad_norm_(net.parameters(), 3.0)
+    model.optimizer.step()
+    return {"policy_loss": float(pl.item()), "value_loss": float(vl.item()), "total_loss": float(loss.item())}
+
+
+def broadcast_model(model: PyTorchModel, src: int = 0):
+    world, _ = _world()
+    if world == 1:
+        return
+    for t in list(model.net.parameters()) + list(model.net.buffers()):
+        dist.broadcast(t.data, src)
+
+
+# ------------------------------------------------------------------ the training loop (train.py:575-842)
+def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterations: int = 5, games_per_iteration: int = 8,
+                    n_simulations: int = 50, buffer_size: int = 10000, batch_size: int = 128, epochs_per_iter: int = 2,
+                    temp_threshold: int = 8, eval_games: int = 12, eval_mcts_simulations: int = 200,
+                    win_rate_threshold: float = 0.55, cpuct: float = 1.2, model_dir: str = "models", save_every: int = 1,
+                    pretrained_model_path: Optional[str] = None, next_iteration_continuation: int = 1,
+                    dirichlet_alpha: float = 0.03, dirichlet_epsilon: float = 0.25, dirichlet_n_moves: int = 30,
+                    selfplay_num_workers: int = 0, selfplay_device: str = "cpu", selfplay_games_per_task: int = 1,
+                    selfplay_base_seed: int = 12345, selfplay_torch_threads: int = 1, eval_num_workers: int = 0,
+                    eval_device: str = "cpu", eval_games_per_task: int = 1, eval_base_seed: int = 54321,
+                    eval_torch_threads: int = 1, n_res_blocks: int = 3, channels: int = 64, concurrent_games: int = 0):
+    """Same keyword arguments as the reference (the multiprocessing ones are accepted and ignored:
+    the process pool is replaced by device batching); ``n_res_blocks`` / ``channels`` /
+    ``concurrent_games`` are engine extras.  Returns the best model."""
+    world, rank = _world()
+    dev = f"cuda:{torch.cuda.current_device()}"
+    os.makedirs(model_dir, exist_ok=True)
+    mk = lambda: PyTorchModel(board_size=board_size, device=dev, n_res_blocks=n_res_blocks, channels=channels)
+    model_best, model_candidate = mk(), mk()
+    if pretrained_model_path and os.path.exists(pretrained_model_path):
+        model_best.load(pretrained_model_path)
+    broadcast_model(model_best)
+    model_candidate.net.load_state_dict(model_best.net.state_dict())
+    model_candidate.optimizer.load_state_dict(model_best.optimizer.state_dict())
+    buffer_path = os.path.join(model_dir, "replay_buffer_latest.pkl")
+    buffer = load_replay_buffer(buffer_path, buffer_size) or ReplayBuffer(capacity=buffer_size)
+    my_games = (games_per_iteration + world - 1) // world
+    G = concurrent_games or min(my_games, 2048)
+    for it in range(next_iteration_continuation, next_iteration_continuation + num_iterations):
+        t0 = time.time()
+        if rank == 0:
+            print(f"\n=== ITER {it}: self-play (games={games_per_iteration}, sims={n_simulations}) {datetime.now():%Y-%m-%d %H:%M:%S} ===")
+        sp = SelfPlay(model_candidate, rule=0, n_games=G, n_sims=n_simulations, cpuct=cpuct, noise=True,
+                      alpha=dirichlet_alpha, eps=dirichlet_epsilon, noise_plies=dirichlet_n_moves,
+                      temp_threshold=float(temp_threshold), max_moves=board_size * board_size,
+                      example_capacity=max(my_games, G) * 225 * 8, seed=selfplay_base_seed + rank * 100003 + it,
+                      node_capacity=max(4096, 4 * n_simulations), device=dev)
+        finished = 0
+        winners = {0: 0, 1: 0, 2: 0}
+        while finished < my_games:
+            sp.step()
+            w = sp.winners[sp.done.bool()].cpu().tolist()
+            for x in w:
+                winners[int(x)] = winners.get(int(x), 0) + 1
+            finished += len(w)
+        rows = gather_rows(sp.drain_examples())
+        sp.close()
+        buffer.add_rows(rows)
+        if rank == 0:
+            print(f"[self-play] {finished * world} games, {rows.shape[0]} examples, winners {winners}, {(time.time() - t0) / 60:.2f} min")
+        # ---- training (train.py:754-763): every rank draws the same batches (shared seed) and takes its slice
+        n_batches = len(buffer) // batch_size
+        rng_state = random.getstate()
+        random.seed(1000003 * it + 17)
+        for ep in range(epochs_per_iter):
+            tot = 0.0
+            for _ in range(n_batches):
+                states, pis, zs = buffer.sample(batch_size)
+                sl = slice(rank * batch_size // world, (rank + 1) * batch_size // world)
+                tot += train_batch_dp(model_candidate, states[sl], pis[sl], zs[sl])["total_loss"]
+            if rank == 0 and n_batches:
+                print(f"[train] epoch {ep + 1}/{epochs_per_iter} mean loss {tot / n_batches:.4f}")
+        random.setstate(rng_state)
+        # ---- evaluation and accept / reject (train.py:768-827), rank 0 decides
+        accept = torch.zeros(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            try:
+                new_wins, win_rate, draws = evaluate_models(model_candidate, model_best, game_name, n_games=eval_games,
+                                                            n_simulations=eval_mcts_simulations, cpuct=cpuct)
+            except Exception as e:      # the reference prints and continues with win_rate 0
+                print(f"[eval] failed: {e}")
+                new_wins, win_rate, draws = 0, 0.0, 0
+            print(f"[eval] new model wins {new_wins}/{eval_games} (draws {draws}) win rate {win_rate:.3f}")
+            accept[0] = int(win_rate >= win_rate_threshold)
+        if world > 1:
+            dist.broadcast(accept, 0)
+        if int(accept.item()):
+            model_best.net.load_state_dict(model_candidate.net.state_dict())
+            model_best.optimizer.load_state_dict(model_candidate.optimizer.state_dict())
+        else:
+            model_candidate.net.load_state_dict(model_best.net.state_dict())
+            model_candidate.optimizer.load_state_dict(model_best.optimizer.state_dict())
+        if rank == 0 and it % save_every == 0:
+            model_best.save(os.path.join(model_dir, f"snapshot_iter{it}_{datetime.now():%Y%m%d_%H%M%S}.pt"))
+            save_replay_buffer(buffer, buffer_path)
+        if rank == 0:
+            print(f"=== ITER {it} done in {(time.time() - t0) / 60:.2f} min ===")
+    return model_best

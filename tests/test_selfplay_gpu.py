@@ -101,9 +101,10 @@ def test_examples_labels_and_symmetries():
     n = int(cursor.item())
     assert n == 2 * len(moves0) * 8
     rows = out[:n].cpu().numpy()
-    # rows of a game are contiguous (one reservation per game); find each game's block by its first plane
+    # rows of a game are contiguous (one atomic reservation per game, in either order); the first
+    # ply's pi tells the two games apart (their first positions are both the empty board)
     blocks = [rows[:n // 2], rows[n // 2:]]
-    if not np.array_equal(blocks[0][0, :675].reshape(3, 15, 15), expected[0][0][0]):
+    if not np.array_equal(blocks[0][0, 675:900], expected[0][0][1]):
         blocks = blocks[::-1]
     for g in range(G):
         k = 0

@@ -52,7 +52,7 @@ struct azg_ctl {
 
 // Engine-wide device view handed to kernels by value.
 struct azg_dev {
-  int32_t G, rule, queue_len, cap, hcap, noise_on, noise_plies, n_sims;
+  int32_t G, rule, queue_len, cap, hcap, noise_on, noise_plies, n_sims, game_base;
   float cpuct;
   double eps, alpha, cpuct64;   // cpuct64: the Python float the reference multiplies with at a float64 root
   unsigned long long seed;

@@ -67,7 +67,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
   int h = 64;
   while (h < 2 * cfg->node_capacity) h <<= 1;
   d.hcap = h;
-  d.noise_on = cfg->noise_on; d.noise_plies = cfg->noise_plies; d.n_sims = 0;
+  d.noise_on = cfg->noise_on; d.noise_plies = cfg->noise_plies; d.n_sims = 0; d.game_base = cfg->game_base;
   d.cpuct = (float)cfg->cpuct; d.cpuct64 = cfg->cpuct; d.eps = cfg->eps; d.alpha = cfg->alpha; d.seed = cfg->seed;
   const size_t G = d.G, C = d.cap;
   int rc = AZG_OK;

@@ -18,7 +18,9 @@ struct ConvArgs {
   int relu;
   const float* shift_host;        // HOST [C]: folded BatchNorm shift of this layer (the scale lives in the weights)
   const __nv_bfloat16* residual;  // padded activation buffer added before the ReLU, or null
-  __nv_bfloat16* out;             // padded activation buffer
+  __nv_bfloat16* out;             // padded activation buffer (null: do not store, fused-heads layer only)
+  const float* head_host;         // HOST [3*C + 6]: fused 1x1 head weights, BN scale[3], shift[3]; null = plain layer
+  float* hidden;                  // head features, tiled [b/32][676][32] (fused-heads layer only)
   int* error;                     // device flag set by the pipeline watchdogs
   unsigned long long* prof;       // optional device counters [8] (cycles spent waiting per role), or null
 };
@@ -58,7 +60,7 @@ struct HeadArgs {
   float* values;                  // [n] (may be null)
   float* logits;                  // [n][225] optional raw logits (may be null)
 };
-int azg_heads_launch(int C, const HeadArgs& a, int n_sm, cudaStream_t stream);
+int azg_heads_launch(int C, const HeadArgs& a, int n_sm, cudaStream_t stream, bool skip_head1);
 
 struct PackArgs {
   int C, n_blocks;

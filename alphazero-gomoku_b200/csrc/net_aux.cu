@@ -363,16 +363,19 @@ __global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
   }
 }
 
-int azg_heads_launch(int C, const HeadArgs& a, int n_sm, cudaStream_t stream) {
+int azg_heads_launch(int C, const HeadArgs& a, int n_sm, cudaStream_t stream, bool skip_head1) {
   int grid = n_sm * 4;
   if (grid > a.max_boards) grid = a.max_boards;
   if (grid < 1) grid = 1;
-  if (C == 64) head1_kernel<64><<<grid, 256, 0, stream>>>(a);
-  else if (C == 128) head1_kernel<128><<<grid, 256, 0, stream>>>(a);
-  else if (C == 256) head1_kernel<256><<<grid, 256, 0, stream>>>(a);
-  else return azg_fail(AZG_E_ARG, "heads: channels must be 64, 128 or 256");
-  int rc = azg_check_launch("head1_kernel");
-  if (rc) return rc;
+  int rc = AZG_OK;
+  if (!skip_head1) {          // the 1x1 convs are normally fused into the last trunk layer's epilogue
+    if (C == 64) head1_kernel<64><<<grid, 256, 0, stream>>>(a);
+    else if (C == 128) head1_kernel<128><<<grid, 256, 0, stream>>>(a);
+    else if (C == 256) head1_kernel<256><<<grid, 256, 0, stream>>>(a);
+    else return azg_fail(AZG_E_ARG, "heads: channels must be 64, 128 or 256");
+    rc = azg_check_launch("head1_kernel");
+    if (rc) return rc;
+  }
   cudaError_t e = cudaFuncSetAttribute(head2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHead2Smem);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
   int tiles = (a.max_boards + 31) / 32;

@@ -46,12 +46,21 @@ struct ConvShift {
   float v[C];
 };
 
+// 1x1 head convolutions fused into the epilogue of the last trunk layer (network.py:102-104,
+// 109-111): rows 0-1 policy_conv, row 2 value_conv, with their folded BatchNorm.
+template <int C>
+struct HeadConst {
+  float w[3][C];
+  float scale[3];
+  float shift[3];
+};
+
 enum { ERR_BFULL = 1, ERR_EMPTY = 2, ERR_FULL = 3, ERR_TEMPTY = 4, ERR_TFULL = 5 };
 
-template <int C>
+template <int C, bool HEADS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w, ConvArgs p,
-                    const __grid_constant__ ConvShift<C> shift) {
+                    const __grid_constant__ ConvShift<C> shift, const __grid_constant__ HeadConst<HEADS ? C : 1> head) {
   using K = Cfg<C>;
   constexpr int kStages = K::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -180,9 +189,14 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     }
   } else {
     // ============================== epilogue (warps 2..9, both CTAs) ==============================
-    // Two warps per TMEM lane quadrant; each takes half of the channels of its 32 rows.
+    // Two warps per TMEM lane quadrant; each takes half of the channels of its 32 rows.  In the
+    // fused-heads variant (last layer) one warp per quadrant takes all channels of its rows so
+    // that the three head dot products stay inside a thread; the other warp only signals.
     const int quad = warp & 3;
-    const int ch0 = ((warp - 2) >> 2) * (C / 2);
+    const int half = (warp - 2) >> 2;
+    constexpr int NCH = HEADS ? C : C / 2;           // channels handled by a working warp
+    const int ch0 = HEADS ? 0 : half * (C / 2);
+    const bool working = !HEADS || half == 0;
     const int row = quad * 32 + lane;
     const int qi = (int)rank * 128 + row;
     const bool pad = (qi < 16) || ((qi & 15) == 15);
@@ -193,40 +207,61 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
       const int acc = it & 1;
       const size_t grow = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)qi;
-      __nv_bfloat16* orow = p.out + grow * C;
-      const __nv_bfloat16* rrow = p.residual ? p.residual + grow * C : nullptr;
+      __nv_bfloat16* orow = p.out ? p.out + grow * C : nullptr;
+      const __nv_bfloat16* rrow = (p.residual && working) ? p.residual + grow * C : nullptr;
       // the residual row is fetched while the MMAs of this board are still running
-      uint32_t res[C / 4];
+      uint32_t res[NCH / 2];
       if (rrow) {
 #pragma unroll
-        for (int j = 0; j < C / 32; ++j) ptx::ldg256(rrow + ch0 + 16 * j, &res[8 * j]);
+        for (int j = 0; j < NCH / 16; ++j) ptx::ldg256(rrow + ch0 + 16 * j, &res[8 * j]);
       }
       const long long t0 = clock64();
       if (!ptx::mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u)) { atomicExch(p.error, ERR_TFULL); ok = false; break; }
       t_tfull += clock64() - t0;
       ptx::tc_fence_after();
+      if (working) {
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < C / 2; cc += 32) {
-        const int ch = ch0 + cc;
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * C + ch), v);
-        ptx::tmem_ld_wait();
-        uint32_t outv[16];
+        for (int cc = 0; cc < NCH; cc += 32) {
+          const int ch = ch0 + cc;
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * C + ch), v);
+          ptx::tmem_ld_wait();
+          uint32_t outv[16];
 #pragma unroll
-        for (int h = 0; h < 16; ++h) {
-          float y0 = __uint_as_float(v[2 * h]) + (ch0 ? shift.v[C / 2 + cc + 2 * h] : shift.v[cc + 2 * h]);
-          float y1 = __uint_as_float(v[2 * h + 1]) + (ch0 ? shift.v[C / 2 + cc + 2 * h + 1] : shift.v[cc + 2 * h + 1]);
-          if (rrow) {
-            y0 += __uint_as_float(res[cc / 2 + h] << 16);
-            y1 += __uint_as_float(res[cc / 2 + h] & 0xffff0000u);
+          for (int h = 0; h < 16; ++h) {
+            float y0 = __uint_as_float(v[2 * h]) + ((!HEADS && half) ? shift.v[(C / 2 + cc + 2 * h) % C] : shift.v[cc + 2 * h]);
+            float y1 = __uint_as_float(v[2 * h + 1]) + ((!HEADS && half) ? shift.v[(C / 2 + cc + 2 * h + 1) % C] : shift.v[cc + 2 * h + 1]);
+            if (rrow) {
+              y0 += __uint_as_float(res[cc / 2 + h] << 16);
+              y1 += __uint_as_float(res[cc / 2 + h] & 0xffff0000u);
+            }
+            if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            if (pad) { y0 = 0.f; y1 = 0.f; }
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
+            outv[h] = *reinterpret_cast<const uint32_t*>(&pk);
+            if constexpr (HEADS) {
+              // the heads see the bf16-rounded activations, exactly like the unfused path
+              const float z0 = __uint_as_float(outv[h] << 16), z1 = __uint_as_float(outv[h] & 0xffff0000u);
+              d0 = fmaf(z0, head.w[0][cc + 2 * h], d0); d0 = fmaf(z1, head.w[0][cc + 2 * h + 1], d0);
+              d1 = fmaf(z0, head.w[1][cc + 2 * h], d1); d1 = fmaf(z1, head.w[1][cc + 2 * h + 1], d1);
+              d2 = fmaf(z0, head.w[2][cc + 2 * h], d2); d2 = fmaf(z1, head.w[2][cc + 2 * h + 1], d2);
+            }
           }
-          if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-          if (pad) { y0 = 0.f; y1 = 0.f; }
-          const __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
-          outv[h] = *reinterpret_cast<const uint32_t*>(&pk);
+          if (orow) {
+            ptx::stg256(orow + ch, &outv[0]);
+            ptx::stg256(orow + ch + 16, &outv[8]);
+          }
         }
-        ptx::stg256(orow + ch, &outv[0]);
-        ptx::stg256(orow + ch + 16, &outv[8]);
+        if constexpr (HEADS) {
+          if (!pad) {
+            const int pix = ((qi >> 4) - 1) * 15 + (qi & 15);
+            float* hid = p.hidden + (size_t)(b >> 5) * AZG_HIDDEN_TILE + (b & 31);
+            hid[(size_t)pix * 32] = fmaxf(fmaf(d0, head.scale[0], head.shift[0]), 0.f);
+            hid[(size_t)(225 + pix) * 32] = fmaxf(fmaf(d1, head.scale[1], head.shift[1]), 0.f);
+            hid[(size_t)(450 + pix) * 32] = fmaxf(fmaf(d2, head.scale[2], head.shift[2]), 0.f);
+          }
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -244,17 +279,28 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   if (warp == 1) ptx::tmem_dealloc<2>(tmem_base, K::TMEM_COLS);
 }
 
-template <int C>
+template <int C, bool HEADS>
 int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm, cudaStream_t stream) {
   using K = Cfg<C>;
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<C, HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
   int grid = n_sm & ~1;
   const int want = 2 * args.max_boards;
   if (grid > want) grid = want < 2 ? 2 : want;
   ConvShift<C> shift;
   for (int i = 0; i < C; ++i) shift.v[i] = args.shift_host[i];
-  conv3x3_pair_kernel<C><<<grid, kThreads, K::SMEM, stream>>>(tm_act, tm_w, args, shift);
+  HeadConst<HEADS ? C : 1> head;
+  if constexpr (HEADS) {
+    for (int r = 0; r < 3; ++r) {
+      for (int i = 0; i < C; ++i) head.w[r][i] = args.head_host[r * C + i];
+      head.scale[r] = args.head_host[3 * C + r];
+      head.shift[r] = args.head_host[3 * C + 3 + r];
+    }
+  } else {
+    head.w[0][0] = head.w[1][0] = head.w[2][0] = 0.f;
+    for (int r = 0; r < 3; ++r) head.scale[r] = head.shift[r] = 0.f;
+  }
+  conv3x3_pair_kernel<C, HEADS><<<grid, kThreads, K::SMEM, stream>>>(tm_act, tm_w, args, shift, head);
   return azg_check_launch("conv3x3_pair_kernel");
 }
 
@@ -262,7 +308,8 @@ int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvAr
 
 int azg_conv3x3_launch(int C, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm,
                        cudaStream_t stream) {
-  if (C == 128) return launch_conv<128>(tm_act, tm_w, args, n_sm, stream);
-  if (C == 64) return launch_conv<64>(tm_act, tm_w, args, n_sm, stream);
+  const bool heads = args.head_host != nullptr;
+  if (C == 128) return heads ? launch_conv<128, true>(tm_act, tm_w, args, n_sm, stream) : launch_conv<128, false>(tm_act, tm_w, args, n_sm, stream);
+  if (C == 64) return heads ? launch_conv<64, true>(tm_act, tm_w, args, n_sm, stream) : launch_conv<64, false>(tm_act, tm_w, args, n_sm, stream);
   return azg_fail(AZG_E_ARG, "conv3x3: resident-weight kernel supports 64 or 128 channels");
 }

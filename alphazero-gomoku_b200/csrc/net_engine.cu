@@ -32,6 +32,7 @@ struct azg_net {
   int profiling = 0;
   std::vector<cudaEvent_t> ev;          // start/stop pairs
   std::vector<float> shift_host;        // [2*n_blocks][C] folded BatchNorm shifts of the 3x3 layers
+  std::vector<float> head_host;         // [3*C + 6] 1x1 head weights + folded BN scale[3], shift[3]
   size_t ev_used = 0;
   long long prof_launches = 0;
 };
@@ -166,6 +167,10 @@ extern "C" int azg_net_load(azg_net* n, const azg_net_weights* w, void* stream_)
   n->shift_host.resize((size_t)2 * n->n_blocks * C + 1);
   if (n->n_blocks > 0)
     AZG_CUDA(cudaMemcpyAsync(n->shift_host.data(), n->shift3, (size_t)2 * n->n_blocks * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+  n->head_host.resize((size_t)3 * C + 6);
+  AZG_CUDA(cudaMemcpyAsync(n->head_host.data(), n->head_w1, (size_t)3 * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+  AZG_CUDA(cudaMemcpyAsync(n->head_host.data() + 3 * C, n->head_scale1, 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  AZG_CUDA(cudaMemcpyAsync(n->head_host.data() + 3 * C + 3, n->head_shift1, 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
   AZG_CUDA(cudaStreamSynchronize(s));
   n->loaded = 1;
   return AZG_OK;
@@ -181,6 +186,7 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
   stem.n_boards = n_ptr; stem.max_boards = max_boards; stem.w = n->stem_w; stem.shift = n->stem_shift; stem.out = n->act[0];
   if ((rc = azg_stem_launch(C, stem, n->n_sm, s))) return rc;
   int x = 0, t = 1, y = 2;
+  bool fused_heads = false;
   cudaEvent_t ev_stop = nullptr;
   if (n->profiling && n_layers > 0) {
     if (n->ev_used + 2 > n->ev.size()) {
@@ -198,8 +204,11 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
     ConvArgs a;
     a.n_boards = n_ptr; a.max_boards = max_boards; a.layer = l; a.relu = 1;
     a.shift_host = n->shift_host.data() + (size_t)l * C; a.error = n->error_dev; a.prof = n->profiling ? n->prof_dev : nullptr;
+    a.head_host = nullptr; a.hidden = nullptr;
+    const bool fuse = heads && l == n_layers - 1 && (l & 1) == 1;     // last conv2: fuse the 1x1 head convs, skip the store
+    if (fuse) { a.head_host = n->head_host.data(); a.hidden = n->hidden; fused_heads = true; }
     if ((l & 1) == 0) { a.residual = nullptr; a.out = n->act[t]; rc = azg_conv3x3_launch(C, n->tm_act[x], n->tm_w, a, n->n_sm, s); }
-    else { a.residual = n->act[x]; a.out = n->act[y]; rc = azg_conv3x3_launch(C, n->tm_act[t], n->tm_w, a, n->n_sm, s); int tmp = x; x = y; y = tmp; }
+    else { a.residual = n->act[x]; a.out = fuse ? nullptr : n->act[y]; rc = azg_conv3x3_launch(C, n->tm_act[t], n->tm_w, a, n->n_sm, s); int tmp = x; x = y; y = tmp; }
     if (rc) return rc;
   }
   if (ev_stop) cudaEventRecord(ev_stop, s);
@@ -210,7 +219,7 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
     h.n_boards = n_ptr; h.max_boards = max_boards; h.act = n->act[last]; h.w1 = n->head_w1; h.scale1 = n->head_scale1;
     h.shift1 = n->head_shift1; h.hidden = n->hidden; h.pol_wt = n->pol_wt; h.pol_b = n->pol_b; h.v1_wt = n->v1_wt;
     h.v1_b = n->v1_b; h.v2_w = n->v2_w; h.v2_b = n->v2_b; h.probs = probs; h.values = values; h.logits = logits;
-    if ((rc = azg_heads_launch(C, h, n->n_sm, s))) return rc;
+    if ((rc = azg_heads_launch(C, h, n->n_sm, s, fused_heads))) return rc;
   }
   return AZG_OK;
 }

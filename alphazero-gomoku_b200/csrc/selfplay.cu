@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) noise_kernel(azg_dev e, unsigned long lon
     const int a = l + 32 * j;
     lg[j] = -INFINITY;
     if (a < AZG_A) {
-      Philox rng(e.seed ^ 0xD1B54A32D192ED03ULL, (uint32_t)g, (uint32_t)a, (uint32_t)draw);
+      Philox rng(e.seed ^ 0xD1B54A32D192ED03ULL, (uint32_t)(g + e.game_base), (uint32_t)a, (uint32_t)draw);
       lg[j] = log_gamma_variate(rng, e.alpha);
       mx = fmax(mx, lg[j]);
     }
@@ -127,7 +127,7 @@ choose_kernel(azg_dev e, azg_selfplay_buf sp, const float* __restrict__ pi, floa
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1) { const float o = __shfl_up_sync(AZG_FULL, incl, s); if (l >= s) incl += o; }
     const float total = __shfl_sync(AZG_FULL, incl, 31);
-    Philox rng(e.seed ^ 0x8CB92BA72F3D8DD7ULL, (uint32_t)g, (uint32_t)ply, (uint32_t)draw);
+    Philox rng(e.seed ^ 0x8CB92BA72F3D8DD7ULL, (uint32_t)(g + e.game_base), (uint32_t)ply, (uint32_t)draw);
     const uint4 r = rng.next();
     const float u = (float)(rng.uniform53(r.x, r.y) * (double)total);
     float run = incl - mine;

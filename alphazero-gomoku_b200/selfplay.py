@@ -25,12 +25,14 @@ class SelfPlay:
     def __init__(self, model, rule: int = 0, n_games: int = 2048, n_sims: int = 800, cpuct: float = 1.0,
                  queue_len: int = 32, node_capacity: int = 8192, noise: bool = True, alpha: float = 0.05,
                  eps: float = 0.15, noise_plies: int = 10, temp_threshold: float = 10.0, max_moves: int = 225,
-                 use_symmetries: bool = True, example_capacity: int = 1 << 20, seed: int = 12345, device="cuda:0"):
+                 use_symmetries: bool = True, example_capacity: int = 1 << 20, seed: int = 12345, device="cuda:0",
+                 game_base: int = 0):
         self.device = torch.device(device)
         self.G, self.n_sims, self.temp_threshold, self.max_moves = n_games, n_sims, float(temp_threshold), max_moves
         self.use_symmetries = use_symmetries
         self.engine = SearchEngine(rule, n_games, cpuct=cpuct, queue_len=queue_len, node_capacity=node_capacity,
-                                   noise=noise, alpha=alpha, eps=eps, noise_plies=noise_plies, seed=seed, device=device)
+                                   noise=noise, alpha=alpha, eps=eps, noise_plies=noise_plies, seed=seed, device=device,
+                                   game_base=game_base)
         net = model.net if hasattr(model, "net") else model
         self.net = NetEngine(len(net.res_blocks), net.channels, self.device, max_batch=n_games * queue_len)
         self.net.load_state_dict(net.state_dict())

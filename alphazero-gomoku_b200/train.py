@@ -253,7 +253,7 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
         sp = SelfPlay(model_candidate, rule=0, n_games=G, n_sims=n_simulations, cpuct=cpuct, noise=True,
                       alpha=dirichlet_alpha, eps=dirichlet_epsilon, noise_plies=dirichlet_n_moves,
                       temp_threshold=float(temp_threshold), max_moves=board_size * board_size,
-                      example_capacity=max(my_games, G) * 225 * 8, seed=selfplay_base_seed + rank * 100003 + it,
+                      example_capacity=max(my_games, G) * 225 * 8, seed=selfplay_base_seed + it, game_base=rank * G,
                       node_capacity=max(4096, 4 * n_simulations), device=dev)
         finished = 0
         winners = {0: 0, 1: 0, 2: 0}

@@ -225,7 +225,7 @@ def run_ours(args):
     model = PyTorchModel(board_size=15, n_res_blocks=args.blocks, channels=args.channels, device=str(dev))
     sp = SelfPlay(model, rule=rule, n_games=args.games, n_sims=args.sims, cpuct=1.0, queue_len=32,
                   node_capacity=args.node_capacity, noise=True, alpha=0.05, eps=0.15, noise_plies=10, temp_threshold=10.0,
-                  example_capacity=1 << 18, seed=12345 + rank * args.games, device=str(dev))
+                  example_capacity=1 << 18, seed=12345, game_base=rank * args.games, device=str(dev))
     scatter_start(sp, 777 + rank)
 
     def barrier():

@@ -87,7 +87,8 @@ typedef struct azg_config {
   int32_t node_capacity;   /* nodes per game slab */
   int32_t noise_on;        /* add_dirichlet_noise */
   int32_t noise_plies;     /* apply_dirichlet_n_first_moves */
-  int32_t reserved;
+  int32_t game_base;       /* global id of game 0 (rank * G): on-device RNG streams are keyed by the global id, so
+                              results do not depend on how games are sharded over GPUs */
   double cpuct;            /* cpuct */
   double alpha;            /* dirichlet_alpha */
   double eps;              /* epsilon */

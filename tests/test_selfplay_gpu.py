@@ -138,3 +138,52 @@ def test_selfplay_runs_games_to_completion():
     assert torch.allclose(pis.sum(1), torch.ones_like(pis[:, 0]), atol=1e-4)
     assert torch.all(states[:, 2] == 1.0) and torch.all((states[:, 0] * states[:, 1]) == 0)
     sp.close()
+
+
+def test_pente_selfplay_invariants():
+    """BASELINE config 3 (Pente batched self-play) at test size: size-independent properties that
+    must hold at every ply of every game - stones on the board = plies - 2 * captured pairs,
+    capture counters < 5 while the game runs, the side to move alternates."""
+    import alphazero_gomoku_b200 as m
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import SelfPlay
+    torch.manual_seed(1)
+    model = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    sp = SelfPlay(model, rule=1, n_games=128, n_sims=40, node_capacity=4096, example_capacity=1 << 17, temp_threshold=30.0)
+    finished = 0
+    for step in range(90):
+        sp.step()
+        boards, players, lasts, caps, plies = [x.cpu().numpy() for x in sp.engine.rules.unpack(sp.engine.roots())]
+        stones = (boards != 0).sum(1)
+        assert np.array_equal(stones, plies - 2 * caps.sum(1)), step
+        assert (caps < 5).all() and ((players == 1) | (players == 2)).all()
+        assert np.array_equal(players, 1 + (plies % 2))                # player 1 moves on even plies
+        finished += int(sp.done.sum().item())
+    st = sp.engine.stats()
+    assert st["games_in_error"] == 0 and st["dropped_trees"] == 0
+    rows = sp.drain_examples()
+    assert rows.shape[0] % 8 == 0
+    sp.close()
+
+
+def test_results_do_not_depend_on_sharding():
+    """games are independent and the on-device RNG is keyed by the global game id, so
+    16 games in one engine == the same games split over two engines of 8 (as two ranks would)."""
+    import alphazero_gomoku_b200 as m
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import SelfPlay
+    torch.manual_seed(2)
+    model = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    kw = dict(n_sims=64, node_capacity=2048, example_capacity=1 << 14, seed=99, noise=True, alpha=0.3, eps=0.25)
+    whole = SelfPlay(model, n_games=16, game_base=0, **kw)
+    lo = SelfPlay(model, n_games=8, game_base=0, **kw)
+    hi = SelfPlay(model, n_games=8, game_base=8, **kw)
+    for step in range(12):
+        whole.step(); lo.step(); hi.step()
+        a = whole.actions.cpu().numpy()
+        assert np.array_equal(a[:8], lo.actions.cpu().numpy()), step
+        assert np.array_equal(a[8:], hi.actions.cpu().numpy()), step
+        assert torch.equal(whole.last_pi[:8], lo.last_pi) and torch.equal(whole.last_pi[8:], hi.last_pi)
+    assert len(set(whole.actions.cpu().tolist())) > 1, "games must have diverged (noise + sampling)"
+    for s in (whole, lo, hi):
+        s.close()

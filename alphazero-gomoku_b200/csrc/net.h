@@ -25,7 +25,10 @@ struct ConvArgs {
   unsigned long long* prof;       // optional device counters [8] (cycles spent waiting per role), or null
 };
 
-int azg_conv3x3_launch(int C, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm,
+// mode: activation staging variant of the kernel (see net_conv.cu); tm_act must have been encoded
+// with box rows = azg_conv3x3_rows(mode).
+int azg_conv3x3_rows(int mode);
+int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm,
                        cudaStream_t stream);
 
 // net_aux.cu

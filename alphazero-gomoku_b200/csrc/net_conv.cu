@@ -25,18 +25,27 @@
 
 namespace {
 
-constexpr int kCopyRows = 160;                 // 128 tile rows + 16 above + 16 below
-constexpr int kStageBytes = kCopyRows * 128;   // one 64-channel slice of one shifted copy
+// Activation staging modes (template parameter MODE):
+//   0: three column-shifted copies (dc = -1, 0, +1) of 160 rows; row taps are 2 KB-aligned offsets.
+//   1: ONE copy of 162 rows per 64-channel slice; every tap is a row offset of the same tile
+//      (start address not aligned to the 1024-byte swizzle period, descriptor base_offset = 0).
+//   2: as 1, with the descriptor's base_offset field set to (start >> 7) & 7.
+template <int MODE>
+struct Stage {
+  static constexpr int ROWS = MODE == 0 ? 160 : 162;
+  static constexpr int BYTES = ROWS * 128;                         // TMA transaction size
+  static constexpr int PITCH = (BYTES + 1023) & ~1023;             // 1024-aligned stage pitch
+};
 constexpr int kThreads = 320;                  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 
-template <int C>
+template <int C, int MODE>
 struct Cfg {
   static constexpr int KC = C / 64;                       // 64-channel K slices
   static constexpr int BBLK = (C / 2) * 128;              // one (tap, slice) weight block: C/2 rows x 128 B
   static constexpr int BBYTES = 9 * KC * BBLK;            // resident weights per CTA
   static constexpr int TMEM_COLS = 2 * C;                 // two accumulators
-  static constexpr int STAGES = C == 128 ? 4 : 6;         // activation copies in flight
-  static constexpr int SMEM = 1024 + BBYTES + STAGES * kStageBytes + 256;
+  static constexpr int STAGES = MODE == 0 ? (C == 128 ? 4 : 6) : 3;   // activation tiles in flight
+  static constexpr int SMEM = 1024 + BBYTES + STAGES * Stage<MODE>::PITCH + 256;
 };
 
 // Folded BatchNorm shift of the layer, passed by value so the epilogue reads it from the constant
@@ -57,17 +66,18 @@ struct HeadConst {
 
 enum { ERR_BFULL = 1, ERR_EMPTY = 2, ERR_FULL = 3, ERR_TEMPTY = 4, ERR_TFULL = 5 };
 
-template <int C, bool HEADS>
+template <int C, bool HEADS, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w, ConvArgs p,
                     const __grid_constant__ ConvShift<C> shift, const __grid_constant__ HeadConst<HEADS ? C : 1> head) {
-  using K = Cfg<C>;
+  using K = Cfg<C, MODE>;
   constexpr int kStages = K::STAGES;
+  constexpr int kStageBytes = Stage<MODE>::BYTES, kStagePitch = Stage<MODE>::PITCH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;
   uint8_t* sA = smem + K::BBYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kStages * kStagePitch);
   uint64_t* full = bars;                // [kStages]  leader: both CTAs' copies landed
   uint64_t* empty = bars + kStages;     // [kStages]  each CTA: MMAs reading the stage retired
   uint64_t* tfull = bars + 2 * kStages; // [2]        each CTA: accumulator complete
@@ -116,14 +126,14 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       long long t_wait = 0;
       const long long t_begin = clock64();
       for (int b = cid; b < n_boards && ok; b += ncl) {
-        const int row0 = AZG_NET_FRONT + (b * 2 + (int)rank) * 128 - 16;
+        const int row0 = AZG_NET_FRONT + (b * 2 + (int)rank) * 128 - (MODE == 0 ? 16 : 17);
         for (int kc = 0; kc < K::KC && ok; ++kc)
-          for (int dci = 0; dci < 3; ++dci) {
+          for (int dci = 0; dci < (MODE == 0 ? 3 : 1); ++dci) {
             const long long t0 = clock64();
             if (!ptx::mbar_wait(&empty[stage], phase ^ 1u)) { atomicExch(p.error, ERR_EMPTY); ok = false; break; }
             t_wait += clock64() - t0;
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2u * kStageBytes);
-            ptx::tma_load_2d_pair(sA + stage * kStageBytes, &tm_act, &full[stage], kc * 64, row0 + dci - 1);
+            ptx::tma_load_2d_pair(sA + stage * kStagePitch, &tm_act, &full[stage], kc * 64, row0 + (MODE == 0 ? dci - 1 : 0));
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
       }
@@ -155,21 +165,29 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C);
         for (int kc = 0; kc < K::KC && ok; ++kc)
-          for (int dci = 0; dci < 3; ++dci) {
+          for (int dcs = 0; dcs < (MODE == 0 ? 3 : 1); ++dcs) {
             t0 = clock64();
             if (!ptx::mbar_wait(&full[stage], phase)) { if (lane == 0) atomicExch(p.error, ERR_FULL); ok = false; break; }
             t_full += clock64() - t0;
             ptx::tc_fence_after();
-            const uint64_t a_stage = a_desc0 + (uint64_t)((stage * kStageBytes) >> 4);
-            const uint64_t b_slice = b_desc0 + (uint64_t)(((dci * K::KC + kc) * K::BBLK) >> 4);
+            const uint64_t a_stage = a_desc0 + (uint64_t)((stage * kStagePitch) >> 4);
+            const uint64_t b_slice = b_desc0 + (uint64_t)((kc * K::BBLK) >> 4);
             if (ptx::elect_one()) {
 #pragma unroll
               for (int dri = 0; dri < 3; ++dri) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t ad = a_stage + (uint64_t)((dri * 2048 + k * 32) >> 4);
-                  const uint64_t bd = b_slice + (uint64_t)((dri * 3 * K::KC * K::BBLK + k * 32) >> 4);
-                  ptx::umma_bf16<2>(tmem_d, ad, bd, idesc, (kc | dci | dri | k) != 0 ? 1u : 0u);
+                for (int dcu = 0; dcu < (MODE == 0 ? 1 : 3); ++dcu) {
+                  const int dci = MODE == 0 ? dcs : dcu;
+                  // MODE 0: the stage IS the dc copy, the row tap is a 16-row (2 KB) offset.
+                  // MODE 1/2: copy row 17 + 16*(dr) + dc holds the tap's first row (dr, dc in -1..1).
+                  const int arow = MODE == 0 ? dri * 16 : 17 + 16 * (dri - 1) + (dcu - 1);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    uint64_t ad = a_stage + (uint64_t)((arow * 128 + k * 32) >> 4);
+                    if (MODE == 2) ad |= (uint64_t)(arow & 7) << 49;
+                    const uint64_t bd = b_slice + (uint64_t)((((dri * 3 + dci) * K::KC) * K::BBLK + k * 32) >> 4);
+                    ptx::umma_bf16<2>(tmem_d, ad, bd, idesc, (kc | dcs | dri | dcu | k) != 0 ? 1u : 0u);
+                  }
                 }
               }
               ptx::umma_commit_pair(&empty[stage], 3);        // frees the stage in both CTAs
@@ -279,10 +297,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   if (warp == 1) ptx::tmem_dealloc<2>(tmem_base, K::TMEM_COLS);
 }
 
-template <int C, bool HEADS>
+template <int C, bool HEADS, int MODE>
 int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm, cudaStream_t stream) {
-  using K = Cfg<C>;
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<C, HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+  using K = Cfg<C, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<C, HEADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
   int grid = n_sm & ~1;
   const int want = 2 * args.max_boards;
@@ -300,16 +318,31 @@ int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvAr
     head.w[0][0] = head.w[1][0] = head.w[2][0] = 0.f;
     for (int r = 0; r < 3; ++r) head.scale[r] = head.shift[r] = 0.f;
   }
-  conv3x3_pair_kernel<C, HEADS><<<grid, kThreads, K::SMEM, stream>>>(tm_act, tm_w, args, shift, head);
+  conv3x3_pair_kernel<C, HEADS, MODE><<<grid, kThreads, K::SMEM, stream>>>(tm_act, tm_w, args, shift, head);
   return azg_check_launch("conv3x3_pair_kernel");
+}
+
+template <int C, int MODE>
+int launch_conv_heads(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm, cudaStream_t stream) {
+  return args.head_host ? launch_conv<C, true, MODE>(tm_act, tm_w, args, n_sm, stream)
+                        : launch_conv<C, false, MODE>(tm_act, tm_w, args, n_sm, stream);
 }
 
 }  // namespace
 
-int azg_conv3x3_launch(int C, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm,
+int azg_conv3x3_rows(int mode) { return mode == 0 ? Stage<0>::ROWS : Stage<1>::ROWS; }
+
+int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm,
                        cudaStream_t stream) {
-  const bool heads = args.head_host != nullptr;
-  if (C == 128) return heads ? launch_conv<128, true>(tm_act, tm_w, args, n_sm, stream) : launch_conv<128, false>(tm_act, tm_w, args, n_sm, stream);
-  if (C == 64) return heads ? launch_conv<64, true>(tm_act, tm_w, args, n_sm, stream) : launch_conv<64, false>(tm_act, tm_w, args, n_sm, stream);
+  if (C == 128) {
+    if (mode == 0) return launch_conv_heads<128, 0>(tm_act, tm_w, args, n_sm, stream);
+    if (mode == 1) return launch_conv_heads<128, 1>(tm_act, tm_w, args, n_sm, stream);
+    return launch_conv_heads<128, 2>(tm_act, tm_w, args, n_sm, stream);
+  }
+  if (C == 64) {
+    if (mode == 0) return launch_conv_heads<64, 0>(tm_act, tm_w, args, n_sm, stream);
+    if (mode == 1) return launch_conv_heads<64, 1>(tm_act, tm_w, args, n_sm, stream);
+    return launch_conv_heads<64, 2>(tm_act, tm_w, args, n_sm, stream);
+  }
   return azg_fail(AZG_E_ARG, "conv3x3: resident-weight kernel supports 64 or 128 channels");
 }

@@ -1,6 +1,7 @@
 // Host side of the leaf evaluator: weight repacking, activation buffers, TMA descriptors and the
 // layer schedule.  C ABI: azg_net_* (include/azgomoku_b200.h).  Replaces AlphaZeroNet.forward +
 // PyTorchModel.predict (network.py:85-117, 168-183).
+#include <stdlib.h>
 #include <new>
 #include <vector>
 #include "common.cuh"
@@ -13,7 +14,7 @@ int azg_pack_launch_stem(const float*, const float*, int, float*, cudaStream_t);
 int azg_pack_launch_transpose(const float*, int, int, float*, cudaStream_t);
 
 struct azg_net {
-  int device = 0, n_blocks = 0, C = 0, max_batch = 0, n_sm = 0, loaded = 0;
+  int device = 0, n_blocks = 0, C = 0, max_batch = 0, n_sm = 0, loaded = 0, conv_mode = 0;
   int64_t bytes = 0;
   size_t rows = 0;                       // rows of one activation buffer (front pad + boards*256 + back pad)
   __nv_bfloat16* w3 = nullptr;           // [(layer*9+tap)*C + cout][cin]
@@ -127,8 +128,13 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
   cudaMemset(n->error_dev, 0, 16);
   cudaMemset(n->prof_dev, 0, 128);
   cudaMemset(n->hidden, 0, (size_t)((max_batch + 31) / 32) * AZG_HIDDEN_TILE * 4);
+  {
+    const char* m = getenv("AZG_CONV_MODE");        // experiment switch for the activation staging variant
+    n->conv_mode = m ? atoi(m) : 1;                 // 1: single activation copy per slice (fastest, validated)
+    if (n->conv_mode < 0 || n->conv_mode > 2) n->conv_mode = 1;
+  }
   for (int i = 0; i < 3; ++i)
-    if ((rc = make_map(&n->tm_act[i], n->act[i], n->rows, C, 160))) { azg_net_destroy(n); return rc; }
+    if ((rc = make_map(&n->tm_act[i], n->act[i], n->rows, C, (uint32_t)azg_conv3x3_rows(n->conv_mode)))) { azg_net_destroy(n); return rc; }
   if ((rc = make_map(&n->tm_w, n->w3, (L ? L : 1) * 9 * C, C, (uint32_t)(C / 2)))) { azg_net_destroy(n); return rc; }
   cudaError_t ce = cudaDeviceSynchronize();
   if (ce != cudaSuccess) { azg_net_destroy(n); return azg_fail(AZG_E_CUDA, cudaGetErrorString(ce)); }
@@ -207,8 +213,8 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
     a.head_host = nullptr; a.hidden = nullptr;
     const bool fuse = heads && l == n_layers - 1 && (l & 1) == 1;     // last conv2: fuse the 1x1 head convs, skip the store
     if (fuse) { a.head_host = n->head_host.data(); a.hidden = n->hidden; fused_heads = true; }
-    if ((l & 1) == 0) { a.residual = nullptr; a.out = n->act[t]; rc = azg_conv3x3_launch(C, n->tm_act[x], n->tm_w, a, n->n_sm, s); }
-    else { a.residual = n->act[x]; a.out = fuse ? nullptr : n->act[y]; rc = azg_conv3x3_launch(C, n->tm_act[t], n->tm_w, a, n->n_sm, s); int tmp = x; x = y; y = tmp; }
+    if ((l & 1) == 0) { a.residual = nullptr; a.out = n->act[t]; rc = azg_conv3x3_launch(C, n->conv_mode, n->tm_act[x], n->tm_w, a, n->n_sm, s); }
+    else { a.residual = n->act[x]; a.out = fuse ? nullptr : n->act[y]; rc = azg_conv3x3_launch(C, n->conv_mode, n->tm_act[t], n->tm_w, a, n->n_sm, s); int tmp = x; x = y; y = tmp; }
     if (rc) return rc;
   }
   if (ev_stop) cudaEventRecord(ev_stop, s);

@@ -108,16 +108,27 @@ def _oracle_model(blocks, channels):
     return onet.CpuModel(mynet.AlphaZeroNet(n_res_blocks=blocks, channels=channels).state_dict())
 
 
+_WORKER_MODEL = None
+
+
+def _cpu_worker_init(blocks, channels):
+    """Per-process model, created once (the reference's _selfplay_worker_init, train.py:30-59)."""
+    global _WORKER_MODEL
+    import torch
+    torch.set_num_threads(1)
+    _WORKER_MODEL = _oracle_model(blocks, channels)
+
+
 def _cpu_worker(job):
-    """One process of the reference's parallel mode (train.py:62-129): own model, one torch thread,
-    one MCTS.run of `sims` simulations from the empty board with root noise."""
+    """One task of the reference's parallel mode (train.py:62-129): one torch thread, one MCTS.run
+    of `sims` simulations from the empty board with root noise, fresh tree."""
     blocks, channels, rule, sims, seed = job
     import torch
     torch.set_num_threads(1)
     from oracle import rules
     from oracle.search import Search
     np.random.seed(seed)
-    model = _oracle_model(blocks, channels)
+    model = _WORKER_MODEL or _oracle_model(blocks, channels)
     s = Search(rule, sims, model, cpuct=1.0, queue_len=32, alpha=0.05, eps=0.15, noise_plies=10, noise=True)
     t0 = time.perf_counter()
     s.run(rules.Position(rule), 0)
@@ -160,9 +171,9 @@ def run_reference(args):
     workers = max(1, (os.cpu_count() or 2) - 1)
     workers = min(workers, 64)
     rule = 1 if args.rule == "pente" else 0
-    sims = 100
+    sims = 200
     ctx = mp.get_context("spawn")
-    with ctx.Pool(workers) as pool:
+    with ctx.Pool(workers, initializer=_cpu_worker_init, initargs=(args.blocks, args.channels)) as pool:
         for w in range(args.warmup):
             pool.map(_cpu_worker, [(args.blocks, args.channels, rule, 32, 1000 + i) for i in range(workers)])
         t0 = time.perf_counter()

@@ -28,8 +28,9 @@ struct ConvArgs {
 // mode: activation staging variant of the kernel (see net_conv.cu); tm_act must have been encoded
 // with box rows = azg_conv3x3_rows(mode).
 int azg_conv3x3_rows(int mode);
-int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm,
-                       cudaStream_t stream);
+// tm_out: box {32 channels, 32 rows}, SWIZZLE_64B, over the output buffer (epilogue TMA stores).
+int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtensorMap& tm_out,
+                       const ConvArgs& args, int n_sm, cudaStream_t stream);
 
 // net_aux.cu
 struct StemArgs {

@@ -91,19 +91,29 @@ int azg_planes_to_keys_launch(const float* planes, int n, uint32_t* keys, uint32
 // tap contributes a sum of at most two weight vectors - no multiplies.  One block per board,
 // warp w owns padded rows 32w..32w+31, lane l owns C/32 consecutive channels: every store
 // instruction writes one full pixel row (C*2 bytes, coalesced).
+// Row-pattern tables: for tap row d (dr = d-1) and the 6-bit pattern of its three neighbour states
+// (2 bits each: 0 off-board, 1 empty, 2 mover, 3 opponent) the summed weight vector of that row is
+// precomputed in shared memory, so a pixel costs three 16-byte table reads instead of nine.
 template <int C>
 __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
   constexpr int CPL = C / 32;
-  __shared__ __align__(16) float s_t[27 * C];   // [tap][state-1]: ones-plane weight (+ mover / opponent weight)
-  __shared__ __align__(16) float s_empty[C];    // shift + all nine taps on empty in-board cells
+  extern __shared__ __align__(16) float s_rows[];   // [3][64][C]
+  __shared__ __align__(16) float s_empty[C];         // shift + all nine taps on empty in-board cells
   __shared__ __align__(16) float s_shift[C];
-  __shared__ uint8_t s_state[256];              // 0 off-board / pad, 1 empty, 2 mover stone, 3 opponent stone
-  __shared__ uint32_t s_code[256];              // the nine neighbour states of each padded pixel, 2 bits per tap
-  for (int i = threadIdx.x; i < 27 * C; i += 256) {
-    const int c = i % C, st = (i / C) % 3, tap = i / (3 * C);
-    float v = a.w[(tap * 3 + 2) * C + c];
-    if (st >= 1) v += a.w[(tap * 3 + (st - 1)) * C + c];
-    s_t[i] = v;
+  __shared__ uint8_t s_state[256];                   // 0 off-board / pad, 1 empty, 2 mover stone, 3 opponent stone
+  __shared__ uint32_t s_code[256];                   // the nine neighbour states of each padded pixel, 2 bits per tap
+  for (int i = threadIdx.x; i < 3 * 64 * C; i += 256) {
+    const int c = i % C, combo = (i / C) & 63, d = i / (64 * C);
+    float v = 0.f;
+#pragma unroll
+    for (int dc = 0; dc < 3; ++dc) {
+      const int st = (combo >> (2 * dc)) & 3;
+      if (st == 0) continue;
+      const int tap = d * 3 + dc;
+      v += a.w[(tap * 3 + 2) * C + c];
+      if (st >= 2) v += a.w[(tap * 3 + (st - 2)) * C + c];
+    }
+    s_rows[i] = v;
   }
   for (int i = threadIdx.x; i < C; i += 256) {
     float e = a.shift[i];
@@ -145,7 +155,7 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
     }
     __syncthreads();
     __nv_bfloat16* out = a.out + ((size_t)AZG_NET_FRONT + (size_t)b * 256) * C;
-#pragma unroll 2
+#pragma unroll 4
     for (int i = 0; i < 32; ++i) {
       const int qi = warp * 32 + i;
       const uint32_t code = s_code[qi];
@@ -160,10 +170,8 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
 #pragma unroll
         for (int j = 0; j < CPL; ++j) acc[j] = s_shift[lane * CPL + j];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t st = (code >> (2 * tap)) & 3u;
-          if (st == 0) continue;
-          const float* w = s_t + (tap * 3 + (int)st - 1) * C + lane * CPL;
+        for (int d = 0; d < 3; ++d) {
+          const float* w = s_rows + (size_t)(d * 64 + ((code >> (6 * d)) & 63u)) * C + lane * CPL;
 #pragma unroll
           for (int j = 0; j < CPL; ++j) acc[j] += w[j];
         }
@@ -187,15 +195,22 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
   }
 }
 
-int azg_stem_launch(int C, const StemArgs& a, int n_sm, cudaStream_t stream) {
-  int grid = n_sm * 4;
+template <int C>
+static int stem_launch_t(const StemArgs& a, int n_sm, cudaStream_t stream) {
+  const int smem = 3 * 64 * C * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(stem_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
+  int grid = n_sm * (C == 64 ? 4 : 2);
   if (grid > a.max_boards) grid = a.max_boards;
   if (grid < 1) grid = 1;
-  if (C == 64) stem_kernel<64><<<grid, 256, 0, stream>>>(a);
-  else if (C == 128) stem_kernel<128><<<grid, 256, 0, stream>>>(a);
-  else if (C == 256) stem_kernel<256><<<grid, 256, 0, stream>>>(a);
-  else return azg_fail(AZG_E_ARG, "stem: channels must be 64, 128 or 256");
+  stem_kernel<C><<<grid, 256, smem, stream>>>(a);
   return azg_check_launch("stem_kernel");
+}
+
+int azg_stem_launch(int C, const StemArgs& a, int n_sm, cudaStream_t stream) {
+  if (C == 64) return stem_launch_t<64>(a, n_sm, stream);
+  if (C == 128) return stem_launch_t<128>(a, n_sm, stream);
+  return azg_fail(AZG_E_ARG, "stem: channels must be 64 or 128");
 }
 
 // ------------------------------------------------------------------------------------------------

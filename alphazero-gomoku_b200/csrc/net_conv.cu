@@ -29,7 +29,9 @@ namespace {
 //   0: three column-shifted copies (dc = -1, 0, +1) of 160 rows; row taps are 2 KB-aligned offsets.
 //   1: ONE copy of 162 rows per 64-channel slice; every tap is a row offset of the same tile
 //      (start address not aligned to the 1024-byte swizzle period, descriptor base_offset = 0).
-//   2: as 1, with the descriptor's base_offset field set to (start >> 7) & 7.
+//   2: as 1, with the descriptor's base_offset field set to (start >> 7) & 7 (WRONG results on
+//      B200: the swizzle is applied to absolute address bits; kept only as the recorded experiment).
+//   3: as 1 but with the direct (row-per-thread) epilogue instead of the staged one.
 template <int MODE>
 struct Stage {
   static constexpr int ROWS = MODE == 0 ? 160 : 162;
@@ -45,7 +47,8 @@ struct Cfg {
   static constexpr int BBYTES = 9 * KC * BBLK;            // resident weights per CTA
   static constexpr int TMEM_COLS = 2 * C;                 // two accumulators
   static constexpr int STAGES = MODE == 0 ? (C == 128 ? 4 : 6) : 3;   // activation tiles in flight
-  static constexpr int SMEM = 1024 + BBYTES + STAGES * Stage<MODE>::PITCH + 256;
+  static constexpr int EPI = (MODE == 0 || MODE == 3) ? 0 : 8 * 2048;                // per-warp epilogue staging tiles (32 rows x 64 B)
+  static constexpr int SMEM = 1024 + BBYTES + STAGES * Stage<MODE>::PITCH + EPI + 256;
 };
 
 // Folded BatchNorm shift of the layer, passed by value so the epilogue reads it from the constant
@@ -68,7 +71,8 @@ enum { ERR_BFULL = 1, ERR_EMPTY = 2, ERR_FULL = 3, ERR_TEMPTY = 4, ERR_TFULL = 5
 
 template <int C, bool HEADS, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w, ConvArgs p,
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
+                    const __grid_constant__ CUtensorMap tm_out, ConvArgs p,
                     const __grid_constant__ ConvShift<C> shift, const __grid_constant__ HeadConst<HEADS ? C : 1> head) {
   using K = Cfg<C, MODE>;
   constexpr int kStages = K::STAGES;
@@ -77,7 +81,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;
   uint8_t* sA = smem + K::BBYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kStages * kStagePitch);
+  uint8_t* sEpi = sA + kStages * kStagePitch;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + K::EPI);
   uint64_t* full = bars;                // [kStages]  leader: both CTAs' copies landed
   uint64_t* empty = bars + kStages;     // [kStages]  each CTA: MMAs reading the stage retired
   uint64_t* tfull = bars + 2 * kStages; // [2]        each CTA: accumulator complete
@@ -222,16 +227,38 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     bool ok = true;
     long long t_tfull = 0;
     const long long t_begin = clock64();
+    // MODE >= 1: global traffic of the epilogue is coalesced through a per-warp 2 KB staging tile
+    // (32 rows x 32 channels, 64-byte rows, 16-byte units XOR-swizzled with (row >> 1) & 3, which is
+    // both bank-conflict free and the layout of a SWIZZLE_64B TMA box): residual rows are read with
+    // coalesced 16-byte loads (8 rows x 64 B per instruction) and transposed through the tile, results
+    // leave by one TMA store per tile.  MODE 0 keeps the direct row-per-thread accesses.
+    constexpr bool STAGED = MODE == 1 || MODE == 2;
+    constexpr int NCHUNK = NCH / 32;
+    const uint32_t tile = ptx::smem_u32(sEpi) + (uint32_t)(warp - 2) * 2048u;
+    const uint32_t own = tile + (uint32_t)lane * 64u;                      // this thread's row in the tile
+    const uint32_t own_sw = (uint32_t)((lane >> 1) & 3);
+    const int crow = lane >> 2, cunit = lane & 3;                          // coalesced mapping: row 8i + crow, unit cunit
     for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
       const int acc = it & 1;
-      const size_t grow = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)qi;
+      const size_t grow0 = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)rank * 128 + (size_t)quad * 32;   // first row of this warp
+      const size_t grow = grow0 + (size_t)lane;
       __nv_bfloat16* orow = p.out ? p.out + grow * C : nullptr;
-      const __nv_bfloat16* rrow = (p.residual && working) ? p.residual + grow * C : nullptr;
-      // the residual row is fetched while the MMAs of this board are still running
-      uint32_t res[NCH / 2];
-      if (rrow) {
+      const bool has_res = p.residual != nullptr && working;
+      // the residual is fetched while the MMAs of this board are still running
+      uint4 rc[STAGED ? NCHUNK * 4 : 1];
+      uint32_t res[STAGED ? 16 : NCH / 2];
+      if (has_res) {
+        if constexpr (STAGED) {
 #pragma unroll
-        for (int j = 0; j < NCH / 16; ++j) ptx::ldg256(rrow + ch0 + 16 * j, &res[8 * j]);
+          for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              rc[c * 4 + i] = ptx::ldg128(p.residual + (grow0 + (size_t)(8 * i + crow)) * C + ch0 + 32 * c + 8 * cunit);
+        } else {
+          const __nv_bfloat16* rrow = p.residual + grow * C;
+#pragma unroll
+          for (int j = 0; j < NCH / 16; ++j) ptx::ldg256(rrow + ch0 + 16 * j, &res[8 * j]);
+        }
       }
       const long long t0 = clock64();
       if (!ptx::mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u)) { atomicExch(p.error, ERR_TFULL); ok = false; break; }
@@ -240,19 +267,41 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       if (working) {
         float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < NCH; cc += 32) {
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int cc = 32 * c;
           const int ch = ch0 + cc;
           uint32_t v[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * C + ch), v);
+          if constexpr (STAGED) {
+            if (p.out) {                       // the previous TMA store must have finished reading the tile
+              if (lane == 0) ptx::bulk_wait_read0();
+              __syncwarp();
+            }
+            if (has_res) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = 8 * i + crow;
+                ptx::sts128(tile + (uint32_t)r * 64u + (uint32_t)((cunit ^ ((r >> 1) & 3)) * 16), rc[c * 4 + i]);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint4 q = ptx::lds128(own + (uint32_t)(((uint32_t)u ^ own_sw) * 16u));
+                res[4 * u] = q.x; res[4 * u + 1] = q.y; res[4 * u + 2] = q.z; res[4 * u + 3] = q.w;
+              }
+              __syncwarp();
+            }
+          }
           ptx::tmem_ld_wait();
           uint32_t outv[16];
 #pragma unroll
           for (int h = 0; h < 16; ++h) {
             float y0 = __uint_as_float(v[2 * h]) + ((!HEADS && half) ? shift.v[(C / 2 + cc + 2 * h) % C] : shift.v[cc + 2 * h]);
             float y1 = __uint_as_float(v[2 * h + 1]) + ((!HEADS && half) ? shift.v[(C / 2 + cc + 2 * h + 1) % C] : shift.v[cc + 2 * h + 1]);
-            if (rrow) {
-              y0 += __uint_as_float(res[cc / 2 + h] << 16);
-              y1 += __uint_as_float(res[cc / 2 + h] & 0xffff0000u);
+            if (has_res) {
+              const uint32_t rw = STAGED ? res[h] : res[(cc / 2 + h) % (STAGED ? 16 : NCH / 2)];
+              y0 += __uint_as_float(rw << 16);
+              y1 += __uint_as_float(rw & 0xffff0000u);
             }
             if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
             if (pad) { y0 = 0.f; y1 = 0.f; }
@@ -266,9 +315,22 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
               d2 = fmaf(z0, head.w[2][cc + 2 * h], d2); d2 = fmaf(z1, head.w[2][cc + 2 * h + 1], d2);
             }
           }
-          if (orow) {
-            ptx::stg256(orow + ch, &outv[0]);
-            ptx::stg256(orow + ch + 16, &outv[8]);
+          if (p.out) {
+            if constexpr (STAGED) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                ptx::sts128(own + (uint32_t)(((uint32_t)u ^ own_sw) * 16u),
+                            make_uint4(outv[4 * u], outv[4 * u + 1], outv[4 * u + 2], outv[4 * u + 3]));
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                ptx::tma_store_2d(&tm_out, sEpi + (warp - 2) * 2048, ch, (int)grow0);
+                ptx::bulk_commit();
+              }
+            } else {
+              ptx::stg256(orow + ch, &outv[0]);
+              ptx::stg256(orow + ch + 16, &outv[8]);
+            }
           }
         }
         if constexpr (HEADS) {
@@ -285,6 +347,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
     }
+    if (STAGED && lane == 0) ptx::bulk_wait0();            // all stores of this warp have landed before the CTA exits
     if (p.prof && rank == 0 && warp == 2 && lane == 0) {   // one representative epilogue warp
       atomicAdd(p.prof + 5, (unsigned long long)t_tfull);
       atomicAdd(p.prof + 6, (unsigned long long)(clock64() - t_begin));
@@ -298,7 +361,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
 }
 
 template <int C, bool HEADS, int MODE>
-int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm, cudaStream_t stream) {
+int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtensorMap& tm_out, const ConvArgs& args, int n_sm,
+                cudaStream_t stream) {
   using K = Cfg<C, MODE>;
   cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<C, HEADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
@@ -318,31 +382,34 @@ int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvAr
     head.w[0][0] = head.w[1][0] = head.w[2][0] = 0.f;
     for (int r = 0; r < 3; ++r) head.scale[r] = head.shift[r] = 0.f;
   }
-  conv3x3_pair_kernel<C, HEADS, MODE><<<grid, kThreads, K::SMEM, stream>>>(tm_act, tm_w, args, shift, head);
+  conv3x3_pair_kernel<C, HEADS, MODE><<<grid, kThreads, K::SMEM, stream>>>(tm_act, tm_w, tm_out, args, shift, head);
   return azg_check_launch("conv3x3_pair_kernel");
 }
 
 template <int C, int MODE>
-int launch_conv_heads(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm, cudaStream_t stream) {
-  return args.head_host ? launch_conv<C, true, MODE>(tm_act, tm_w, args, n_sm, stream)
-                        : launch_conv<C, false, MODE>(tm_act, tm_w, args, n_sm, stream);
+int launch_conv_heads(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtensorMap& tm_out, const ConvArgs& args, int n_sm,
+                      cudaStream_t stream) {
+  return args.head_host ? launch_conv<C, true, MODE>(tm_act, tm_w, tm_out, args, n_sm, stream)
+                        : launch_conv<C, false, MODE>(tm_act, tm_w, tm_out, args, n_sm, stream);
 }
 
 }  // namespace
 
 int azg_conv3x3_rows(int mode) { return mode == 0 ? Stage<0>::ROWS : Stage<1>::ROWS; }
 
-int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvArgs& args, int n_sm,
-                       cudaStream_t stream) {
+int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtensorMap& tm_out,
+                       const ConvArgs& args, int n_sm, cudaStream_t stream) {
   if (C == 128) {
-    if (mode == 0) return launch_conv_heads<128, 0>(tm_act, tm_w, args, n_sm, stream);
-    if (mode == 1) return launch_conv_heads<128, 1>(tm_act, tm_w, args, n_sm, stream);
-    return launch_conv_heads<128, 2>(tm_act, tm_w, args, n_sm, stream);
+    if (mode == 0) return launch_conv_heads<128, 0>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (mode == 1) return launch_conv_heads<128, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (mode == 3) return launch_conv_heads<128, 3>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    return launch_conv_heads<128, 2>(tm_act, tm_w, tm_out, args, n_sm, stream);
   }
   if (C == 64) {
-    if (mode == 0) return launch_conv_heads<64, 0>(tm_act, tm_w, args, n_sm, stream);
-    if (mode == 1) return launch_conv_heads<64, 1>(tm_act, tm_w, args, n_sm, stream);
-    return launch_conv_heads<64, 2>(tm_act, tm_w, args, n_sm, stream);
+    if (mode == 0) return launch_conv_heads<64, 0>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (mode == 1) return launch_conv_heads<64, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (mode == 3) return launch_conv_heads<64, 3>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    return launch_conv_heads<64, 2>(tm_act, tm_w, tm_out, args, n_sm, stream);
   }
   return azg_fail(AZG_E_ARG, "conv3x3: resident-weight kernel supports 64 or 128 channels");
 }

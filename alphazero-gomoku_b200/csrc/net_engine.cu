@@ -28,7 +28,7 @@ struct azg_net {
   int *n_dev = nullptr, *error_dev = nullptr;
   unsigned long long* prof_dev = nullptr;
   int* pinned = nullptr;
-  CUtensorMap tm_act[3], tm_w;
+  CUtensorMap tm_act[3], tm_w, tm_st[3];      // tm_st: 32x32 SWIZZLE_64B store boxes over the activation buffers
   // optional timing of the 3x3 trunk (one CUDA-event pair per forward pass, on the launch stream)
   int profiling = 0;
   std::vector<cudaEvent_t> ev;          // start/stop pairs
@@ -53,16 +53,18 @@ static encode_fn get_encode() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows][cols] tensor, box {64 columns, box_rows}, 128-byte swizzle.
-static int make_map(CUtensorMap* m, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D bf16 row-major [rows][cols] tensor, box {box_cols columns, box_rows}, 128-byte swizzle for 64-column
+// boxes (operand tiles) and 64-byte swizzle for 32-column boxes (epilogue store tiles).
+static int make_map(CUtensorMap* m, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols = 64) {
   encode_fn enc = get_encode();
   if (!enc) return azg_fail(AZG_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return azg_fail(AZG_E_CUDA, "cuTensorMapEncodeTiled failed");
   return AZG_OK;
 }
@@ -131,10 +133,12 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
   {
     const char* m = getenv("AZG_CONV_MODE");        // experiment switch for the activation staging variant
     n->conv_mode = m ? atoi(m) : 1;                 // 1: single activation copy per slice (fastest, validated)
-    if (n->conv_mode < 0 || n->conv_mode > 2) n->conv_mode = 1;
+    if (n->conv_mode < 0 || n->conv_mode > 3) n->conv_mode = 1;
   }
   for (int i = 0; i < 3; ++i)
     if ((rc = make_map(&n->tm_act[i], n->act[i], n->rows, C, (uint32_t)azg_conv3x3_rows(n->conv_mode)))) { azg_net_destroy(n); return rc; }
+  for (int i = 0; i < 3; ++i)
+    if ((rc = make_map(&n->tm_st[i], n->act[i], n->rows, C, 32, 32))) { azg_net_destroy(n); return rc; }
   if ((rc = make_map(&n->tm_w, n->w3, (L ? L : 1) * 9 * C, C, (uint32_t)(C / 2)))) { azg_net_destroy(n); return rc; }
   cudaError_t ce = cudaDeviceSynchronize();
   if (ce != cudaSuccess) { azg_net_destroy(n); return azg_fail(AZG_E_CUDA, cudaGetErrorString(ce)); }
@@ -213,8 +217,8 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
     a.head_host = nullptr; a.hidden = nullptr;
     const bool fuse = heads && l == n_layers - 1 && (l & 1) == 1;     // last conv2: fuse the 1x1 head convs, skip the store
     if (fuse) { a.head_host = n->head_host.data(); a.hidden = n->hidden; fused_heads = true; }
-    if ((l & 1) == 0) { a.residual = nullptr; a.out = n->act[t]; rc = azg_conv3x3_launch(C, n->conv_mode, n->tm_act[x], n->tm_w, a, n->n_sm, s); }
-    else { a.residual = n->act[x]; a.out = fuse ? nullptr : n->act[y]; rc = azg_conv3x3_launch(C, n->conv_mode, n->tm_act[t], n->tm_w, a, n->n_sm, s); int tmp = x; x = y; y = tmp; }
+    if ((l & 1) == 0) { a.residual = nullptr; a.out = n->act[t]; rc = azg_conv3x3_launch(C, n->conv_mode, n->tm_act[x], n->tm_w, n->tm_st[t], a, n->n_sm, s); }
+    else { a.residual = n->act[x]; a.out = fuse ? nullptr : n->act[y]; rc = azg_conv3x3_launch(C, n->conv_mode, n->tm_act[t], n->tm_w, n->tm_st[y], a, n->n_sm, s); int tmp = x; x = y; y = tmp; }
     if (rc) return rc;
   }
   if (ev_stop) cudaEventRecord(ev_stop, s);

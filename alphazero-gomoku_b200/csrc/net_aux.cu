@@ -94,9 +94,13 @@ int azg_planes_to_keys_launch(const float* planes, int n, uint32_t* keys, uint32
 // Row-pattern tables: for tap row d (dr = d-1) and the 6-bit pattern of its three neighbour states
 // (2 bits each: 0 off-board, 1 empty, 2 mover, 3 opponent) the summed weight vector of that row is
 // precomputed in shared memory, so a pixel costs three 16-byte table reads instead of nine.
-template <int C>
+template <int CT>
 __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
+  // CT channels in total; a block computes a slab of C = min(CT, 128) of them (blockIdx.y selects it)
+  constexpr int C = CT > 128 ? 128 : CT;
   constexpr int CPL = C / 32;
+  const int cbase = blockIdx.y * C;
+  a.w += cbase; a.shift += cbase; a.out += cbase;
   extern __shared__ __align__(16) float s_rows[];   // [3][64][C]
   __shared__ __align__(16) float s_empty[C];         // shift + all nine taps on empty in-board cells
   __shared__ __align__(16) float s_shift[C];
@@ -110,14 +114,14 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
       const int st = (combo >> (2 * dc)) & 3;
       if (st == 0) continue;
       const int tap = d * 3 + dc;
-      v += a.w[(tap * 3 + 2) * C + c];
-      if (st >= 2) v += a.w[(tap * 3 + (st - 2)) * C + c];
+      v += a.w[(tap * 3 + 2) * CT + c];
+      if (st >= 2) v += a.w[(tap * 3 + (st - 2)) * CT + c];
     }
     s_rows[i] = v;
   }
   for (int i = threadIdx.x; i < C; i += 256) {
     float e = a.shift[i];
-    for (int tap = 0; tap < 9; ++tap) e += a.w[(tap * 3 + 2) * C + i];
+    for (int tap = 0; tap < 9; ++tap) e += a.w[(tap * 3 + 2) * CT + i];
     s_empty[i] = e;
     s_shift[i] = a.shift[i];
   }
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
       s_code[qi] = s_state[qi] ? code : 0xffffffffu;      // pad rows/columns are written as zeros
     }
     __syncthreads();
-    __nv_bfloat16* out = a.out + ((size_t)AZG_NET_FRONT + (size_t)b * 256) * C;
+    __nv_bfloat16* out = a.out + ((size_t)AZG_NET_FRONT + (size_t)b * 256) * CT;
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
       const int qi = warp * 32 + i;
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
 #pragma unroll
         for (int j = 0; j < CPL; ++j) acc[j] = fmaxf(acc[j], 0.f);
       }
-      __nv_bfloat16* o = out + (size_t)qi * C + lane * CPL;
+      __nv_bfloat16* o = out + (size_t)qi * CT + lane * CPL;
       if constexpr (CPL == 2) {
         *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(acc[0], acc[1]);
       } else {
@@ -197,20 +201,22 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
 
 template <int C>
 static int stem_launch_t(const StemArgs& a, int n_sm, cudaStream_t stream) {
-  const int smem = 3 * 64 * C * (int)sizeof(float);
+  constexpr int CB = C > 128 ? 128 : C;
+  const int smem = 3 * 64 * CB * (int)sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(stem_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
-  int grid = n_sm * (C == 64 ? 4 : 2);
+  int grid = n_sm * (C == 64 ? 4 : 2) / (C / CB);
   if (grid > a.max_boards) grid = a.max_boards;
   if (grid < 1) grid = 1;
-  stem_kernel<C><<<grid, 256, smem, stream>>>(a);
+  stem_kernel<C><<<dim3(grid, C / CB), 256, smem, stream>>>(a);
   return azg_check_launch("stem_kernel");
 }
 
 int azg_stem_launch(int C, const StemArgs& a, int n_sm, cudaStream_t stream) {
   if (C == 64) return stem_launch_t<64>(a, n_sm, stream);
   if (C == 128) return stem_launch_t<128>(a, n_sm, stream);
-  return azg_fail(AZG_E_ARG, "stem: channels must be 64 or 128");
+  if (C == 256) return stem_launch_t<256>(a, n_sm, stream);
+  return azg_fail(AZG_E_ARG, "stem: channels must be 64, 128 or 256");
 }
 
 // ------------------------------------------------------------------------------------------------

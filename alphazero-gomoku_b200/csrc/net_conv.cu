@@ -44,7 +44,11 @@ template <int C, int MODE>
 struct Cfg {
   static constexpr int KC = C / 64;                       // 64-channel K slices
   static constexpr int BBLK = (C / 2) * 128;              // one (tap, slice) weight block: C/2 rows x 128 B
-  static constexpr int BBYTES = 9 * KC * BBLK;            // resident weights per CTA
+  // C <= 128: all 9*KC weight blocks of the layer stay resident.  C = 256 (1.18 MB of weights per
+  // layer) streams them through a ring of 9 blocks (one 64-channel slice of all taps) instead.
+  static constexpr bool STREAM = C > 128;
+  static constexpr int NBLK = STREAM ? 9 : 9 * KC;        // weight blocks held in shared memory
+  static constexpr int BBYTES = NBLK * BBLK;
   static constexpr int TMEM_COLS = 2 * C;                 // two accumulators
   static constexpr int STAGES = MODE == 0 ? (C == 128 ? 4 : 6) : 3;   // activation tiles in flight
   static constexpr int EPI = (MODE == 0 || MODE == 3) ? 0 : 8 * 2048;                // per-warp epilogue staging tiles (32 rows x 64 B)
@@ -87,8 +91,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   uint64_t* empty = bars + kStages;     // [kStages]  each CTA: MMAs reading the stage retired
   uint64_t* tfull = bars + 2 * kStages; // [2]        each CTA: accumulator complete
   uint64_t* tempty = tfull + 2;         // [2]        leader: both epilogues drained the accumulator
-  uint64_t* bfull = tempty + 2;         // leader: both weight halves resident
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  uint64_t* bfull = tempty + 2;         // leader: both weight halves resident (resident mode)
+  uint64_t* wfull = bfull + 1;          // [9] leader: weight ring slot filled by both CTAs (streaming mode)
+  uint64_t* wempty = wfull + 9;         // [9] each CTA: MMAs reading the slot retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wempty + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -105,6 +111,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
       for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 16); }
       ptx::mbar_init(bfull, 1);
+      for (int i = 0; i < 9; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -120,13 +127,15 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   if (warp == 0) {
     // ============================== TMA producer (both CTAs) ==============================
     if (lane == 0) {
-      if (rank == 0) ptx::mbar_arrive_expect_tx(bfull, 2u * K::BBYTES);
-      for (int blk = 0; blk < 9 * K::KC; ++blk) {
-        const int tap = blk / K::KC, kc = blk % K::KC;
-        ptx::tma_load_2d_pair(sB + blk * K::BBLK, &tm_w, bfull, kc * 64, (p.layer * 9 + tap) * C + (int)rank * (C / 2));
+      if constexpr (!K::STREAM) {
+        if (rank == 0) ptx::mbar_arrive_expect_tx(bfull, 2u * K::BBYTES);
+        for (int blk = 0; blk < 9 * K::KC; ++blk) {
+          const int tap = blk / K::KC, kc = blk % K::KC;
+          ptx::tma_load_2d_pair(sB + blk * K::BBLK, &tm_w, bfull, kc * 64, (p.layer * 9 + tap) * C + (int)rank * (C / 2));
+        }
       }
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, ws = 0;
+      uint32_t phase = 0, wphase = 0;
       bool ok = true;
       long long t_wait = 0;
       const long long t_begin = clock64();
@@ -140,6 +149,14 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2u * kStageBytes);
             ptx::tma_load_2d_pair(sA + stage * kStagePitch, &tm_act, &full[stage], kc * 64, row0 + (MODE == 0 ? dci - 1 : 0));
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            if constexpr (K::STREAM) {          // the nine tap blocks of this slice follow their activations
+              for (int tap = 0; tap < 9 && ok; ++tap) {
+                if (!ptx::mbar_wait(&wempty[ws], wphase ^ 1u)) { atomicExch(p.error, ERR_EMPTY); ok = false; break; }
+                if (rank == 0) ptx::mbar_arrive_expect_tx(&wfull[ws], 2u * K::BBLK);
+                ptx::tma_load_2d_pair(sB + ws * K::BBLK, &tm_w, &wfull[ws], kc * 64, (p.layer * 9 + tap) * C + (int)rank * (C / 2));
+                if (++ws == 9) { ws = 0; wphase ^= 1u; }
+              }
+            }
           }
       }
       if (p.prof && rank == 0) {
@@ -156,10 +173,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       constexpr uint32_t idesc = ptx::idesc_bf16(256, C);
       const uint64_t a_desc0 = ptx::smem_desc_sw128(ptx::smem_u32(sA));
       const uint64_t b_desc0 = ptx::smem_desc_sw128(ptx::smem_u32(sB));
-      bool ok = ptx::mbar_wait(bfull, 0);
+      bool ok = K::STREAM ? true : ptx::mbar_wait(bfull, 0);
       if (!ok && lane == 0) atomicExch(p.error, ERR_BFULL);
-      int stage = 0, it = 0;
-      uint32_t phase = 0;
+      int stage = 0, it = 0, ws = 0;
+      uint32_t phase = 0, wphase = 0;
       long long t_full = 0, t_tempty = 0;
       const long long t_begin = clock64();
       for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
@@ -177,25 +194,47 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
             ptx::tc_fence_after();
             const uint64_t a_stage = a_desc0 + (uint64_t)((stage * kStagePitch) >> 4);
             const uint64_t b_slice = b_desc0 + (uint64_t)((kc * K::BBLK) >> 4);
-            if (ptx::elect_one()) {
+            if constexpr (!K::STREAM) {
+              if (ptx::elect_one()) {
 #pragma unroll
-              for (int dri = 0; dri < 3; ++dri) {
+                for (int dri = 0; dri < 3; ++dri) {
 #pragma unroll
-                for (int dcu = 0; dcu < (MODE == 0 ? 1 : 3); ++dcu) {
-                  const int dci = MODE == 0 ? dcs : dcu;
-                  // MODE 0: the stage IS the dc copy, the row tap is a 16-row (2 KB) offset.
-                  // MODE 1/2: copy row 17 + 16*(dr) + dc holds the tap's first row (dr, dc in -1..1).
-                  const int arow = MODE == 0 ? dri * 16 : 17 + 16 * (dri - 1) + (dcu - 1);
+                  for (int dcu = 0; dcu < (MODE == 0 ? 1 : 3); ++dcu) {
+                    const int dci = MODE == 0 ? dcs : dcu;
+                    // MODE 0: the stage IS the dc copy, the row tap is a 16-row (2 KB) offset.
+                    // MODE 1/2: copy row 17 + 16*(dr) + dc holds the tap's first row (dr, dc in -1..1).
+                    const int arow = MODE == 0 ? dri * 16 : 17 + 16 * (dri - 1) + (dcu - 1);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    uint64_t ad = a_stage + (uint64_t)((arow * 128 + k * 32) >> 4);
-                    if (MODE == 2) ad |= (uint64_t)(arow & 7) << 49;
-                    const uint64_t bd = b_slice + (uint64_t)((((dri * 3 + dci) * K::KC) * K::BBLK + k * 32) >> 4);
-                    ptx::umma_bf16<2>(tmem_d, ad, bd, idesc, (kc | dcs | dri | dcu | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                      uint64_t ad = a_stage + (uint64_t)((arow * 128 + k * 32) >> 4);
+                      if (MODE == 2) ad |= (uint64_t)(arow & 7) << 49;
+                      const uint64_t bd = b_slice + (uint64_t)((((dri * 3 + dci) * K::KC) * K::BBLK + k * 32) >> 4);
+                      ptx::umma_bf16<2>(tmem_d, ad, bd, idesc, (kc | dcs | dri | dcu | k) != 0 ? 1u : 0u);
+                    }
                   }
                 }
+                ptx::umma_commit_pair(&empty[stage], 3);        // frees the stage in both CTAs
               }
-              ptx::umma_commit_pair(&empty[stage], 3);        // frees the stage in both CTAs
+            } else {
+              // streaming weights (single activation copy only): one ring slot per tap
+#pragma unroll 1
+              for (int tap = 0; tap < 9 && ok; ++tap) {
+                if (!ptx::mbar_wait(&wfull[ws], wphase)) { if (lane == 0) atomicExch(p.error, ERR_BFULL); ok = false; break; }
+                ptx::tc_fence_after();
+                const int arow = 17 + 16 * (tap / 3 - 1) + (tap % 3 - 1);
+                const uint64_t a_tap = a_stage + (uint64_t)((arow * 128) >> 4);
+                const uint64_t b_tap = b_desc0 + (uint64_t)((ws * K::BBLK) >> 4);
+                if (ptx::elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16<2>(tmem_d, a_tap + (uint64_t)((k * 32) >> 4), b_tap + (uint64_t)((k * 32) >> 4), idesc,
+                                      (kc | tap | k) != 0 ? 1u : 0u);
+                  ptx::umma_commit_pair(&wempty[ws], 3);
+                  if (tap == 8) ptx::umma_commit_pair(&empty[stage], 3);
+                }
+                __syncwarp();
+                if (++ws == 9) { ws = 0; wphase ^= 1u; }
+              }
             }
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -411,5 +450,10 @@ int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtenso
     if (mode == 3) return launch_conv_heads<64, 3>(tm_act, tm_w, tm_out, args, n_sm, stream);
     return launch_conv_heads<64, 2>(tm_act, tm_w, tm_out, args, n_sm, stream);
   }
-  return azg_fail(AZG_E_ARG, "conv3x3: resident-weight kernel supports 64 or 128 channels");
+  if (C == 256) {
+    if (args.head_host) return azg_fail(AZG_E_ARG, "conv3x3: the fused-heads epilogue is built for 64 and 128 channels");
+    if (mode == 3) return launch_conv<256, false, 3>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    return launch_conv<256, false, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
+  }
+  return azg_fail(AZG_E_ARG, "conv3x3: channels must be 64, 128 or 256");
 }

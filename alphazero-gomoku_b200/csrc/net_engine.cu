@@ -92,7 +92,8 @@ extern "C" int azg_net_destroy(azg_net* n) {
 
 extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_batch, azg_net** out) {
   if (!out || n_blocks < 0 || n_blocks > AZG_NET_MAX_BLOCKS || max_batch < 1) return azg_fail(AZG_E_ARG, "azg_net_create: bad argument");
-  if (channels != 64 && channels != 128) return azg_fail(AZG_E_ARG, "azg_net_create: channels must be 64 or 128");
+  if (channels != 64 && channels != 128 && channels != 256)
+    return azg_fail(AZG_E_ARG, "azg_net_create: channels must be 64, 128 or 256");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
     cudaGetLastError();
@@ -134,6 +135,7 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
     const char* m = getenv("AZG_CONV_MODE");        // experiment switch for the activation staging variant
     n->conv_mode = m ? atoi(m) : 1;                 // 1: single activation copy per slice (fastest, validated)
     if (n->conv_mode < 0 || n->conv_mode > 3) n->conv_mode = 1;
+    if (channels == 256 && n->conv_mode != 3) n->conv_mode = 1;      // the streaming-weights kernel needs the single-copy layout
   }
   for (int i = 0; i < 3; ++i)
     if ((rc = make_map(&n->tm_act[i], n->act[i], n->rows, C, (uint32_t)azg_conv3x3_rows(n->conv_mode)))) { azg_net_destroy(n); return rc; }
@@ -215,7 +217,7 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
     a.n_boards = n_ptr; a.max_boards = max_boards; a.layer = l; a.relu = 1;
     a.shift_host = n->shift_host.data() + (size_t)l * C; a.error = n->error_dev; a.prof = n->profiling ? n->prof_dev : nullptr;
     a.head_host = nullptr; a.hidden = nullptr;
-    const bool fuse = heads && l == n_layers - 1 && (l & 1) == 1;     // last conv2: fuse the 1x1 head convs, skip the store
+    const bool fuse = heads && C <= 128 && l == n_layers - 1 && (l & 1) == 1;     // last conv2: fuse the 1x1 head convs, skip the store
     if (fuse) { a.head_host = n->head_host.data(); a.hidden = n->hidden; fused_heads = true; }
     if ((l & 1) == 0) { a.residual = nullptr; a.out = n->act[t]; rc = azg_conv3x3_launch(C, n->conv_mode, n->tm_act[x], n->tm_w, n->tm_st[t], a, n->n_sm, s); }
     else { a.residual = n->act[x]; a.out = fuse ? nullptr : n->act[y]; rc = azg_conv3x3_launch(C, n->conv_mode, n->tm_act[t], n->tm_w, n->tm_st[y], a, n->n_sm, s); int tmp = x; x = y; y = tmp; }

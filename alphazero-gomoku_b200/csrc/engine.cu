@@ -162,7 +162,12 @@ extern "C" int azg_search_fill(azg_engine* e, int32_t* n_leaves_host, int32_t* n
     if (n_leaves_host) *n_leaves_host = h[0];
     if (n_active_host) *n_active_host = h[1];
     if (n_roots_host) *n_roots_host = h[3];
-    if (h[2] > 0) return azg_fail(AZG_E_SEARCH, "search error on at least one game (node slab full, path too deep or terminal root); see azg_search_stats");
+    if (h[2] > 0) {
+      char msg[200];
+      snprintf(msg, sizeof msg, "search error on %d game(s): node slab full (raise node_capacity or pass reserve to azg_search_advance), "
+               "path deeper than %d, or a root that is already terminal; azg_search_stats reports the error bits", h[2], AZG_MAX_DEPTH);
+      return azg_fail(AZG_E_SEARCH, msg);
+    }
   }
   return AZG_OK;
 }

@@ -29,8 +29,8 @@ namespace {
 //   0: three column-shifted copies (dc = -1, 0, +1) of 160 rows; row taps are 2 KB-aligned offsets.
 //   1: ONE copy of 162 rows per 64-channel slice; every tap is a row offset of the same tile
 //      (start address not aligned to the 1024-byte swizzle period, descriptor base_offset = 0).
-//   2: as 1, with the descriptor's base_offset field set to (start >> 7) & 7 (WRONG results on
-//      B200: the swizzle is applied to absolute address bits; kept only as the recorded experiment).
+//      (Setting base_offset = (start >> 7) & 7 instead was tried and gives WRONG results on B200: the
+//      swizzle is a function of absolute shared-memory address bits.)
 //   3: as 1 but with the direct (row-per-thread) epilogue instead of the staged one.
 template <int MODE>
 struct Stage {
@@ -202,12 +202,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
                   for (int dcu = 0; dcu < (MODE == 0 ? 1 : 3); ++dcu) {
                     const int dci = MODE == 0 ? dcs : dcu;
                     // MODE 0: the stage IS the dc copy, the row tap is a 16-row (2 KB) offset.
-                    // MODE 1/2: copy row 17 + 16*(dr) + dc holds the tap's first row (dr, dc in -1..1).
+                    // MODE 1/3: copy row 17 + 16*(dr) + dc holds the tap's first row (dr, dc in -1..1).
                     const int arow = MODE == 0 ? dri * 16 : 17 + 16 * (dri - 1) + (dcu - 1);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                      uint64_t ad = a_stage + (uint64_t)((arow * 128 + k * 32) >> 4);
-                      if (MODE == 2) ad |= (uint64_t)(arow & 7) << 49;
+                      const uint64_t ad = a_stage + (uint64_t)((arow * 128 + k * 32) >> 4);
                       const uint64_t bd = b_slice + (uint64_t)((((dri * 3 + dci) * K::KC) * K::BBLK + k * 32) >> 4);
                       ptx::umma_bf16<2>(tmem_d, ad, bd, idesc, (kc | dcs | dri | dcu | k) != 0 ? 1u : 0u);
                     }
@@ -271,7 +270,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     // both bank-conflict free and the layout of a SWIZZLE_64B TMA box): residual rows are read with
     // coalesced 16-byte loads (8 rows x 64 B per instruction) and transposed through the tile, results
     // leave by one TMA store per tile.  MODE 0 keeps the direct row-per-thread accesses.
-    constexpr bool STAGED = MODE == 1 || MODE == 2;
+    constexpr bool STAGED = MODE == 1;
     constexpr int NCHUNK = NCH / 32;
     const uint32_t tile = ptx::smem_u32(sEpi) + (uint32_t)(warp - 2) * 2048u;
     const uint32_t own = tile + (uint32_t)lane * 64u;                      // this thread's row in the tile
@@ -442,13 +441,13 @@ int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtenso
     if (mode == 0) return launch_conv_heads<128, 0>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 1) return launch_conv_heads<128, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 3) return launch_conv_heads<128, 3>(tm_act, tm_w, tm_out, args, n_sm, stream);
-    return launch_conv_heads<128, 2>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    return azg_fail(AZG_E_ARG, "conv3x3: unknown staging mode");
   }
   if (C == 64) {
     if (mode == 0) return launch_conv_heads<64, 0>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 1) return launch_conv_heads<64, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 3) return launch_conv_heads<64, 3>(tm_act, tm_w, tm_out, args, n_sm, stream);
-    return launch_conv_heads<64, 2>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    return azg_fail(AZG_E_ARG, "conv3x3: unknown staging mode");
   }
   if (C == 256) {
     if (args.head_host) return azg_fail(AZG_E_ARG, "conv3x3: the fused-heads epilogue is built for 64 and 128 channels");

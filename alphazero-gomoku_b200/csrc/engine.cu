@@ -142,11 +142,15 @@ extern "C" int azg_get_roots(azg_engine* e, azg_pos* roots_out) {
   return AZG_OK;
 }
 
-extern "C" int azg_search_begin(azg_engine* e, const int32_t* plies, int n_sims) {
+extern "C" int azg_search_begin_masked(azg_engine* e, const int32_t* plies, int n_sims, const int32_t* mask) {
   if (!e || n_sims < 0) return azg_fail(AZG_E_ARG, "azg_search_begin: bad argument");
   e->dev.n_sims = n_sims;
-  azg_begin_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, plies, n_sims);
+  azg_begin_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, plies, n_sims, mask);
   return azg_check_launch("azg_search_begin");
+}
+
+extern "C" int azg_search_begin(azg_engine* e, const int32_t* plies, int n_sims) {
+  return azg_search_begin_masked(e, plies, n_sims, nullptr);
 }
 
 extern "C" int azg_search_fill(azg_engine* e, int32_t* n_leaves_host, int32_t* n_active_host, int32_t* n_roots_host) {

@@ -525,10 +525,15 @@ azg_commit_kernel(azg_dev e, const float* __restrict__ probs, const double* __re
 // run control
 // ------------------------------------------------------------------------------------------------
 // Start a run on every game (new_mcts_alpha.py:77-83): fix the root key, look it up.
-extern "C" __global__ void __launch_bounds__(128) azg_begin_kernel(azg_dev e, const int32_t* __restrict__ plies, int n_sims) {
+extern "C" __global__ void __launch_bounds__(128)
+azg_begin_kernel(azg_dev e, const int32_t* __restrict__ plies, int n_sims, const int32_t* __restrict__ mask) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= e.G) return;
   azg_ctl* ctl = e.ctl + g;
+  if (mask && !mask[g]) {            // this game sits the run out (evaluation arena: the other model is to move)
+    if (lane_id() == 0) { ctl->state = AZG_ST_DONE; ctl->err = 0; ctl->sims_left = 0; ctl->root_node = -1; ctl->susp = 0; ctl->n_pending = 0; }
+    return;
+  }
   const WPos root = wpos_load(&ctl->root);
   int state = AZG_ST_RUN, err = 0, root_node = -1;
   if (wpos_winner(root, e.rule) != 0 || !wpos_any_empty(root)) {

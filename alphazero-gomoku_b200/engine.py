@@ -146,10 +146,12 @@ class SearchEngine:
         check(lib.azg_get_roots(self._h, ptr(out)))
         return out
 
-    def begin(self, n_sims: int, plies: torch.Tensor | None = None):
+    def begin(self, n_sims: int, plies: torch.Tensor | None = None, mask: torch.Tensor | None = None):
+        """Start a run; games with mask == 0 (if given) sit it out."""
         self._sync_stream()
         p = None if plies is None else plies.to(self.device, torch.int32).contiguous()
-        check(lib.azg_search_begin(self._h, ptr(p), int(n_sims)))
+        m = None if mask is None else mask.to(self.device, torch.int32).contiguous()
+        check(lib.azg_search_begin_masked(self._h, ptr(p), int(n_sims), ptr(m)))
 
     def fill(self):
         """-> (n_leaves, n_more, n_roots) after a host sync: batch size, games that need another

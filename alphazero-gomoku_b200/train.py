@@ -134,6 +134,67 @@ def play_game_and_collect(mcts: MCTS, game, temp_fn, max_moves=225, use_symmetri
 # ------------------------------------------------------------------ evaluation arena (train.py:418-486)
 def evaluate_models(model_new: PyTorchModel, model_best: PyTorchModel, game_name: str, n_games: int = 20,
                     n_simulations: int = 100, cpuct: float = 1.0) -> Tuple[int, float, int]:
+    """Same protocol as the reference - random first stone in the central 9x9, the new model starts the
+    even games, argmax play without noise, one search tree per (model, game) kept for the whole game -
+    with all ``n_games`` games advancing in lock step on two batched engines (one per model)."""
+    from .engine import SearchEngine
+    dev = torch.device(model_new.device if str(model_new.device) != "cuda" else f"cuda:{torch.cuda.current_device()}")
+    G = n_games
+    center, radius = model_new.board_size // 2, 4
+    boards = np.zeros((G, 225), np.int8)
+    lasts = np.zeros(G, np.int32)
+    for i in range(G):
+        r, c = random.randint(center - radius, center + radius), random.randint(center - radius, center + radius)
+        boards[i, r * 15 + c] = 1
+        lasts[i] = r * 15 + c
+    engines = [SearchEngine(0, G, cpuct=cpuct, queue_len=32, node_capacity=max(4096, 3 * n_simulations), noise=False, device=dev)
+               for _ in range(2)]                                     # 0: new model, 1: best model
+    nets = [model_new._ensure_engine(), model_best._ensure_engine()]
+    rules = engines[0].rules
+    pos = rules.pack(boards, np.full(G, 2, np.int32), lasts, np.zeros((G, 2), np.int32), np.ones(G, np.int32))
+    new_starts = (torch.arange(G, device=dev) % 2 == 0)
+    alive = torch.ones(G, dtype=torch.bool, device=dev)
+    status = torch.zeros(G, dtype=torch.int32, device=dev)
+    probs = torch.empty((G * 32, 225), dtype=torch.float32, device=dev)
+    reserve = n_simulations + n_simulations // 32 + 8
+    for move_number in range(1, 226):
+        if not bool(alive.any()):
+            break
+        players = pos[:, 16]
+        new_to_move = ((players == 1) & new_starts) | ((players == 2) & ~new_starts)
+        action = torch.full((G,), -1, dtype=torch.int32, device=dev)
+        for side, (eng, net) in enumerate(zip(engines, nets)):
+            mask = alive & (new_to_move if side == 0 else ~new_to_move)
+            if not bool(mask.any()):
+                continue
+            eng.set_roots(pos, clear_tree=False)
+            eng.advance(torch.full((G,), -1, dtype=torch.int32, device=dev), gc=True, reserve=reserve)
+            eng.begin(n_simulations, mask=mask)
+            while True:
+                n_leaves, n_more, _ = eng.fill()
+                if n_leaves > 0:
+                    net.forward_leaves(eng, probs)
+                    eng.commit(probs, None)
+                if n_more == 0:
+                    break
+            pi, _ = eng.result()
+            action = torch.where(mask, pi.argmax(dim=1).to(torch.int32), action)
+        st = rules.play(pos, action)
+        status = torch.where(alive, st, status)
+        alive = alive & ((st & 4) == 0)
+    for e in engines:
+        e.close()
+    winner = (status & 3).cpu().numpy()
+    starts = new_starts.cpu().numpy()
+    draws = int((winner == 0).sum())
+    new_wins = int((((winner == 1) & starts) | ((winner == 2) & ~starts)).sum())
+    return new_wins, new_wins / float(n_games), draws
+
+
+def evaluate_models_serial(model_new: PyTorchModel, model_best: PyTorchModel, game_name: str, n_games: int = 20,
+                           n_simulations: int = 100, cpuct: float = 1.0) -> Tuple[int, float, int]:
+    """The reference's loop verbatim in shape (one game at a time through the drop-in ``MCTS``); kept as
+    the cross-check of the batched arena (same seeds -> same results)."""
     new_wins = draws = 0
     for i in range(n_games):
         game = GameClass(size=model_new.board_size)

@@ -109,6 +109,9 @@ int azg_get_roots(azg_engine* e, azg_pos* roots_out);
 /* MCTS.run, first half (new_mcts_alpha.py:77-83): fix the root keys and the budget.
  * plies[g] is the reference's move_number (NULL = the root's own ply count). */
 int azg_search_begin(azg_engine* e, const int32_t* plies, int n_sims);
+/* As above, but games with mask[g] == 0 sit this run out (their result rows are zero).  Used by the
+ * evaluation arena (train.py:418-486), where two models alternate on the same set of games. */
+int azg_search_begin_masked(azg_engine* e, const int32_t* plies, int n_sims, const int32_t* mask);
 /* Run simulations on every game until its leaf queue is full or its budget is spent
  * (MCTS.search, new_mcts_alpha.py:102-151), then assemble the leaf batch.
  * The outputs (each may be NULL) receive the batch size, the number of games that need

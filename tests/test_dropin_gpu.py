@@ -77,3 +77,21 @@ def test_train_loop_smoke(tmp_path):
     s, p, z = buf.sample(16)
     assert s.shape == (16, 3, 15, 15) and p.shape == (16, 225) and z.shape == (16, 1)
     assert best.net.channels == 64
+
+
+def test_batched_arena_equals_game_by_game():
+    """evaluate_models on the two batched engines == the reference-shaped loop (one game at a time
+    through the drop-in MCTS) for the same random openings: argmax play is deterministic."""
+    import random
+    from alphazero_gomoku_b200 import train as tr
+    from alphazero_gomoku_b200.network import PyTorchModel
+    torch.manual_seed(11)
+    a = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    torch.manual_seed(12)
+    b = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    random.seed(5)
+    batched = tr.evaluate_models(a, b, "gomoku", n_games=6, n_simulations=40, cpuct=1.0)
+    random.seed(5)
+    serial = tr.evaluate_models_serial(a, b, "gomoku", n_games=6, n_simulations=40, cpuct=1.0)
+    assert batched == serial, (batched, serial)
+    assert 0 <= batched[0] + batched[2] <= 6

@@ -73,6 +73,59 @@ class ReplayBuffer:
         return len(self.buffer)
 
 
+class DeviceReplayBuffer:
+    """The same interface with the rows kept in HBM (float32[capacity, 901] ring: planes 675, pi 225, z):
+    ``add_rows`` takes ``SelfPlay.drain_examples()`` without a host copy, ``sample`` returns device
+    tensors that ``train_batch`` consumes directly.  ``to_host`` / ``from_host`` convert to and from the
+    reference's buffer (and therefore its pickle format)."""
+
+    def __init__(self, capacity: int = 20000, device="cuda"):
+        self.capacity = capacity
+        self.rows = torch.empty((capacity, 901), dtype=torch.float32, device=device)
+        self.size = 0
+        self.head = 0                      # next slot to overwrite (oldest first, like deque(maxlen))
+
+    def add_rows(self, rows: torch.Tensor):
+        rows = rows.to(self.rows.device, torch.float32)
+        if rows.shape[0] >= self.capacity:
+            rows = rows[-self.capacity:]
+        n = rows.shape[0]
+        first = min(n, self.capacity - self.head)
+        self.rows[self.head:self.head + first] = rows[:first]
+        if n > first:
+            self.rows[: n - first] = rows[first:]
+        self.head = (self.head + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def add(self, examples):
+        if examples:
+            flat = np.stack([np.concatenate([np.asarray(s, np.float32).reshape(-1), np.asarray(p, np.float32).reshape(-1),
+                                             np.array([z], np.float32)]) for s, p, z in examples])
+            self.add_rows(torch.from_numpy(flat))
+
+    def sample(self, batch_size: int, generator=None):
+        idx = torch.randint(0, self.size, (batch_size,), device=self.rows.device, generator=generator)
+        r = self.rows[idx]
+        return r[:, :675].reshape(-1, 3, 15, 15), r[:, 675:900], r[:, 900:901]
+
+    def __len__(self):
+        return self.size
+
+    def to_host(self) -> ReplayBuffer:
+        buf = ReplayBuffer(self.capacity)
+        order = torch.arange(self.size, device=self.rows.device)
+        if self.size == self.capacity:
+            order = (order + self.head) % self.capacity          # oldest first
+        buf.add_rows(self.rows[order])
+        return buf
+
+    @classmethod
+    def from_host(cls, buf: ReplayBuffer, device="cuda") -> "DeviceReplayBuffer":
+        out = cls(buf.capacity, device)
+        out.add(list(buf.buffer))
+        return out
+
+
 def save_replay_buffer(buffer: ReplayBuffer, filepath: str):
     try:
         with open(filepath, "wb") as f:
@@ -304,7 +357,9 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
     model_candidate.net.load_state_dict(model_best.net.state_dict())
     model_candidate.optimizer.load_state_dict(model_best.optimizer.state_dict())
     buffer_path = os.path.join(model_dir, "replay_buffer_latest.pkl")
-    buffer = load_replay_buffer(buffer_path, buffer_size) or ReplayBuffer(capacity=buffer_size)
+    host_buffer = load_replay_buffer(buffer_path, buffer_size)
+    buffer = DeviceReplayBuffer.from_host(host_buffer, dev) if host_buffer else DeviceReplayBuffer(buffer_size, dev)
+    sample_gen = torch.Generator(device=dev)
     my_games = (games_per_iteration + world - 1) // world
     G = concurrent_games or min(my_games, 2048)
     for it in range(next_iteration_continuation, next_iteration_continuation + num_iterations):
@@ -331,17 +386,15 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
             print(f"[self-play] {finished * world} games, {rows.shape[0]} examples, winners {winners}, {(time.time() - t0) / 60:.2f} min")
         # ---- training (train.py:754-763): every rank draws the same batches (shared seed) and takes its slice
         n_batches = len(buffer) // batch_size
-        rng_state = random.getstate()
-        random.seed(1000003 * it + 17)
+        sample_gen.manual_seed(1000003 * it + 17)      # identical buffers + identical draws on every rank
         for ep in range(epochs_per_iter):
             tot = 0.0
             for _ in range(n_batches):
-                states, pis, zs = buffer.sample(batch_size)
+                states, pis, zs = buffer.sample(batch_size, generator=sample_gen)
                 sl = slice(rank * batch_size // world, (rank + 1) * batch_size // world)
                 tot += train_batch_dp(model_candidate, states[sl], pis[sl], zs[sl])["total_loss"]
             if rank == 0 and n_batches:
                 print(f"[train] epoch {ep + 1}/{epochs_per_iter} mean loss {tot / n_batches:.4f}")
-        random.setstate(rng_state)
         # ---- evaluation and accept / reject (train.py:768-827), rank 0 decides
         accept = torch.zeros(1, dtype=torch.int32, device=dev)
         if rank == 0:
@@ -363,7 +416,7 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
             model_candidate.optimizer.load_state_dict(model_best.optimizer.state_dict())
         if rank == 0 and it % save_every == 0:
             model_best.save(os.path.join(model_dir, f"snapshot_iter{it}_{datetime.now():%Y%m%d_%H%M%S}.pt"))
-            save_replay_buffer(buffer, buffer_path)
+            save_replay_buffer(buffer.to_host(), buffer_path)
         if rank == 0:
             print(f"=== ITER {it} done in {(time.time() - t0) / 60:.2f} min ===")
     return model_best

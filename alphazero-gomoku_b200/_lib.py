@@ -67,6 +67,7 @@ PROTOTYPES = {
     "azg_search_begin": (_I, [_P, _P, _I]),
     "azg_search_begin_masked": (_I, [_P, _P, _I, _P]),
     "azg_search_fill": (_I, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "azg_search_read_counters": (_I, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "azg_search_counters": (_P, [_P]),
     "azg_search_leaf_planes": (_I, [_P, _P]),
     "azg_search_commit": (_I, [_P, _P, _P]),

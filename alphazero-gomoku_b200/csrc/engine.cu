@@ -176,6 +176,19 @@ extern "C" int azg_search_fill(azg_engine* e, int32_t* n_leaves_host, int32_t* n
   return AZG_OK;
 }
 
+// Host copy of the counters written by the last azg_search_fill (synchronises the engine's stream only).
+extern "C" int azg_search_read_counters(azg_engine* e, int32_t* n_leaves_host, int32_t* n_active_host, int32_t* n_roots_host) {
+  if (!e) return azg_fail(AZG_E_ARG, "null engine");
+  int32_t* h = (int32_t*)e->pinned;
+  AZG_CUDA(cudaMemcpyAsync(h, e->dev.counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  AZG_CUDA(cudaStreamSynchronize(e->stream));
+  if (n_leaves_host) *n_leaves_host = h[0];
+  if (n_active_host) *n_active_host = h[1];
+  if (n_roots_host) *n_roots_host = h[3];
+  if (h[2] > 0) return azg_fail(AZG_E_SEARCH, "search error on at least one game; azg_search_stats reports the error bits");
+  return AZG_OK;
+}
+
 extern "C" const int32_t* azg_search_counters(const azg_engine* e) { return e ? e->dev.counters : nullptr; }
 
 extern "C" int azg_search_leaf_planes(azg_engine* e, float* planes) {

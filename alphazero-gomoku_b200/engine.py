@@ -165,6 +165,13 @@ class SearchEngine:
         self._sync_stream()
         check(lib.azg_search_fill(self._h, None, None, None))
 
+    def read_counters(self):
+        """-> (n_leaves, n_more, n_roots) of the last ``fill_async`` (synchronises this engine's stream only)."""
+        self._sync_stream()
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        check(lib.azg_search_read_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def counters_ptr(self) -> int:
         return int(lib.azg_search_counters(self._h))
 

@@ -90,9 +90,43 @@ class SelfPlay:
         self.total_launches += launches + 1
         return eng.result()
 
-    def step(self):
+    # the same run split into its asynchronous pieces (used by PipelinedSelfPlay)
+    def search_begin(self):
         eng = self.engine
+        eng.begin(self.n_sims)
+        self._launches = 1
+        if self.noise is not None:
+            eng._sync_stream()
+            check(lib.azg_selfplay_noise(eng._h, self.draw, ptr(self.noise)))
+            self._launches += 1
+        eng.fill_async()
+        self._launches += 2
+
+    def search_round(self) -> bool:
+        """Consume the outstanding fill: evaluate + commit its leaf batch and queue the next fill.
+        Returns False when the run is complete."""
+        eng = self.engine
+        n_leaves, n_more, _ = eng.read_counters()
+        if n_leaves > 0:
+            self.net.forward_leaves(eng, self.probs)
+            eng.commit(self.probs, self.noise)
+            self._launches += 1 + self.n_layers + 2 + 1
+            self.total_evals += n_leaves
+            self.total_rounds += 1
+        if n_more == 0:
+            self.total_sims += self.G * self.n_sims
+            self.total_launches += self._launches + 1
+            return False
+        eng.fill_async()
+        self._launches += 2
+        return True
+
+    def step(self):
         pi, visits = self.search()
+        return self.finish_step(pi)
+
+    def finish_step(self, pi):
+        eng = self.engine
         self.last_pi = pi
         self.draw += 1
         check(lib.azg_selfplay_choose(eng._h, ptr(pi), C.c_float(self.temp_threshold), self.draw, ptr(self.actions)))
@@ -118,3 +152,76 @@ class SelfPlay:
     def split(rows: torch.Tensor):
         """-> (states [n,3,15,15], pis [n,225], zs [n,1]) as ReplayBuffer.sample returns them (train.py:287-293)."""
         return rows[:, :675].reshape(-1, 3, 15, 15), rows[:, 675:900], rows[:, 900:901]
+
+
+class PipelinedSelfPlay:
+    """Two half-size ``SelfPlay`` groups on two CUDA streams.  While one group's leaf batch is in the
+    tensor-core trunk, the other group's FILL kernel (a warp per game, no shared memory, latency
+    bound) runs next to it on the same SMs, so the tree walk disappears from the critical path.
+    Results per game are identical to the unpipelined driver (games are independent and the RNG is
+    keyed by the global game id)."""
+
+    def __init__(self, model, n_games: int = 2048, game_base: int = 0, device="cuda:0", **kw):
+        if n_games % 2:
+            raise ValueError("n_games must be even")
+        self.device = torch.device(device)
+        self.G = n_games
+        h = n_games // 2
+        cap = kw.pop("example_capacity", 1 << 20)
+        self.halves = [SelfPlay(model, n_games=h, game_base=game_base + i * h, device=device, example_capacity=cap // 2, **kw)
+                       for i in range(2)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        self.n_sims = self.halves[0].n_sims
+
+    def close(self):
+        for s in self.halves:
+            s.close()
+
+    def step(self):
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+        for sp, st in zip(self.halves, self.streams):
+            with torch.cuda.stream(st):
+                sp.search_begin()
+        active = [True, True]
+        while any(active):
+            for i, (sp, st) in enumerate(zip(self.halves, self.streams)):
+                if active[i]:
+                    with torch.cuda.stream(st):
+                        active[i] = sp.search_round()
+        out = []
+        for sp, st in zip(self.halves, self.streams):
+            with torch.cuda.stream(st):
+                pi, _ = sp.engine.result()
+                out.append(sp.finish_step(pi))
+        for st in self.streams:
+            cur.wait_stream(st)
+        return torch.cat(out)
+
+    # aggregated views used by bench.py / tests
+    @property
+    def last_pi(self):
+        return torch.cat([s.last_pi for s in self.halves])
+
+    @property
+    def actions(self):
+        return torch.cat([s.actions for s in self.halves])
+
+    @property
+    def done(self):
+        return torch.cat([s.done for s in self.halves])
+
+    def counters(self) -> dict:
+        keys = ("total_sims", "total_evals", "total_rounds", "total_launches")
+        return {k: sum(getattr(s, k) for s in self.halves) for k in keys}
+
+    def stats(self) -> dict:
+        a, b = (s.engine.stats() for s in self.halves)
+        out = {k: a[k] + b[k] for k in a}
+        out["max_nodes"] = max(a["max_nodes"], b["max_nodes"])
+        out["error_bits"] = a["error_bits"] | b["error_bits"]
+        return out
+
+    def drain_examples(self) -> torch.Tensor:
+        return torch.cat([s.drain_examples() for s in self.halves])

@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--node-capacity", type=int, default=16384)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
+                    help="game groups per GPU: 2 overlaps one group's tree walk with the other group's leaf evaluation")
     return ap.parse_args()
 
 
@@ -56,7 +58,7 @@ def workload(args):
                         f"{args.blocks}x{args.channels} ResNet, leaf queue 32",
             "games_per_gpu": args.games, "sims_per_move": args.sims, "net": f"{args.blocks}x{args.channels}",
             "rule": args.rule, "cache": "working set (tree slabs + activations, >10 GB) exceeds the 126 MB L2",
-            "parallelism": f"independent games per GPU x{args.gpus}"}
+            "parallelism": f"independent games per GPU x{args.gpus}", "game_groups_per_gpu": args.pipeline}
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -221,7 +223,7 @@ def run_ours(args):
     import torch.distributed as dist
     import alphazero_gomoku_b200 as m
     from alphazero_gomoku_b200.network import PyTorchModel
-    from alphazero_gomoku_b200.selfplay import SelfPlay, TRUNK_FLOPS
+    from alphazero_gomoku_b200.selfplay import PipelinedSelfPlay, SelfPlay, TRUNK_FLOPS
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,10 +236,16 @@ def run_ours(args):
 
     torch.manual_seed(0)
     model = PyTorchModel(board_size=15, n_res_blocks=args.blocks, channels=args.channels, device=str(dev))
-    sp = SelfPlay(model, rule=rule, n_games=args.games, n_sims=args.sims, cpuct=1.0, queue_len=32,
-                  node_capacity=args.node_capacity, noise=True, alpha=0.05, eps=0.15, noise_plies=10, temp_threshold=10.0,
-                  example_capacity=1 << 18, seed=12345, game_base=rank * args.games, device=str(dev))
-    scatter_start(sp, 777 + rank)
+    kw = dict(rule=rule, n_sims=args.sims, cpuct=1.0, queue_len=32, node_capacity=args.node_capacity, noise=True, alpha=0.05,
+              eps=0.15, noise_plies=10, temp_threshold=10.0, example_capacity=1 << 18, seed=12345)
+    if args.pipeline == 2:
+        sp = PipelinedSelfPlay(model, n_games=args.games, game_base=rank * args.games, device=str(dev), **kw)
+        units = sp.halves
+    else:
+        sp = SelfPlay(model, n_games=args.games, game_base=rank * args.games, device=str(dev), **kw)
+        units = [sp]
+    for i, u in enumerate(units):
+        scatter_start(u, 777 + 2 * rank + i)
 
     def barrier():
         torch.cuda.synchronize()
@@ -245,61 +253,88 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def totals():
+        return {k: sum(getattr(u, k) for u in units) for k in ("total_sims", "total_evals", "total_launches", "total_rounds")}
+
+    def reset_cursors():
+        for u in units:
+            u.cursor.zero_()
+
     for _ in range(args.warmup):
         sp.step()
-        sp.cursor.zero_()
+        reset_cursors()
 
     # ---- timed region A: device-resident self-play
     clocks = ClockSampler(local)
-    sims0, evals0, launches0, rounds0 = sp.total_sims, sp.total_evals, sp.total_launches, sp.total_rounds
-    sp.net.profile(True)
-    sp.net.profile_read()
+    t_before = totals()
+    for u in units:
+        u.net.profile(True)
+        u.net.profile_read()
+        u.net.profile_counters()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         sp.step()
-        sp.cursor.zero_()
+        reset_cursors()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    trunk_ms, conv_launches = sp.net.profile_read()
-    pipe = sp.net.profile_counters()
-    sp.net.profile(False)
-    sims, evals = sp.total_sims - sims0, sp.total_evals - evals0
-    launches, rounds = sp.total_launches - launches0, sp.total_rounds - rounds0
+    trunk_ms, conv_launches, pipe = 0.0, 0, {}
+    for u in units:
+        t_ms, n_l = u.net.profile_read()
+        trunk_ms += t_ms
+        conv_launches += n_l
+        for k, v in u.net.profile_counters().items():
+            pipe[k] = pipe.get(k, 0) + v
+        u.net.profile(False)
+    t_after = totals()
+    sims, evals = t_after["total_sims"] - t_before["total_sims"], t_after["total_evals"] - t_before["total_evals"]
+    launches, rounds = t_after["total_launches"] - t_before["total_launches"], t_after["total_rounds"] - t_before["total_rounds"]
     clk = clocks.stop()
-    stats = sp.engine.stats()
+    per_unit = [u.engine.stats() for u in units]
+    stats = {k: sum(x[k] for x in per_unit) for k in per_unit[0]}
+    stats["max_nodes"] = max(x["max_nodes"] for x in per_unit)
+    stats["error_bits"] = 0
+    for x in per_unit:
+        stats["error_bits"] |= x["error_bits"]
 
     # ---- timed region B: the same step driven through HOST buffers
-    G = args.games
-    h_boards = torch.empty((G, 225), dtype=torch.int8).pin_memory()
-    h_meta = torch.empty((G, 5), dtype=torch.int32).pin_memory()          # player, last, caps0, caps1, plies
-    h_pi = torch.empty((G, 225), dtype=torch.float32).pin_memory()
-    h_act = torch.empty((G, 2), dtype=torch.int32).pin_memory()           # action, status
-    R = sp.engine.rules
+    host = []
+    for u in units:
+        g = u.G
+        host.append(dict(boards=torch.empty((g, 225), dtype=torch.int8).pin_memory(),
+                         meta=torch.empty((g, 5), dtype=torch.int32).pin_memory(),          # player, last, caps0, caps1, plies
+                         pi=torch.empty((g, 225), dtype=torch.float32).pin_memory(),
+                         act=torch.empty((g, 2), dtype=torch.int32).pin_memory()))          # action, status
 
-    def download():
-        boards, players, lasts, caps, plies = R.unpack(sp.engine.roots())
-        h_boards.copy_(boards, non_blocking=True)
-        h_meta.copy_(torch.stack([players, lasts, caps[:, 0], caps[:, 1], plies], dim=1), non_blocking=True)
+    def download(u, hb):
+        boards, players, lasts, caps, plies = u.engine.rules.unpack(u.engine.roots())
+        hb["boards"].copy_(boards, non_blocking=True)
+        hb["meta"].copy_(torch.stack([players, lasts, caps[:, 0], caps[:, 1], plies], dim=1), non_blocking=True)
 
-    download()
+    for u, hb in zip(units, host):
+        download(u, hb)
     torch.cuda.synchronize()
-    h2d = h_boards.numel() + h_meta.numel() * 4
-    d2h = h_pi.numel() * 4 + h_act.numel() * 4 + h2d
+    h2d = sum(hb["boards"].numel() + hb["meta"].numel() * 4 for hb in host)
+    d2h = sum(hb["pi"].numel() * 4 + hb["act"].numel() * 4 for hb in host) + h2d
 
     def e2e_step():
-        d_boards = h_boards.to(dev, non_blocking=True)
-        d_meta = h_meta.to(dev, non_blocking=True)
-        pos = R.pack(d_boards, d_meta[:, 0].contiguous(), d_meta[:, 1].contiguous(), d_meta[:, 2:4].contiguous(), d_meta[:, 4].contiguous())
-        sp.engine.set_roots(pos, clear_tree=False)
+        for u, hb in zip(units, host):
+            d_boards = hb["boards"].to(dev, non_blocking=True)
+            d_meta = hb["meta"].to(dev, non_blocking=True)
+            pos = u.engine.rules.pack(d_boards, d_meta[:, 0].contiguous(), d_meta[:, 1].contiguous(), d_meta[:, 2:4].contiguous(),
+                                      d_meta[:, 4].contiguous())
+            u.engine.set_roots(pos, clear_tree=False)
         status = sp.step()
-        h_pi.copy_(sp.last_pi, non_blocking=True)
-        h_act.copy_(torch.stack([sp.actions, status], dim=1), non_blocking=True)
-        download()
+        off = 0
+        for u, hb in zip(units, host):
+            hb["pi"].copy_(u.last_pi, non_blocking=True)
+            hb["act"].copy_(torch.stack([u.actions, status[off:off + u.G]], dim=1), non_blocking=True)
+            off += u.G
+            download(u, hb)
         torch.cuda.synchronize()
-        sp.cursor.zero_()
+        reset_cursors()
 
     e2e_step()
     barrier()
@@ -347,9 +382,10 @@ def run_ours(args):
                          "algorithmic_flops_per_position_per_launch": TRUNK_FLOPS[args.channels],
                          "pipeline_cycles_per_board": {k: round(v / max(pipe["boards"], 1), 1) for k, v in pipe.items() if k != "boards"}},
             "clocks": clk,
-            "search": {"rounds": int(rounds), "games_in_error": stats["games_in_error"], "error_bits": stats["error_bits"],
-                       "max_nodes_per_game": stats["max_nodes"], "dropped_trees": stats["dropped_trees"], "engine_gb": sp.engine.memory_bytes / 1e9,
-                       "net_gb": sp.net.memory_bytes / 1e9},
+            "search": {"rounds": int(rounds), "game_groups": len(units), "games_in_error": stats["games_in_error"],
+                       "error_bits": stats["error_bits"], "max_nodes_per_game": stats["max_nodes"],
+                       "dropped_trees": stats["dropped_trees"], "engine_gb": sum(u.engine.memory_bytes for u in units) / 1e9,
+                       "net_gb": sum(u.net.memory_bytes for u in units) / 1e9},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)

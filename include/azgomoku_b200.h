@@ -119,6 +119,9 @@ int azg_search_begin_masked(azg_engine* e, const int32_t* plies, int n_sims, con
  * in the batch (the only case in which the reference draws Dirichlet noise,
  * new_mcts_alpha.py:171); passing all NULL skips the host synchronisation. */
 int azg_search_fill(azg_engine* e, int32_t* n_leaves_host, int32_t* n_active_host, int32_t* n_roots_host);
+/* The three outputs of the last azg_search_fill that was issued with NULL outputs (asynchronously):
+ * synchronises the engine's stream only, so another engine's work on another stream keeps running. */
+int azg_search_read_counters(azg_engine* e, int32_t* n_leaves_host, int32_t* n_active_host, int32_t* n_roots_host);
 /* Device address of int32 {n_leaves, n_active, n_errors, n_roots, ...} for on-device consumers. */
 const int32_t* azg_search_counters(const azg_engine* e);
 /* Encoded planes of the current leaf batch, float32[n_leaves][3][15][15] - what the

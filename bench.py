@@ -48,8 +48,10 @@ def parse():
     ap.add_argument("--node-capacity", type=int, default=16384)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
-                    help="game groups per GPU: 2 overlaps one group's tree walk with the other group's leaf evaluation")
+    ap.add_argument("--pipeline", type=int, default=1, choices=[1, 2],
+                    help="game groups per GPU: 2 overlaps one group's tree walk with the other group's leaf evaluation "
+                         "(+1.6 %% sims/s measured; the per-launch CUDA-event timing of the trunk kernel, and with it the "
+                         "roofline block, is only meaningful with 1 because the two groups' event brackets overlap)")
     return ap.parse_args()
 
 

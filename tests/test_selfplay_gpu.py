@@ -187,3 +187,26 @@ def test_results_do_not_depend_on_sharding():
     assert len(set(whole.actions.cpu().tolist())) > 1, "games must have diverged (noise + sampling)"
     for s in (whole, lo, hi):
         s.close()
+
+
+def test_pipelined_driver_matches_plain_driver():
+    """Two game groups on two streams (fill of one group overlapping the other's leaf evaluation) must
+    produce exactly the moves and visit distributions of the single-group driver."""
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import PipelinedSelfPlay, SelfPlay
+    torch.manual_seed(6)
+    model = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    kw = dict(n_sims=96, node_capacity=2048, example_capacity=1 << 14, seed=5, noise=True, alpha=0.3, eps=0.25)
+    plain = SelfPlay(model, n_games=32, **kw)
+    piped = PipelinedSelfPlay(model, n_games=32, **kw)
+    for step in range(10):
+        plain.step()
+        piped.step()
+        torch.cuda.synchronize()
+        assert torch.equal(plain.actions, piped.actions), step
+        assert torch.equal(plain.last_pi, piped.last_pi), step
+    c = piped.counters()
+    assert c["total_sims"] == plain.total_sims and c["total_evals"] == plain.total_evals
+    assert piped.stats()["games_in_error"] == 0
+    plain.close()
+    piped.close()

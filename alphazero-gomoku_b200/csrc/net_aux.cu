@@ -284,31 +284,34 @@ __global__ void __launch_bounds__(256) head1_kernel(HeadArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// heads, part 2: policy_fc + softmax, value_fc1 + ReLU + value_fc2 + tanh, 32 boards per block
+// heads, part 2: policy_fc + softmax, value_fc1 + ReLU + value_fc2 + tanh, 16 boards per block
 // ------------------------------------------------------------------------------------------------
-constexpr int kHead2Smem = (AZG_HID * 32 + 32 * 228 + 32 * 64) * 4;
+// 16 boards (half a feature tile) per block: 62 KB of shared memory, three blocks per SM.
+constexpr int kH2B = 16;
+constexpr int kHead2Smem = (AZG_HID * kH2B + kH2B * 228 + kH2B * 64) * 4;
 
 __global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
   extern __shared__ float sm[];
-  float* s_h = sm;                       // [676][32]
-  float* s_lg = sm + AZG_HID * 32;       // [32][228] logits
-  float* s_v = s_lg + 32 * 228;          // [32][64]
+  float* s_h = sm;                         // [676][16]
+  float* s_lg = sm + AZG_HID * kH2B;       // [16][228] logits
+  float* s_v = s_lg + kH2B * 228;          // [16][64]
   int n = *a.n_boards;
   if (n > a.max_boards) n = a.max_boards;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tiles = (n + 31) >> 5;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int n_units = (n + kH2B - 1) / kH2B;
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int tile = unit >> 1, half = unit & 1, b0 = unit * kH2B;
     __syncthreads();
-    const float4* src = reinterpret_cast<const float4*>(a.hidden + (size_t)tile * (AZG_HID * 32));
+    const float4* src = reinterpret_cast<const float4*>(a.hidden + (size_t)tile * (AZG_HID * 32) + half * kH2B);
     float4* dst = reinterpret_cast<float4*>(s_h);
-    for (int i = tid; i < AZG_HID * 8; i += 256) dst[i] = src[i];
+    for (int i = tid; i < AZG_HID * 4; i += 256) dst[i] = src[(i >> 2) * 8 + (i & 3)];     // row k: 16 of the 32 boards
     __syncthreads();
     // policy_fc (network.py:106): logits[b][o] = bias[o] + sum_k W[o][k] h[b][k]
     if (tid < 225) {
-      float acc[32];
+      float acc[kH2B];
       const float bias = a.pol_b[tid];
 #pragma unroll
-      for (int b = 0; b < 32; ++b) acc[b] = bias;
+      for (int b = 0; b < kH2B; ++b) acc[b] = bias;
       for (int k0 = 0; k0 < 450; k0 += 10) {
         float wv[10];                                   // ten weight loads in flight per thread
 #pragma unroll
@@ -316,9 +319,9 @@ __global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
 #pragma unroll
         for (int u = 0; u < 10; ++u) {
           const float w = wv[u];
-          const float4* h = reinterpret_cast<const float4*>(s_h + (k0 + u) * 32);
+          const float4* h = reinterpret_cast<const float4*>(s_h + (k0 + u) * kH2B);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < kH2B / 4; ++q) {
             const float4 hv = h[q];
             acc[4 * q] = fmaf(w, hv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(w, hv.y, acc[4 * q + 1]);
             acc[4 * q + 2] = fmaf(w, hv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, hv.w, acc[4 * q + 3]);
@@ -326,31 +329,37 @@ __global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
         }
       }
 #pragma unroll
-      for (int b = 0; b < 32; ++b) s_lg[b * 228 + tid] = acc[b];
+      for (int b = 0; b < kH2B; ++b) s_lg[b * 228 + tid] = acc[b];
     }
     // value_fc1 + ReLU (network.py:113)
     if (tid < 64) {
-      float acc[32];
+      float acc[kH2B];
       const float bias = a.v1_b[tid];
 #pragma unroll
-      for (int b = 0; b < 32; ++b) acc[b] = bias;
-      for (int k = 0; k < 225; ++k) {
-        const float w = __ldg(a.v1_wt + (size_t)k * 64 + tid);
-        const float4* h = reinterpret_cast<const float4*>(s_h + (450 + k) * 32);
+      for (int b = 0; b < kH2B; ++b) acc[b] = bias;
+      for (int k0 = 0; k0 < 225; k0 += 5) {
+        float wv[5];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 hv = h[q];
-          acc[4 * q] = fmaf(w, hv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(w, hv.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(w, hv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, hv.w, acc[4 * q + 3]);
+        for (int u = 0; u < 5; ++u) wv[u] = __ldg(a.v1_wt + (size_t)(k0 + u) * 64 + tid);
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const float w = wv[u];
+          const float4* h = reinterpret_cast<const float4*>(s_h + (450 + k0 + u) * kH2B);
+#pragma unroll
+          for (int q = 0; q < kH2B / 4; ++q) {
+            const float4 hv = h[q];
+            acc[4 * q] = fmaf(w, hv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(w, hv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(w, hv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, hv.w, acc[4 * q + 3]);
+          }
         }
       }
 #pragma unroll
-      for (int b = 0; b < 32; ++b) s_v[b * 64 + tid] = fmaxf(acc[b], 0.f);
+      for (int b = 0; b < kH2B; ++b) s_v[b * 64 + tid] = fmaxf(acc[b], 0.f);
     }
     __syncthreads();
-    // softmax over all 225 logits (network.py:180), 4 boards per warp
-    for (int bb = 0; bb < 4; ++bb) {
-      const int b = warp * 4 + bb, gb = tile * 32 + b;
+    // softmax over all 225 logits (network.py:180), 2 boards per warp
+    for (int bb = 0; bb < kH2B / 8; ++bb) {
+      const int b = warp * (kH2B / 8) + bb, gb = b0 + b;
       if (gb >= n) break;
       float v[8], mx = -INFINITY;
 #pragma unroll
@@ -376,10 +385,10 @@ __global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
         if (lane + 32 * j < 225) a.probs[(size_t)gb * 225 + lane + 32 * j] = v[j] * inv;
     }
     // value_fc2 + tanh (network.py:114-115)
-    if (a.values && tid < 32 && tile * 32 + tid < n) {
+    if (a.values && tid < kH2B && b0 + tid < n) {
       float acc = a.v2_b[0];
       for (int o = 0; o < 64; ++o) acc = fmaf(s_v[tid * 64 + o], a.v2_w[o], acc);
-      a.values[tile * 32 + tid] = tanhf(acc);
+      a.values[b0 + tid] = tanhf(acc);
     }
   }
 }
@@ -399,8 +408,8 @@ int azg_heads_launch(int C, const HeadArgs& a, int n_sm, cudaStream_t stream, bo
   }
   cudaError_t e = cudaFuncSetAttribute(head2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHead2Smem);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
-  int tiles = (a.max_boards + 31) / 32;
-  int grid2 = tiles < n_sm ? tiles : n_sm;
+  int tiles = (a.max_boards + kH2B - 1) / kH2B;
+  int grid2 = tiles < 3 * n_sm ? tiles : 3 * n_sm;
   head2_kernel<<<grid2, 256, kHead2Smem, stream>>>(a);
   return azg_check_launch("head2_kernel");
 }

@@ -60,6 +60,7 @@ class SelfPlay:
         self.total_launches = 0
         self.games_finished = 0
         self.last_pi = None
+        self._graph_rounds = 0
 
     def close(self):
         self.engine.close()
@@ -122,8 +123,64 @@ class SelfPlay:
         return True
 
     def step(self):
+        if self._graph_rounds:
+            return self._step_graph()
         pi, visits = self.search()
         return self.finish_step(pi)
+
+    # ------------------------------------------------------------------ whole ply as one CUDA graph
+    def enable_graph(self, extra_rounds: int = 1):
+        """Capture one full ply - begin, noise, a FIXED number of FILL -> leaf evaluation -> COMMIT rounds,
+        result, move choice, advance, game-end handling, restart - into a CUDA graph.  A run of n
+        simulations queues at most n + n/queue_len + 1 leaves, i.e. needs at most
+        ceil(that / queue_len) + 1 rounds; rounds after a game (or all games) finished are no-ops
+        (every kernel reads its work count from device memory), so no host synchronisation is left in
+        the ply.  Results are identical to the host-driven loop."""
+        q = self.engine.queue_len
+        leaves = self.n_sims + self.n_sims // q + 1
+        self._graph_rounds = (leaves + q - 1) // q + extra_rounds
+        self._draw_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._graph = None
+
+    def _ply_async(self):
+        """Everything of one ply, without host synchronisation (capturable)."""
+        eng = self.engine
+        eng.begin(self.n_sims)
+        if self.noise is not None:
+            eng._sync_stream()
+            check(lib.azg_selfplay_noise(eng._h, self.draw, ptr(self.noise)))
+        for _ in range(self._graph_rounds):
+            eng.fill_async()
+            self.net.forward_leaves(eng, self.probs)
+            eng.commit(self.probs, self.noise)
+        check(lib.azg_search_result(eng._h, ptr(self._pi), ptr(self._visits)))
+        check(lib.azg_selfplay_choose(eng._h, ptr(self._pi), C.c_float(self.temp_threshold), self.draw + 1, ptr(self.actions)))
+        reserve = self.n_sims + self.n_sims // eng.queue_len + 8
+        check(lib.azg_search_advance(eng._h, ptr(self.actions), 1, reserve, ptr(self._status)))
+        check(lib.azg_selfplay_finish(eng._h, ptr(self._status), self.max_moves, int(self.use_symmetries), ptr(self.examples),
+                                      self.capacity, ptr(self.cursor), ptr(self.done), ptr(self.winners)))
+        check(lib.azg_set_roots(eng._h, ptr(self.empty_roots), ptr(self.done), 1))
+
+    def _step_graph(self):
+        """The RNG draw counter is a kernel argument, so the graph is re-captured when it changes;
+        capture costs a few hundred microseconds against a ply of hundreds of milliseconds."""
+        if not hasattr(self, "_pi"):
+            self._pi = torch.empty((self.G, 225), dtype=torch.float32, device=self.device)
+            self._visits = torch.empty((self.G, 225), dtype=torch.int32, device=self.device)
+            self._status = torch.empty(self.G, dtype=torch.int32, device=self.device)
+        g = torch.cuda.CUDAGraph()
+        self.net.profile(False)
+        with torch.cuda.graph(g):
+            self.engine._sync_stream()
+            self._ply_async()
+        g.replay()
+        self._graph = g
+        self.draw += 1
+        self.last_pi = self._pi
+        self.total_sims += self.G * self.n_sims
+        self.total_rounds += self._graph_rounds
+        self.total_launches += 2 + self._graph_rounds * (2 + 1 + self.n_layers + 2 + 1) + 5
+        return self._status
 
     def finish_step(self, pi):
         eng = self.engine

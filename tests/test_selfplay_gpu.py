@@ -210,3 +210,26 @@ def test_pipelined_driver_matches_plain_driver():
     assert piped.stats()["games_in_error"] == 0
     plain.close()
     piped.close()
+
+
+def test_graph_captured_ply_matches_host_driven_loop():
+    """One CUDA graph per ply (fixed number of rounds, no host sync) == the host-driven loop."""
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import SelfPlay
+    torch.manual_seed(8)
+    model = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    kw = dict(n_sims=100, node_capacity=2048, example_capacity=1 << 14, seed=3, noise=True, alpha=0.3, eps=0.25, max_moves=40)
+    plain = SelfPlay(model, n_games=24, **kw)
+    graph = SelfPlay(model, n_games=24, **kw)
+    graph.enable_graph()
+    for step in range(45):                      # long enough for games to end and restart (max_moves 40)
+        plain.step()
+        graph.step()
+        torch.cuda.synchronize()
+        assert torch.equal(plain.actions, graph.actions), step
+        assert torch.equal(plain.last_pi, graph.last_pi), step
+        assert torch.equal(plain.done, graph.done), step
+    assert plain.n_examples() == graph.n_examples() > 0
+    assert graph.engine.stats()["evals"] == plain.engine.stats()["evals"]
+    plain.close()
+    graph.close()

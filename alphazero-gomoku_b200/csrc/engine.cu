@@ -115,7 +115,7 @@ extern "C" int azg_destroy(azg_engine* e) {
   cudaFree(d.ctl); cudaFree(d.P); cudaFree(d.Nv); cudaFree(d.W); cudaFree(d.key); cudaFree(d.meta); cudaFree(d.slots);
   cudaFree(d.freelist); cudaFree(d.path); cudaFree(d.P64); cudaFree(d.leaf_game); cudaFree(d.leaf_node);
   cudaFree(d.counters); cudaFree(e->stats_dev);
-  cudaFree(e->sp.ex_key); cudaFree(e->sp.ex_player); cudaFree(e->sp.ex_pi); cudaFree(e->sp.n_plies);
+  cudaFree(e->sp.ex_key); cudaFree(e->sp.ex_player); cudaFree(e->sp.ex_pi); cudaFree(e->sp.n_plies); cudaFree(e->sp.n_done);
   if (e->pinned) cudaFreeHost(e->pinned);
   delete e;
   return AZG_OK;

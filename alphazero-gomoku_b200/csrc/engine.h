@@ -8,6 +8,7 @@ struct azg_selfplay_buf {
   int32_t* ex_player = nullptr;   // [G][max_plies]     side to move
   float* ex_pi = nullptr;         // [G][max_plies][225] search policy
   int32_t* n_plies = nullptr;     // [G] plies played in the current game
+  int32_t* n_done = nullptr;      // [G] games finished so far (part of the RNG counter: streams never repeat)
   int32_t max_plies = 0;
 };
 

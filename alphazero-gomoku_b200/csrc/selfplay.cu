@@ -17,9 +17,9 @@
 struct Philox {
   uint32_t key[2];
   uint32_t ctr[4];
-  __device__ Philox(unsigned long long seed, uint32_t c0, uint32_t c1, uint32_t c2) {
+  __device__ Philox(unsigned long long seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3 = 0) {
     key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
-    ctr[0] = c0; ctr[1] = c1; ctr[2] = c2; ctr[3] = 0;
+    ctr[0] = c0; ctr[1] = c1; ctr[2] = c2; ctr[3] = c3;      // next() increments ctr[3]: keep the low 8 bits of c3 zero
   }
   __device__ uint4 next() {                       // one block of 4 x 32 random bits; bumps ctr[3]
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3]++;
@@ -57,17 +57,22 @@ __device__ double log_gamma_variate(Philox& rng, double alpha) {
 }
 
 // noise[g][0..224] ~ Dirichlet(alpha, ..., alpha) over all 225 actions (new_mcts_alpha.py:172).
-__global__ void __launch_bounds__(128) noise_kernel(azg_dev e, unsigned long long draw, double* __restrict__ noise) {
+// The stream of a draw is keyed by (global game id, action, caller's draw index, games finished by
+// this slot, ply of the current game): nothing has to change on the host from ply to ply, which is
+// what lets a whole ply be captured once in a CUDA graph.
+__global__ void __launch_bounds__(128)
+noise_kernel(azg_dev e, azg_selfplay_buf sp, unsigned long long draw, double* __restrict__ noise) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= e.G) return;
   const int l = lane_id();
+  const uint32_t epoch = ((uint32_t)(sp.n_done ? sp.n_done[g] : 0) * 1024u + (uint32_t)(sp.n_plies ? sp.n_plies[g] : 0)) << 8;
   double lg[8], mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int a = l + 32 * j;
     lg[j] = -INFINITY;
     if (a < AZG_A) {
-      Philox rng(e.seed ^ 0xD1B54A32D192ED03ULL, (uint32_t)(g + e.game_base), (uint32_t)a, (uint32_t)draw);
+      Philox rng(e.seed ^ 0xD1B54A32D192ED03ULL, (uint32_t)(g + e.game_base), (uint32_t)a, (uint32_t)draw, epoch);
       lg[j] = log_gamma_variate(rng, e.alpha);
       mx = fmax(mx, lg[j]);
     }
@@ -127,7 +132,7 @@ choose_kernel(azg_dev e, azg_selfplay_buf sp, const float* __restrict__ pi, floa
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1) { const float o = __shfl_up_sync(AZG_FULL, incl, s); if (l >= s) incl += o; }
     const float total = __shfl_sync(AZG_FULL, incl, 31);
-    Philox rng(e.seed ^ 0x8CB92BA72F3D8DD7ULL, (uint32_t)(g + e.game_base), (uint32_t)ply, (uint32_t)draw);
+    Philox rng(e.seed ^ 0x8CB92BA72F3D8DD7ULL, (uint32_t)(g + e.game_base), (uint32_t)ply, (uint32_t)draw, (uint32_t)sp.n_done[g] << 8);
     const uint4 r = rng.next();
     const float u = (float)(rng.uniform53(r.x, r.y) * (double)total);
     float run = incl - mine;
@@ -215,7 +220,7 @@ finish_games_kernel(azg_dev e, azg_selfplay_buf sp, const int32_t* __restrict__ 
       }
     }
   }
-  if (threadIdx.x == 0) sp.n_plies[g] = 0;
+  if (threadIdx.x == 0) { sp.n_plies[g] = 0; sp.n_done[g] += 1; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -229,19 +234,21 @@ extern "C" int azg_selfplay_enable(azg_engine* e, int max_plies) {
   AZG_CUDA(cudaSetDevice(e->cfg.device));
   const size_t slots = (size_t)e->dev.G * max_plies;
   if (cudaMalloc((void**)&e->sp.ex_key, slots * 16 * 4) != cudaSuccess || cudaMalloc((void**)&e->sp.ex_player, slots * 4) != cudaSuccess ||
-      cudaMalloc((void**)&e->sp.ex_pi, slots * AZG_A * 4) != cudaSuccess || cudaMalloc((void**)&e->sp.n_plies, (size_t)e->dev.G * 4) != cudaSuccess) {
+      cudaMalloc((void**)&e->sp.ex_pi, slots * AZG_A * 4) != cudaSuccess || cudaMalloc((void**)&e->sp.n_plies, (size_t)e->dev.G * 4) != cudaSuccess ||
+      cudaMalloc((void**)&e->sp.n_done, (size_t)e->dev.G * 4) != cudaSuccess) {
     cudaGetLastError();
     return azg_fail(AZG_E_NOMEM, "azg_selfplay_enable: cudaMalloc failed");
   }
   e->bytes += (int64_t)(slots * (16 * 4 + 4 + AZG_A * 4) + (size_t)e->dev.G * 4);
   e->sp.max_plies = max_plies;
   AZG_CUDA(cudaMemset(e->sp.n_plies, 0, (size_t)e->dev.G * 4));
+  AZG_CUDA(cudaMemset(e->sp.n_done, 0, (size_t)e->dev.G * 4));
   return AZG_OK;
 }
 
 extern "C" int azg_selfplay_noise(azg_engine* e, uint64_t draw, double* noise) {
   if (!e || !noise) return azg_fail(AZG_E_ARG, "null argument");
-  noise_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, draw, noise);
+  noise_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, e->sp, draw, noise);
   return azg_check_launch("noise_kernel");
 }
 

@@ -139,7 +139,6 @@ class SelfPlay:
         q = self.engine.queue_len
         leaves = self.n_sims + self.n_sims // q + 1
         self._graph_rounds = (leaves + q - 1) // q + extra_rounds
-        self._draw_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._graph = None
 
     def _ply_async(self):
@@ -154,7 +153,7 @@ class SelfPlay:
             self.net.forward_leaves(eng, self.probs)
             eng.commit(self.probs, self.noise)
         check(lib.azg_search_result(eng._h, ptr(self._pi), ptr(self._visits)))
-        check(lib.azg_selfplay_choose(eng._h, ptr(self._pi), C.c_float(self.temp_threshold), self.draw + 1, ptr(self.actions)))
+        check(lib.azg_selfplay_choose(eng._h, ptr(self._pi), C.c_float(self.temp_threshold), self.draw, ptr(self.actions)))
         reserve = self.n_sims + self.n_sims // eng.queue_len + 8
         check(lib.azg_search_advance(eng._h, ptr(self.actions), 1, reserve, ptr(self._status)))
         check(lib.azg_selfplay_finish(eng._h, ptr(self._status), self.max_moves, int(self.use_symmetries), ptr(self.examples),
@@ -162,20 +161,18 @@ class SelfPlay:
         check(lib.azg_set_roots(eng._h, ptr(self.empty_roots), ptr(self.done), 1))
 
     def _step_graph(self):
-        """The RNG draw counter is a kernel argument, so the graph is re-captured when it changes;
-        capture costs a few hundred microseconds against a ply of hundreds of milliseconds."""
-        if not hasattr(self, "_pi"):
+        """Captured once, replayed every ply (the RNG streams are keyed on device-side counters)."""
+        if self._graph is None:
             self._pi = torch.empty((self.G, 225), dtype=torch.float32, device=self.device)
             self._visits = torch.empty((self.G, 225), dtype=torch.int32, device=self.device)
             self._status = torch.empty(self.G, dtype=torch.int32, device=self.device)
-        g = torch.cuda.CUDAGraph()
-        self.net.profile(False)
-        with torch.cuda.graph(g):
-            self.engine._sync_stream()
-            self._ply_async()
-        g.replay()
-        self._graph = g
-        self.draw += 1
+            g = torch.cuda.CUDAGraph()
+            self.net.profile(False)
+            with torch.cuda.graph(g):
+                self.engine._sync_stream()
+                self._ply_async()
+            self._graph = g
+        self._graph.replay()
         self.last_pi = self._pi
         self.total_sims += self.G * self.n_sims
         self.total_rounds += self._graph_rounds
@@ -185,7 +182,6 @@ class SelfPlay:
     def finish_step(self, pi):
         eng = self.engine
         self.last_pi = pi
-        self.draw += 1
         check(lib.azg_selfplay_choose(eng._h, ptr(pi), C.c_float(self.temp_threshold), self.draw, ptr(self.actions)))
         status = eng.advance(self.actions, gc=True, reserve=self.n_sims + self.n_sims // self.engine.queue_len + 8)
         check(lib.azg_selfplay_finish(eng._h, ptr(status), self.max_moves, int(self.use_symmetries), ptr(self.examples),

@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--node-capacity", type=int, default=16384)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay each ply as one CUDA graph (fixed round count, no host synchronisation inside the ply); "
+                         "the per-launch trunk timing is then unavailable (events are not recorded inside the graph)")
     ap.add_argument("--pipeline", type=int, default=1, choices=[1, 2],
                     help="game groups per GPU: 2 overlaps one group's tree walk with the other group's leaf evaluation "
                          "(+1.6 %% sims/s measured; the per-launch CUDA-event timing of the trunk kernel, and with it the "
@@ -248,6 +251,8 @@ def run_ours(args):
         units = [sp]
     for i, u in enumerate(units):
         scatter_start(u, 777 + 2 * rank + i)
+        if args.graph:
+            u.enable_graph()
 
     def barrier():
         torch.cuda.synchronize()
@@ -256,7 +261,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def totals():
-        return {k: sum(getattr(u, k) for u in units) for k in ("total_sims", "total_evals", "total_launches", "total_rounds")}
+        t = {k: sum(getattr(u, k) for u in units) for k in ("total_sims", "total_launches", "total_rounds")}
+        t["total_evals"] = sum(u.engine.stats()["evals"] for u in units)      # device-side count (also valid in graph mode)
+        return t
 
     def reset_cursors():
         for u in units:

@@ -148,7 +148,8 @@ int azg_search_stats(azg_engine* e, uint64_t* out_host);
 /* Allocate example capture for games of up to max_plies moves (train.py max_moves). */
 int azg_selfplay_enable(azg_engine* e, int max_plies);
 /* noise float64[G][225] ~ Dirichlet(alpha) over all 225 actions (new_mcts_alpha.py:172);
- * `draw` distinguishes successive draws. */
+ * The Philox stream is keyed by (global game id, action, `draw`, games finished in this slot, ply of
+ * the current game); `draw` is an extra caller-chosen index and may stay constant. */
 int azg_selfplay_noise(azg_engine* e, uint64_t draw, double* noise);
 /* sample_action_from_pi with temperature max(0, 1 - ply/temp_threshold) (train.py:252-266,
  * 647-648), illegal-pick fallback to argmax (train.py:380-382); records (position, pi) as the

@@ -385,7 +385,13 @@ def run_ours(args):
             "e2e": {"value": tot_sims / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "conv3x3_pair_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak if peak else None,
+                         # DRAM bytes per launch from the committed ncu --set full capture (65 536 positions per launch, the
+                         # same size as the bench's rounds): mean of a layer without (8.58 GB) and with residual (12.89 GB)
+                         "traffic": 10.734e9 if (args.channels == 128 and args.games * 32 == 65536) else None,
+                         "traffic_source": "profiles/conv3x3_r01_final_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum",
+                         "algorithmic_bytes_per_launch": int((evals / max(rounds, 1)) * 225 * args.channels * 2 * 2.5),
+                         "peak_source": peak_src,
                          "launches": int(conv_launches), "avg_launch_ms": trunk_ms / max(conv_launches, 1),
                          "trunk_share_of_step": trunk_ms / ms if ms else None,
                          "algorithmic_flops_per_position_per_launch": TRUNK_FLOPS[args.channels],

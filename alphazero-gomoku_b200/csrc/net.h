@@ -22,7 +22,8 @@ struct ConvArgs {
   const float* head_host;         // HOST [3*C + 6]: fused 1x1 head weights, BN scale[3], shift[3]; null = plain layer
   float* hidden;                  // head features, tiled [b/32][676][32] (fused-heads layer only)
   int* error;                     // device flag set by the pipeline watchdogs
-  unsigned long long* prof;       // optional device counters [8] (cycles spent waiting per role), or null
+  unsigned long long* prof;       // optional device counters [16] (cycles spent waiting per role), or null
+  int prof_detail;                // also clock the phases of one epilogue warp (slightly intrusive)
 };
 
 // mode: activation staging variant of the kernel (see net_conv.cu); tm_act must have been encoded

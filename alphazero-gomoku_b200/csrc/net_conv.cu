@@ -263,7 +263,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     const bool pad = (qi < 16) || ((qi & 15) == 15);
     int it = 0;
     bool ok = true;
-    long long t_tfull = 0;
+    long long t_tfull = 0, t_wr = 0, t_rt = 0, t_ld = 0, t_cs = 0, t_st = 0;
+    const bool detail = p.prof != nullptr && p.prof_detail != 0;      // per-phase clocks only on request (AZG_CONV_PHASES=1)
     const long long t_begin = clock64();
     // MODE >= 1: global traffic of the epilogue is coalesced through a per-warp 2 KB staging tile
     // (32 rows x 32 channels, 64-byte rows, 16-byte units XOR-swizzled with (row >> 1) & 3, which is
@@ -311,10 +312,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
           uint32_t v[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * C + ch), v);
           if constexpr (STAGED) {
+            long long tp = detail ? clock64() : 0;
             if (p.out) {                       // the previous TMA store must have finished reading the tile
               if (lane == 0) ptx::bulk_wait_read0();
               __syncwarp();
             }
+            if (detail) { t_wr += clock64() - tp; tp = clock64(); }
             if (has_res) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -329,8 +332,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
               }
               __syncwarp();
             }
+            if (detail) t_rt += clock64() - tp;
           }
+          long long tq = detail ? clock64() : 0;
           ptx::tmem_ld_wait();
+          if (detail) { t_ld += clock64() - tq; tq = clock64(); }
           uint32_t outv[16];
 #pragma unroll
           for (int h = 0; h < 16; ++h) {
@@ -359,12 +365,14 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
               for (int u = 0; u < 4; ++u)
                 ptx::sts128(own + (uint32_t)(((uint32_t)u ^ own_sw) * 16u),
                             make_uint4(outv[4 * u], outv[4 * u + 1], outv[4 * u + 2], outv[4 * u + 3]));
+              if (detail) { t_cs += clock64() - tq; tq = clock64(); }
               ptx::fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
                 ptx::tma_store_2d(&tm_out, sEpi + (warp - 2) * 2048, ch, (int)grow0);
                 ptx::bulk_commit();
               }
+              if (detail) t_st += clock64() - tq;
             } else {
               ptx::stg256(orow + ch, &outv[0]);
               ptx::stg256(orow + ch + 16, &outv[8]);
@@ -389,6 +397,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     if (p.prof && rank == 0 && warp == 2 && lane == 0) {   // one representative epilogue warp
       atomicAdd(p.prof + 5, (unsigned long long)t_tfull);
       atomicAdd(p.prof + 6, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(p.prof + 8, (unsigned long long)t_wr);
+      atomicAdd(p.prof + 9, (unsigned long long)t_rt);
+      atomicAdd(p.prof + 10, (unsigned long long)t_ld);
+      atomicAdd(p.prof + 11, (unsigned long long)t_cs);
+      atomicAdd(p.prof + 12, (unsigned long long)t_st);
     }
   }
 

@@ -14,7 +14,7 @@ int azg_pack_launch_stem(const float*, const float*, int, float*, cudaStream_t);
 int azg_pack_launch_transpose(const float*, int, int, float*, cudaStream_t);
 
 struct azg_net {
-  int device = 0, n_blocks = 0, C = 0, max_batch = 0, n_sm = 0, loaded = 0, conv_mode = 0;
+  int device = 0, n_blocks = 0, C = 0, max_batch = 0, n_sm = 0, loaded = 0, conv_mode = 0, prof_detail = 0;
   int64_t bytes = 0;
   size_t rows = 0;                       // rows of one activation buffer (front pad + boards*256 + back pad)
   __nv_bfloat16* w3 = nullptr;           // [(layer*9+tap)*C + cout][cin]
@@ -132,6 +132,8 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
   cudaMemset(n->prof_dev, 0, 128);
   cudaMemset(n->hidden, 0, (size_t)((max_batch + 31) / 32) * AZG_HIDDEN_TILE * 4);
   {
+    const char* pd = getenv("AZG_CONV_PHASES");      // clock the epilogue phases too when profiling
+    n->prof_detail = pd ? atoi(pd) : 0;
     const char* m = getenv("AZG_CONV_MODE");        // experiment switch for the activation staging variant
     n->conv_mode = m ? atoi(m) : 1;                 // 1: single activation copy per slice (fastest, validated)
     if (n->conv_mode != 0 && n->conv_mode != 1 && n->conv_mode != 3) n->conv_mode = 1;
@@ -215,7 +217,7 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
   for (int l = 0; l < n_layers; ++l) {
     ConvArgs a;
     a.n_boards = n_ptr; a.max_boards = max_boards; a.layer = l; a.relu = 1;
-    a.shift_host = n->shift_host.data() + (size_t)l * C; a.error = n->error_dev; a.prof = n->profiling ? n->prof_dev : nullptr;
+    a.shift_host = n->shift_host.data() + (size_t)l * C; a.error = n->error_dev; a.prof = n->profiling ? n->prof_dev : nullptr; a.prof_detail = n->prof_detail;
     a.head_host = nullptr; a.hidden = nullptr;
     const bool fuse = heads && C <= 128 && l == n_layers - 1 && (l & 1) == 1;     // last conv2: fuse the 1x1 head convs, skip the store
     if (fuse) { a.head_host = n->head_host.data(); a.hidden = n->hidden; fused_heads = true; }
@@ -338,12 +340,14 @@ extern "C" int azg_net_profile_read(azg_net* n, double* trunk_ms, int64_t* launc
 
 // Pipeline wait counters of the conv3x3 kernel accumulated while profiling is enabled (cycles,
 // summed over clusters): {mma wait-full, mma wait-tmem-empty, mma total, producer wait-empty,
-// producer total, epilogue wait-tmem-full, epilogue total, boards}; reading resets them.
+// producer total, epilogue wait-tmem-full, epilogue total, boards, then five epilogue phases of one
+// warp: wait-for-store-drain, residual transpose, tcgen05.ld wait, compute + stage, fence + TMA store,
+// and three reserved}; out must hold 16 values; reading resets them.
 extern "C" int azg_net_profile_counters(azg_net* n, uint64_t* out8) {
   if (!n || !out8) return azg_fail(AZG_E_ARG, "null argument");
   AZG_CUDA(cudaSetDevice(n->device));
   AZG_CUDA(cudaDeviceSynchronize());
-  AZG_CUDA(cudaMemcpy(out8, n->prof_dev, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  AZG_CUDA(cudaMemcpy(out8, n->prof_dev, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   AZG_CUDA(cudaMemset(n->prof_dev, 0, 128));
   return AZG_OK;
 }

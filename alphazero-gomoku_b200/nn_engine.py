@@ -96,10 +96,11 @@ class NetEngine:
         return ms.value, n.value
 
     def profile_counters(self) -> dict:
-        out = (C.c_uint64 * 8)()
+        out = (C.c_uint64 * 16)()
         check(lib.azg_net_profile_counters(self._h, out))
         keys = ("mma_wait_full", "mma_wait_tmem_empty", "mma_total", "producer_wait_empty", "producer_total",
-                "epilogue_wait_tmem_full", "epilogue_total", "boards")
+                "epilogue_wait_tmem_full", "epilogue_total", "boards", "epi_wait_store_drain", "epi_residual_transpose",
+                "epi_tmem_ld_wait", "epi_compute_stage", "epi_fence_store")
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     def check(self):

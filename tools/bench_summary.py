@@ -14,4 +14,5 @@ for line in sys.stdin:
           "clk", d.get("clocks", {}).get("sm_mhz"), "conv TF", round(r.get("achieved", 0), 1), "frac", round(r.get("frac", 0) or 0, 3),
           "ms/launch", round(r.get("avg_launch_ms", 0), 3), "trunk share", round(r.get("trunk_share_of_step", 0) or 0, 3),
           "wait_full", pipe.get("mma_wait_full"), "wait_tempty", pipe.get("mma_wait_tmem_empty"),
-          "dropped", d.get("search", {}).get("dropped_trees"), "err", d.get("search", {}).get("games_in_error"))
+          "dropped", d.get("search", {}).get("dropped_trees"), "err", d.get("search", {}).get("games_in_error"),
+          "epi", {k[4:]: v for k, v in pipe.items() if k.startswith("epi_")})

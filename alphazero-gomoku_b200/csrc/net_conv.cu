@@ -20,6 +20,7 @@
 //   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator,
 //     warps 2-9 epilogue (TMEM -> registers -> shift (+residual) -> ReLU -> bf16 -> HBM).
 #include <cuda_bf16.h>
+#include <type_traits>
 #include "net.h"
 #include "ptx.cuh"
 
@@ -338,21 +339,30 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
           ptx::tmem_ld_wait();
           if (detail) { t_ld += clock64() - tq; tq = clock64(); }
           uint32_t outv[16];
+          // shift (constant bank, compile-time index) -> + residual -> ReLU -> bf16 pair; instantiated
+          // per (channel half, residual) so that the inner loop carries no selects
+          auto math = [&](auto SHOFF, auto RES) {
 #pragma unroll
-          for (int h = 0; h < 16; ++h) {
-            float y0 = __uint_as_float(v[2 * h]) + ((!HEADS && half) ? shift.v[(C / 2 + cc + 2 * h) % C] : shift.v[cc + 2 * h]);
-            float y1 = __uint_as_float(v[2 * h + 1]) + ((!HEADS && half) ? shift.v[(C / 2 + cc + 2 * h + 1) % C] : shift.v[cc + 2 * h + 1]);
-            if (has_res) {
-              const uint32_t rw = STAGED ? res[h] : res[(cc / 2 + h) % (STAGED ? 16 : NCH / 2)];
-              y0 += __uint_as_float(rw << 16);
-              y1 += __uint_as_float(rw & 0xffff0000u);
+            for (int h = 0; h < 16; ++h) {
+              float y0 = __uint_as_float(v[2 * h]) + shift.v[decltype(SHOFF)::value + cc + 2 * h];
+              float y1 = __uint_as_float(v[2 * h + 1]) + shift.v[decltype(SHOFF)::value + cc + 2 * h + 1];
+              if constexpr (decltype(RES)::value) {
+                const uint32_t rw = STAGED ? res[h] : res[(cc / 2 + h) % (STAGED ? 16 : NCH / 2)];
+                y0 += __uint_as_float(rw << 16);
+                y1 += __uint_as_float(rw & 0xffff0000u);
+              }
+              const __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(y0, 0.f), fmaxf(y1, 0.f));
+              outv[h] = pad ? 0u : *reinterpret_cast<const uint32_t*>(&pk);
             }
-            if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-            if (pad) { y0 = 0.f; y1 = 0.f; }
-            const __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
-            outv[h] = *reinterpret_cast<const uint32_t*>(&pk);
-            if constexpr (HEADS) {
-              // the heads see the bf16-rounded activations, exactly like the unfused path
+          };
+          using I0 = std::integral_constant<int, 0>;
+          using IH = std::integral_constant<int, HEADS ? 0 : C / 2>;
+          if (!HEADS && half) { if (has_res) math(IH{}, std::true_type{}); else math(IH{}, std::false_type{}); }
+          else { if (has_res) math(I0{}, std::true_type{}); else math(I0{}, std::false_type{}); }
+          if constexpr (HEADS) {
+            // the heads see the bf16-rounded activations, exactly like the unfused path
+#pragma unroll
+            for (int h = 0; h < 16; ++h) {
               const float z0 = __uint_as_float(outv[h] << 16), z1 = __uint_as_float(outv[h] & 0xffff0000u);
               d0 = fmaf(z0, head.w[0][cc + 2 * h], d0); d0 = fmaf(z1, head.w[0][cc + 2 * h + 1], d0);
               d1 = fmaf(z0, head.w[1][cc + 2 * h], d1); d1 = fmaf(z1, head.w[1][cc + 2 * h + 1], d1);

@@ -33,6 +33,7 @@ namespace {
 //      (Setting base_offset = (start >> 7) & 7 instead was tried and gives WRONG results on B200: the
 //      swizzle is a function of absolute shared-memory address bits.)
 //   3: as 1 but with the direct (row-per-thread) epilogue instead of the staged one.
+//   4: as 1 but the staged tile leaves by coalesced 16-byte global stores of the warp instead of a TMA store.
 template <int MODE>
 struct Stage {
   static constexpr int ROWS = MODE == 0 ? 160 : 162;
@@ -52,7 +53,7 @@ struct Cfg {
   static constexpr int BBYTES = NBLK * BBLK;
   static constexpr int TMEM_COLS = 2 * C;                 // two accumulators
   static constexpr int STAGES = MODE == 0 ? (C == 128 ? 4 : 6) : 3;   // activation tiles in flight
-  static constexpr int EPI = (MODE == 0 || MODE == 3) ? 0 : 8 * 2048;                // per-warp epilogue staging tiles (32 rows x 64 B)
+  static constexpr int EPI = (MODE == 1 || MODE == 4) ? 8 * 2048 : 0;                // per-warp epilogue staging tiles (32 rows x 64 B)
   static constexpr int SMEM = 1024 + BBYTES + STAGES * Stage<MODE>::PITCH + EPI + 256;
 };
 
@@ -272,7 +273,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     // both bank-conflict free and the layout of a SWIZZLE_64B TMA box): residual rows are read with
     // coalesced 16-byte loads (8 rows x 64 B per instruction) and transposed through the tile, results
     // leave by one TMA store per tile.  MODE 0 keeps the direct row-per-thread accesses.
-    constexpr bool STAGED = MODE == 1;
+    constexpr bool STAGED = MODE == 1 || MODE == 4;
+    constexpr bool TMA_OUT = MODE == 1;
     constexpr int NCHUNK = NCH / 32;
     const uint32_t tile = ptx::smem_u32(sEpi) + (uint32_t)(warp - 2) * 2048u;
     const uint32_t own = tile + (uint32_t)lane * 64u;                      // this thread's row in the tile
@@ -314,7 +316,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * C + ch), v);
           if constexpr (STAGED) {
             long long tp = detail ? clock64() : 0;
-            if (p.out) {                       // the previous TMA store must have finished reading the tile
+            if (TMA_OUT && p.out) {            // the previous TMA store must have finished reading the tile
               if (lane == 0) ptx::bulk_wait_read0();
               __syncwarp();
             }
@@ -376,11 +378,22 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
                 ptx::sts128(own + (uint32_t)(((uint32_t)u ^ own_sw) * 16u),
                             make_uint4(outv[4 * u], outv[4 * u + 1], outv[4 * u + 2], outv[4 * u + 3]));
               if (detail) { t_cs += clock64() - tq; tq = clock64(); }
-              ptx::fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                ptx::tma_store_2d(&tm_out, sEpi + (warp - 2) * 2048, ch, (int)grow0);
-                ptx::bulk_commit();
+              if constexpr (TMA_OUT) {
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  ptx::tma_store_2d(&tm_out, sEpi + (warp - 2) * 2048, ch, (int)grow0);
+                  ptx::bulk_commit();
+                }
+              } else {
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {      // 8 rows x 64 B per instruction
+                  const int r = 8 * i + crow;
+                  const uint4 q = ptx::lds128(tile + (uint32_t)r * 64u + (uint32_t)((cunit ^ ((r >> 1) & 3)) * 16));
+                  ptx::stg128(p.out + (grow0 + (size_t)r) * C + ch + 8 * cunit, q);
+                }
+                __syncwarp();
               }
               if (detail) t_st += clock64() - tq;
             } else {
@@ -403,7 +416,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
     }
-    if (STAGED && lane == 0) ptx::bulk_wait0();            // all stores of this warp have landed before the CTA exits
+    if (TMA_OUT && lane == 0) ptx::bulk_wait0();            // all stores of this warp have landed before the CTA exits
     if (p.prof && rank == 0 && warp == 2 && lane == 0) {   // one representative epilogue warp
       atomicAdd(p.prof + 5, (unsigned long long)t_tfull);
       atomicAdd(p.prof + 6, (unsigned long long)(clock64() - t_begin));
@@ -464,17 +477,20 @@ int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtenso
     if (mode == 0) return launch_conv_heads<128, 0>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 1) return launch_conv_heads<128, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 3) return launch_conv_heads<128, 3>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (mode == 4) return launch_conv_heads<128, 4>(tm_act, tm_w, tm_out, args, n_sm, stream);
     return azg_fail(AZG_E_ARG, "conv3x3: unknown staging mode");
   }
   if (C == 64) {
     if (mode == 0) return launch_conv_heads<64, 0>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 1) return launch_conv_heads<64, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 3) return launch_conv_heads<64, 3>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (mode == 4) return launch_conv_heads<64, 4>(tm_act, tm_w, tm_out, args, n_sm, stream);
     return azg_fail(AZG_E_ARG, "conv3x3: unknown staging mode");
   }
   if (C == 256) {
     if (args.head_host) return azg_fail(AZG_E_ARG, "conv3x3: the fused-heads epilogue is built for 64 and 128 channels");
     if (mode == 3) return launch_conv<256, false, 3>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (mode == 4) return launch_conv<256, false, 4>(tm_act, tm_w, tm_out, args, n_sm, stream);
     return launch_conv<256, false, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
   }
   return azg_fail(AZG_E_ARG, "conv3x3: channels must be 64, 128 or 256");

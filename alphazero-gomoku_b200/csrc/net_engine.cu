@@ -136,8 +136,8 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
     n->prof_detail = pd ? atoi(pd) : 0;
     const char* m = getenv("AZG_CONV_MODE");        // experiment switch for the activation staging variant
     n->conv_mode = m ? atoi(m) : 1;                 // 1: single activation copy per slice (fastest, validated)
-    if (n->conv_mode != 0 && n->conv_mode != 1 && n->conv_mode != 3) n->conv_mode = 1;
-    if (channels == 256 && n->conv_mode != 3) n->conv_mode = 1;      // the streaming-weights kernel needs the single-copy layout
+    if (n->conv_mode != 0 && n->conv_mode != 1 && n->conv_mode != 3 && n->conv_mode != 4) n->conv_mode = 1;
+    if (channels == 256 && n->conv_mode == 0) n->conv_mode = 1;      // the streaming-weights kernel needs the single-copy layout
   }
   for (int i = 0; i < 3; ++i)
     if ((rc = make_map(&n->tm_act[i], n->act[i], n->rows, C, (uint32_t)azg_conv3x3_rows(n->conv_mode)))) { azg_net_destroy(n); return rc; }

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "azg_rules_legal": (_I, [_P, _P, _I, _P]),
     "azg_rules_encode": (_I, [_P, _P, _I, _P]),
     "azg_rules_play_host": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _I]),
+    "azg_rules_query_host": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I]),
     "azg_create": (_I, [C.POINTER(azg_config), C.POINTER(_P)]),
     "azg_destroy": (_I, [_P]),
     "azg_set_stream": (_I, [_P, _P]),

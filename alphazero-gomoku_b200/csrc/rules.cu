@@ -147,7 +147,7 @@ extern "C" int azg_rules_play_host(int rule, int device, int8_t* boards, int32_t
   AZG_CUDA(cudaSetDevice(device));
   const size_t nb = (size_t)n * AZG_A, ni = (size_t)n * sizeof(int32_t);
   char* buf = nullptr;
-  const size_t total = nb + 256 + 6 * ni + 2 * ni + (size_t)n * sizeof(azg_pos) + 1024;
+  const size_t total = nb + 8 * ni + (size_t)n * sizeof(azg_pos) + 4096;      // every sub-buffer is padded to 256 B
   AZG_CUDA(cudaMalloc(&buf, total));
   size_t o = 0;
   auto take = [&](size_t bytes) { char* p = buf + o; o += (bytes + 255) & ~(size_t)255; return p; };
@@ -173,6 +173,51 @@ extern "C" int azg_rules_play_host(int rule, int device, int8_t* boards, int32_t
   AZG_TRY(cudaMemcpy(caps, d_ca, 2 * ni, cudaMemcpyDeviceToHost));
   AZG_TRY(cudaMemcpy(plies, d_pi, ni, cudaMemcpyDeviceToHost));
   AZG_TRY(cudaMemcpy(status, d_st, ni, cudaMemcpyDeviceToHost));
+#undef AZG_TRY
+done:
+  cudaFree(buf);
+  return rc;
+}
+
+// Host-buffer query used by the Python game shims: status bits, legal mask and encoded planes of n
+// positions given as boards + scalars (nothing is modified).  legal_host / planes_host may be NULL.
+extern "C" int azg_rules_query_host(int rule, int device, const int8_t* boards, const int32_t* players, const int32_t* lasts,
+                                    const int32_t* caps, const int32_t* plies, int32_t* status, float* legal_host,
+                                    float* planes_host, int n) {
+  if (!boards || !players || !lasts || !caps || !plies || !status || n <= 0)
+    return azg_fail(AZG_E_ARG, "azg_rules_query_host: null argument");
+  AZG_CUDA(cudaSetDevice(device));
+  const size_t nb = (size_t)n * AZG_A, ni = (size_t)n * sizeof(int32_t);
+  char* buf = nullptr;
+  const size_t total = nb + 6 * ni + (size_t)n * sizeof(azg_pos) + (size_t)n * AZG_A * 4 * 4 + 4096;
+  AZG_CUDA(cudaMalloc(&buf, total));
+  size_t o = 0;
+  auto take = [&](size_t bytes) { char* p = buf + o; o += (bytes + 255) & ~(size_t)255; return p; };
+  int8_t* d_b = (int8_t*)take(nb);
+  int32_t* d_pl = (int32_t*)take(ni); int32_t* d_la = (int32_t*)take(ni); int32_t* d_ca = (int32_t*)take(2 * ni);
+  int32_t* d_pi = (int32_t*)take(ni); int32_t* d_st = (int32_t*)take(ni);
+  azg_pos* d_pos = (azg_pos*)take((size_t)n * sizeof(azg_pos));
+  float* d_legal = (float*)take((size_t)n * AZG_A * 4);
+  float* d_planes = (float*)take((size_t)n * AZG_A * 12);
+  int rc = AZG_OK;
+  cudaError_t ce;
+#define AZG_TRY(x) do { ce = (x); if (ce != cudaSuccess) { rc = azg_fail(AZG_E_CUDA, cudaGetErrorString(ce)); goto done; } } while (0)
+  AZG_TRY(cudaMemcpy(d_b, boards, nb, cudaMemcpyHostToDevice));
+  AZG_TRY(cudaMemcpy(d_pl, players, ni, cudaMemcpyHostToDevice));
+  AZG_TRY(cudaMemcpy(d_la, lasts, ni, cudaMemcpyHostToDevice));
+  AZG_TRY(cudaMemcpy(d_ca, caps, 2 * ni, cudaMemcpyHostToDevice));
+  AZG_TRY(cudaMemcpy(d_pi, plies, ni, cudaMemcpyHostToDevice));
+  if ((rc = azg_rules_pack(d_b, d_pl, d_la, d_ca, d_pi, d_pos, n, nullptr))) goto done;
+  if ((rc = azg_rules_status(rule, d_pos, d_st, n, nullptr))) goto done;
+  AZG_TRY(cudaMemcpy(status, d_st, ni, cudaMemcpyDeviceToHost));
+  if (legal_host) {
+    if ((rc = azg_rules_legal(d_pos, d_legal, n, nullptr))) goto done;
+    AZG_TRY(cudaMemcpy(legal_host, d_legal, (size_t)n * AZG_A * 4, cudaMemcpyDeviceToHost));
+  }
+  if (planes_host) {
+    if ((rc = azg_rules_encode(d_pos, d_planes, n, nullptr))) goto done;
+    AZG_TRY(cudaMemcpy(planes_host, d_planes, (size_t)n * AZG_A * 12, cudaMemcpyDeviceToHost));
+  }
 #undef AZG_TRY
 done:
   cudaFree(buf);

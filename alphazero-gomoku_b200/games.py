@@ -73,8 +73,24 @@ class _Game:
     def _on_captured(self, before, after, move):
         pass
 
+    def _query(self, want_legal=False, want_planes=False):
+        """Status bits (and optionally the legal mask / encoded planes) of the current position from the
+        CUDA rule kernels (azg_rules_query_host)."""
+        boards = np.ascontiguousarray(self.board.reshape(1, -1).astype(np.int8))
+        players = np.array([self.current_player], np.int32)
+        lasts = np.array([-1 if self.last_move is None else self.last_move[0] * 15 + self.last_move[1]], np.int32)
+        caps = np.array([self._caps()], np.int32)
+        plies = np.array([len(self.move_history)], np.int32)
+        status = np.zeros(1, np.int32)
+        legal = np.zeros((1, 225), np.float32) if want_legal else None
+        planes = np.zeros((1, 3, 15, 15), np.float32) if want_planes else None
+        check(lib.azg_rules_query_host(self.RULE, 0, ptr(boards), ptr(players), ptr(lasts), ptr(caps), ptr(plies), ptr(status),
+                                       ptr(legal), ptr(planes), 1))
+        self._status = int(status[0])
+        return legal, planes
+
     def _refresh(self):
-        _, _, _, _, self._status = self._device_step(-1)     # rejected move: status of the current position
+        self._query()
 
     def check_winner(self) -> int:
         self._refresh()
@@ -95,18 +111,13 @@ class _Game:
         return bool(np.any(self.board == 0))
 
     def get_valid_moves(self) -> np.ndarray:
-        return (self.board.reshape(-1) == 0).astype(np.float32)
+        return self._query(want_legal=True)[0][0]
 
     def get_state(self) -> np.ndarray:
         return self.board.copy()
 
     def get_encoded_state(self) -> np.ndarray:
-        me = self.current_player
-        out = np.empty((3, self.size, self.size), dtype=np.float32)
-        out[0] = self.board == me
-        out[1] = self.board == 3 - me
-        out[2] = 1.0
-        return out
+        return self._query(want_planes=True)[1][0]
 
 
 class Gomoku(_Game):

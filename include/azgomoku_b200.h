@@ -73,6 +73,12 @@ int azg_rules_play_host(int rule, int device, int8_t* boards_host, int32_t* play
                         int32_t* caps_host, int32_t* plies_host, const int32_t* actions_host,
                         int32_t* status_host, int n);
 
+/* Host-buffer query (nothing is modified): status bits, and optionally get_valid_moves
+ * (legal_host float32[n][225]) and get_encoded_state (planes_host float32[n][3][15][15]). */
+int azg_rules_query_host(int rule, int device, const int8_t* boards_host, const int32_t* players_host,
+                         const int32_t* lasts_host, const int32_t* caps_host, const int32_t* plies_host,
+                         int32_t* status_host, float* legal_host, float* planes_host, int n);
+
 /* ------------------------------------------------------------------ search engine
  * One engine = G concurrent games of one rule on one device, each with its own
  * HBM-resident tree slab.  Replaces MCTS.__init__/run/search/_predict_batch/clear_tree

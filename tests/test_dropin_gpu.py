@@ -29,6 +29,9 @@ def test_game_objects_follow_golden_traces():
         c = g.clone()
         assert np.array_equal(c.board, g.board) and c.current_player == g.current_player
         assert np.array_equal(g.get_valid_moves(), (g.board.reshape(-1) == 0).astype(np.float32))
+        enc = g.get_encoded_state()
+        assert enc.shape == (3, 15, 15) and np.array_equal(enc[0], (g.board == g.current_player).astype(np.float32))
+        assert np.array_equal(enc[1], (g.board == 3 - g.current_player).astype(np.float32)) and (enc[2] == 1).all()
     # capture history of the Pente KAT
     p = Pente(15)
     for mv in [(7, 7), (7, 8), (0, 0), (7, 9), (7, 10)]:

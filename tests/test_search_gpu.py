@@ -140,3 +140,54 @@ def test_many_games_vs_oracle(rule):
     s = eng.stats()
     assert s["games_in_error"] == 0 and s["sims"] >= G * n_sims
     eng.close()
+
+
+def test_error_behaviour_is_loud_not_fatal():
+    """Slab exhaustion and terminal roots surface as AzgError (never a hang, a crash or a silent
+    fallback); the reference would raise MemoryError / KeyError in the same situations."""
+    import alphazero_gomoku_b200 as m
+    model = fakes.Hashed()
+    ev = lambda planes: torch.from_numpy(model.predict(planes.cpu().numpy())[0]).cuda()
+    # 1. node slab too small for the run
+    eng = m.SearchEngine(0, 2, node_capacity=64)
+    with pytest.raises(m.AzgError):
+        eng.run(400, ev)
+    assert eng.stats()["games_in_error"] == 2 and eng.stats()["error_bits"] & 1
+    eng.close()
+    # 2. a root that is already won (new_mcts_alpha.py:89 would raise KeyError)
+    p = orules.Position(0)
+    for a in (0, 30, 1, 31, 2, 32, 3, 33, 4):
+        orules.play(p, a)
+    assert orules.game_over(p)
+    eng = m.SearchEngine(0, 1, node_capacity=256)
+    eng.set_roots(eng.rules.pack(p.cells[None, :], [p.player], [p.last], [p.caps], [p.plies]))
+    with pytest.raises(m.AzgError):
+        eng.run(50, ev)
+    assert eng.stats()["error_bits"] & 4
+    eng.close()
+
+
+def test_tree_is_dropped_instead_of_overflowing():
+    """With `reserve`, a game whose slab cannot hold another run restarts from an empty tree (counted)
+    and the search keeps running; visit counts of that move equal a fresh-tree search."""
+    import alphazero_gomoku_b200 as m
+    n_sims = 200
+    eng = m.SearchEngine(0, 1, node_capacity=300, queue_len=32)
+    model = fakes.Hashed()
+    ev = lambda planes: torch.from_numpy(model.predict(planes.cpu().numpy())[0]).cuda()
+    pos = orules.Position(0)
+    reserve = n_sims + n_sims // 32 + 8
+    dropped_before = 0
+    for move in range(4):
+        pi, visits = eng.run(n_sims, ev)
+        fresh = Search(0, n_sims, fakes.Hashed(), queue_len=32, noise=False)
+        want = fresh.run(pos, pos.plies)
+        st = eng.stats()
+        if move > 0 and st["dropped_trees"] > dropped_before:           # this run started from an empty tree
+            assert np.array_equal(pi[0].cpu().numpy(), want)
+        dropped_before = st["dropped_trees"]
+        a = int(np.argmax(want))
+        orules.play(pos, a)
+        eng.advance(torch.tensor([a], dtype=torch.int32).cuda(), gc=True, reserve=reserve)
+    assert eng.stats()["dropped_trees"] >= 1 and eng.stats()["games_in_error"] == 0
+    eng.close()

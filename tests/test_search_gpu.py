@@ -172,7 +172,7 @@ def test_tree_is_dropped_instead_of_overflowing():
     and the search keeps running; visit counts of that move equal a fresh-tree search."""
     import alphazero_gomoku_b200 as m
     n_sims = 200
-    eng = m.SearchEngine(0, 1, node_capacity=300, queue_len=32)
+    eng = m.SearchEngine(0, 1, node_capacity=232, queue_len=32)
     model = fakes.Hashed()
     ev = lambda planes: torch.from_numpy(model.predict(planes.cpu().numpy())[0]).cuda()
     pos = orules.Position(0)

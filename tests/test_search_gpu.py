@@ -173,14 +173,14 @@ def test_tree_is_dropped_instead_of_overflowing():
     import alphazero_gomoku_b200 as m
     n_sims = 200
     eng = m.SearchEngine(0, 1, node_capacity=232, queue_len=32)
-    model = fakes.Hashed()
+    model = fakes.Spiky()           # narrow, deep trees: most nodes stay reachable after a move
     ev = lambda planes: torch.from_numpy(model.predict(planes.cpu().numpy())[0]).cuda()
     pos = orules.Position(0)
     reserve = n_sims + n_sims // 32 + 8
     dropped_before = 0
     for move in range(4):
         pi, visits = eng.run(n_sims, ev)
-        fresh = Search(0, n_sims, fakes.Hashed(), queue_len=32, noise=False)
+        fresh = Search(0, n_sims, fakes.Spiky(), queue_len=32, noise=False)
         want = fresh.run(pos, pos.plies)
         st = eng.stats()
         if move > 0 and st["dropped_trees"] > dropped_before:           # this run started from an empty tree

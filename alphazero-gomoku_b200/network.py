@@ -79,6 +79,15 @@ class AlphaZeroNet(nn.Module):
         return logits, torch.tanh(self.value_fc2(v))
 
 
+def infer_architecture(state_dict) -> Tuple[int, int]:
+    """(n_res_blocks, channels) of a reference-layout state_dict."""
+    channels = int(state_dict["conv.weight"].shape[0])
+    blocks = 0
+    while f"res_blocks.{blocks}.conv1.weight" in state_dict:
+        blocks += 1
+    return blocks, channels
+
+
 class PyTorchModel:
     def __init__(self, board_size: int = 15, action_size: Optional[int] = None, device: Optional[str] = None,
                  n_res_blocks: int = 3, channels: int = 64, lr: float = 1e-3, weight_decay: float = 1e-4):
@@ -155,6 +164,17 @@ class PyTorchModel:
                 self.optimizer.load_state_dict(state["opt"])
             except Exception:
                 pass
+
+    @classmethod
+    def from_checkpoint(cls, path: str, device: Optional[str] = None, **kw) -> "PyTorchModel":
+        """Build a model whose depth and width are read off the checkpoint's state_dict (the reference's
+        checkpoints do not store n_res_blocks / channels, network.py:240-248) and load it."""
+        state = torch.load(path, map_location="cpu")
+        blocks, channels = infer_architecture(state["net"])
+        model = cls(board_size=int(state.get("board_size", 15)), action_size=state.get("action_size"), device=device,
+                    n_res_blocks=blocks, channels=channels, **kw)
+        model.load(path)
+        return model
 
     @staticmethod
     def make_batch_from_states(list_of_encoded_states: list) -> np.ndarray:

@@ -1,0 +1,91 @@
+"""CPU: host-side logic that needs no GPU - argument mapping of the drop-in classes, replay buffers,
+sampling helpers, checkpoint architecture inference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+
+def test_rule_mapping_and_game_fields():
+    from alphazero_gomoku_b200.engine import rule_of, GOMOKU, PENTE
+    from alphazero_gomoku_b200.mcts import game_fields
+
+    class Gomoku:
+        pass
+
+    class Pente:
+        pass
+
+    assert rule_of(Gomoku) == GOMOKU and rule_of(Pente) == PENTE and rule_of("pente") == PENTE and rule_of(Gomoku()) == GOMOKU
+    with pytest.raises(ValueError):
+        rule_of("chess")
+
+    class G:
+        board = np.zeros((15, 15), dtype=int)          # int64 board as players/player_alpha.py:60 builds it
+        current_player = 2
+        last_move = (7, 8)
+        move_history = [(7, 8)]
+        captures = {1: 2, 2: 1}
+    G.board[7, 8] = 1
+    board, player, last, caps, plies = game_fields(G())
+    assert board.dtype == np.int8 and board[7 * 15 + 8] == 1 and player == 2 and last == 113 and caps == (2, 1) and plies == 1
+    G.last_move = None
+    assert game_fields(G())[2] == -1
+
+
+def test_sampling_helpers_match_reference_fixture():
+    from alphazero_gomoku_b200 import train as tr
+    z = load_golden("symmetry_sampling.npz")
+    for t, want in zip(z["temps"], z["tempered"]):
+        assert np.array_equal(np.asarray(tr.softmax_temperature(z["pi"], float(t)), dtype=np.float64), want)
+    assert tr.sample_action_from_pi(z["pi"], 0) == int(np.argmax(z["pi"]))
+    np.random.seed(0)
+    a = [tr.sample_action_from_pi(z["pi"], 1.0) for _ in range(50)]
+    assert all(0 <= x < 225 for x in a) and len(set(a)) > 5
+
+
+def test_replay_buffers(tmp_path):
+    from alphazero_gomoku_b200 import train as tr
+    rows = torch.arange(12 * 901, dtype=torch.float32).reshape(12, 901)
+    host = tr.ReplayBuffer(capacity=10)
+    host.add_rows(rows)
+    assert len(host) == 10 and host.buffer[0][0].shape == (3, 15, 15) and host.buffer[0][1].shape == (225,)
+    s, p, zz = host.sample(4)
+    assert s.shape == (4, 3, 15, 15) and p.shape == (4, 225) and zz.shape == (4, 1)
+    path = str(tmp_path / "buf.pkl")
+    assert tr.save_replay_buffer(host, path)
+    back = tr.load_replay_buffer(path, 10)
+    assert len(back) == 10 and np.array_equal(back.buffer[3][1], host.buffer[3][1])
+    import pickle
+    raw = pickle.load(open(path, "rb"))
+    assert set(raw) == {"buffer", "capacity"} and raw["capacity"] == 10          # the reference's dictionary (train.py:309-312)
+    dev = tr.DeviceReplayBuffer(10, "cpu")
+    dev.add_rows(rows[:7])
+    dev.add_rows(rows[7:])
+    assert len(dev) == 10
+    h2 = dev.to_host()
+    assert [float(x[2]) for x in h2.buffer] == [float(x[2]) for x in host.buffer]      # oldest-first, same eviction as the deque
+    d2 = tr.DeviceReplayBuffer.from_host(host, "cpu")
+    assert len(d2) == 10 and torch.equal(d2.rows[:10, 900], torch.tensor([float(x[2]) for x in host.buffer]))
+    s, p, zz = dev.sample(5)
+    assert s.shape == (5, 3, 15, 15) and zz.shape == (5, 1)
+    assert tr.load_replay_buffer(str(tmp_path / "missing.pkl"), 10) is None
+
+
+def test_architecture_inference():
+    import alphazero_gomoku_b200.network as mynet
+    for blocks, ch in ((3, 64), (6, 128), (2, 256)):
+        net = mynet.AlphaZeroNet(n_res_blocks=blocks, channels=ch)
+        assert mynet.infer_architecture(net.state_dict()) == (blocks, ch)
+    assert sum(p.numel() for p in mynet.AlphaZeroNet(n_res_blocks=3, channels=64).parameters()) == 340010
+    assert sum(p.numel() for p in mynet.AlphaZeroNet().parameters()) == 1892650       # SURVEY: 6x128
+
+
+def test_mcts_symmetries_reference_order():
+    """The host helper of the drop-in MCTS needs no engine: call it unbound."""
+    from alphazero_gomoku_b200.mcts import MCTS
+    z = load_golden("symmetry_sampling.npz")
+    out = MCTS.symmetries(None, z["planes"], z["pi"])
+    for i, (s, g) in enumerate(out):
+        assert np.array_equal(s, z["sym_planes"][i]) and np.array_equal(g, z["sym_pi"][i])

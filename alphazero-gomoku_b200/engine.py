@@ -124,6 +124,10 @@ class SearchEngine:
 
     # -- helpers
     def _sync_stream(self):
+        """Every engine call runs on the engine's own device and on torch's current stream there."""
+        idx = self.device.index or 0
+        if torch.cuda.current_device() != idx:
+            torch.cuda.set_device(idx)
         check(lib.azg_set_stream(self._h, _stream()))
 
     @property

@@ -62,7 +62,6 @@ struct azg_dev {
   int32_t* W;                   // [G][cap][AZG_ROW]
   uint32_t* key;                // [G][cap][16]
   uint32_t* meta;               // [G][cap]  bit0 alive, bit1-2 player, bits 4-7 p64 slot+1
-  uint32_t* hint;               // [G][cap]  (action+1)<<24 | child node: where the last selected child was found
   unsigned long long* slots;    // [G][hcap] (tag<<32)|(node+1), 0 empty
   int32_t* freelist;            // [G][cap]
   uint32_t* path;               // [G][AZG_MAX_DEPTH] (node<<8)|action

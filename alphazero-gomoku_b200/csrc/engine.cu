@@ -74,7 +74,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
   int64_t& tot = e->bytes;
   if ((rc = dev_alloc(&d.ctl, G, &tot)) || (rc = dev_alloc(&d.P, G * C * AZG_ROW, &tot)) ||
       (rc = dev_alloc(&d.Nv, G * C * AZG_ROW, &tot)) || (rc = dev_alloc(&d.W, G * C * AZG_ROW, &tot)) ||
-      (rc = dev_alloc(&d.key, G * C * 16, &tot)) || (rc = dev_alloc(&d.meta, G * C, &tot)) || (rc = dev_alloc(&d.hint, G * C, &tot)) ||
+      (rc = dev_alloc(&d.key, G * C * 16, &tot)) || (rc = dev_alloc(&d.meta, G * C, &tot)) ||
       (rc = dev_alloc(&d.slots, G * (size_t)d.hcap, &tot)) || (rc = dev_alloc(&d.freelist, G * C, &tot)) ||
       (rc = dev_alloc(&d.path, G * AZG_MAX_DEPTH, &tot)) || (rc = dev_alloc(&d.P64, G * AZG_P64_SLOTS * AZG_ROW, &tot)) ||
       (rc = dev_alloc(&d.leaf_game, G * (size_t)d.queue_len, &tot)) ||
@@ -89,7 +89,6 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
   }
   cudaMemset(d.ctl, 0, G * sizeof(azg_ctl));
   cudaMemset(d.meta, 0, G * C * sizeof(uint32_t));
-  cudaMemset(d.hint, 0, G * C * sizeof(uint32_t));
   cudaMemset(d.slots, 0, G * (size_t)d.hcap * sizeof(unsigned long long));
   cudaMemset(d.counters, 0, 8 * sizeof(int32_t));
   // empty boards, player 1 to move
@@ -113,7 +112,7 @@ extern "C" int azg_destroy(azg_engine* e) {
   if (!e) return AZG_OK;
   cudaSetDevice(e->cfg.device);
   azg_dev& d = e->dev;
-  cudaFree(d.ctl); cudaFree(d.P); cudaFree(d.Nv); cudaFree(d.W); cudaFree(d.key); cudaFree(d.meta); cudaFree(d.hint); cudaFree(d.slots);
+  cudaFree(d.ctl); cudaFree(d.P); cudaFree(d.Nv); cudaFree(d.W); cudaFree(d.key); cudaFree(d.meta); cudaFree(d.slots);
   cudaFree(d.freelist); cudaFree(d.path); cudaFree(d.P64); cudaFree(d.leaf_game); cudaFree(d.leaf_node);
   cudaFree(d.counters); cudaFree(e->stats_dev);
   cudaFree(e->sp.ex_key); cudaFree(e->sp.ex_player); cudaFree(e->sp.ex_pi); cudaFree(e->sp.n_plies); cudaFree(e->sp.n_done);

@@ -65,7 +65,6 @@ __device__ __forceinline__ void node_write_key(const azg_dev& e, int g, int node
   const uint32_t x1 = __shfl_sync(AZG_FULL, p.w1, (l & 7) << 2);
   if (l < 16) e.key[off * 16 + l] = (l < 8 ? x0 : x1);
   if (l == 16) e.meta[off] = AZG_META_ALIVE | ((uint32_t)p.player << 1);
-  if (l == 17) e.hint[off] = 0u;
 }
 
 // children arrays of a node: lane L < 28 owns elements 8L..8L+7, lane 28 owns element 224.
@@ -95,7 +94,6 @@ struct NodeData {
   float p[8];
   int n[8], w[8];
   uint32_t meta;
-  uint32_t hint;     // (action+1)<<24 | child node of the last selection made at this node (0: none)
   uint32_t keyw;     // lanes 0..15: key word l of the node
 };
 
@@ -104,7 +102,6 @@ __device__ __forceinline__ void node_load(const azg_dev& e, int g, int node, Nod
   const size_t off = azg_node_off(e, g, node);
   const size_t base = off * AZG_ROW;
   nd.meta = __ldcg(&e.meta[off]);
-  nd.hint = __ldcg(&e.hint[off]);
   nd.keyw = l < 16 ? __ldcg(&e.key[off * 16 + l]) : 0u;
   if (l < 28) {
     const float4* P = reinterpret_cast<const float4*>(e.P + base + 8 * l);
@@ -262,7 +259,6 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
       depth = 0;
     }
     bool parked = false;
-    int parent = -1, guess = -1, took = -1;        // child-location hint of the selection just made
     for (;;) {
       if (!select_here) {
         ++visits;
@@ -272,16 +268,7 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
         const unsigned long long h = wpos_hash(pos);
         int ins = -1;
         if (depth == 0 && root_node >= 0) { node = root_node; node_load(e, g, node, nd); }   // the root key is fixed for the run
-        else {
-          // One round trip when the parent remembers where this child lives; the stored key is still
-          // compared in full, so a stale or wrong hint only costs the normal probe.
-          node = -1;
-          if (guess >= 0 && guess < n_nodes) {
-            node_load(e, g, guess, nd);
-            if ((nd.meta & AZG_META_ALIVE) && node_key_matches(nd, pos)) node = guess;
-          }
-          if (node < 0) node = table_find_load(e, g, pos, h, &ins, nd);
-        }
+        else node = table_find_load(e, g, pos, h, &ins, nd);
         if (node < 0) {                                        // new_mcts_alpha.py:114-132
           if (ins < 0) { err |= AZG_ERR_HASH; break; }
           if (n_free > 0) node = __ldcg(&freelist[--n_free]);
@@ -291,7 +278,6 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
           node_write_key(e, g, node, pos);
           table_put(e, g, ins, h, node);
           if (depth == 0) root_node = node;
-          if (parent >= 0 && l == 0) e.hint[azg_node_off(e, g, parent)] = ((uint32_t)(took + 1) << 24) | (uint32_t)node;
           if (l == 0) ctl->pending[n_pending] = node;
           ++n_pending;
           if (n_pending >= e.queue_len) {                     // park: the queue is evaluated first
@@ -305,13 +291,9 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
           v = 0;
           break;
         }
-        if (parent >= 0 && node != guess && l == 0)            // found by the probe: remember it for next time
-          e.hint[azg_node_off(e, g, parent)] = ((uint32_t)(took + 1) << 24) | (uint32_t)node;
       }
       select_here = false;
       const int a = puct_select(e, g, nd, wpos_legal_byte(pos));
-      parent = node; took = a;
-      guess = ((int)(nd.hint >> 24) == a + 1) ? (int)(nd.hint & 0xffffffu) : -1;
       if (depth >= AZG_MAX_DEPTH) { err |= AZG_ERR_DEPTH; break; }
       if (l == 0) __stcg(&path[depth], ((uint32_t)node << 8) | (uint32_t)a);
       ++depth;

@@ -101,6 +101,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const int cid = (int)ptx::cluster_id_x(), ncl = (int)ptx::ncluster_x();
+  // Programmatic dependent launch: the next layer may start its prologue (barriers, TMEM, its own weight
+  // loads) on idle SMs while this one computes; everything that touches activations waits below.
+  ptx::grid_dep_launch();
   int n_boards = *p.n_boards;
   if (n_boards > p.max_boards) n_boards = p.max_boards;
 
@@ -136,6 +139,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
           ptx::tma_load_2d_pair(sB + blk * K::BBLK, &tm_w, bfull, kc * 64, (p.layer * 9 + tap) * C + (int)rank * (C / 2));
         }
       }
+      ptx::grid_dep_wait();                    // activations of the previous layer are complete from here on
       int stage = 0, ws = 0;
       uint32_t phase = 0, wphase = 0;
       bool ok = true;
@@ -255,6 +259,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     // Two warps per TMEM lane quadrant; each takes half of the channels of its 32 rows.  In the
     // fused-heads variant (last layer) one warp per quadrant takes all channels of its rows so
     // that the three head dot products stay inside a thread; the other warp only signals.
+    ptx::grid_dep_wait();                      // residual reads and output writes follow the previous layer
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int NCH = HEADS ? C : C / 2;           // channels handled by a working warp
@@ -456,7 +461,18 @@ int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtens
     head.w[0][0] = head.w[1][0] = head.w[2][0] = 0.f;
     for (int r = 0; r < 3; ++r) head.scale[r] = head.shift[r] = 0.f;
   }
-  conv3x3_pair_kernel<C, HEADS, MODE><<<grid, kThreads, K::SMEM, stream>>>(tm_act, tm_w, tm_out, args, shift, head);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = K::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see grid_dep_launch / grid_dep_wait in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<C, HEADS, MODE>, tm_act, tm_w, tm_out, args, shift, head);
+  if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
   return azg_check_launch("conv3x3_pair_kernel");
 }
 

@@ -25,58 +25,73 @@ import torch.nn.functional as F
 from . import _lib
 
 
+def _conv3x3(c_in: int, c_out: int) -> nn.Conv2d:
+    return nn.Conv2d(c_in, c_out, kernel_size=3, padding=1, bias=False)
+
+
+def _conv1x1(c_in: int, c_out: int) -> nn.Conv2d:
+    return nn.Conv2d(c_in, c_out, kernel_size=1, bias=False)
+
+
 class ResidualBlock(nn.Module):
-    """Two 3x3 conv + BN with a skip connection (network.py:9-26)."""
+    """conv3x3 - BN - ReLU - conv3x3 - BN, skip connection, ReLU (network.py:9-26).  Attribute names and
+    creation order are part of the checkpoint format and of the seed -> weights mapping."""
 
     def __init__(self, channels: int):
         super().__init__()
-        self.conv1 = nn.Conv2d(channels, channels, kernel_size=3, padding=1, bias=False)
-        self.bn1 = nn.BatchNorm2d(channels)
-        self.conv2 = nn.Conv2d(channels, channels, kernel_size=3, padding=1, bias=False)
-        self.bn2 = nn.BatchNorm2d(channels)
+        self.conv1, self.bn1 = _conv3x3(channels, channels), nn.BatchNorm2d(channels)
+        self.conv2, self.bn2 = _conv3x3(channels, channels), nn.BatchNorm2d(channels)
 
     def forward(self, x):
-        y = F.relu(self.bn1(self.conv1(x)))
-        y = self.bn2(self.conv2(y))
-        return F.relu(y + x)
+        inner = F.relu(self.bn1(self.conv1(x)))
+        return F.relu(self.bn2(self.conv2(inner)) + x)
 
 
 class AlphaZeroNet(nn.Module):
-    """Parameter container with the reference's module names, creation order and
-    initialisation (network.py:41-83), so the same seed yields the same weights and
-    checkpoints are interchangeable.  ``forward`` is the autograd path used for training."""
+    """Parameter container of the policy/value ResNet with the reference's module names, creation order
+    and initialisation (network.py:41-83): the same seed yields the same weights and checkpoints are
+    interchangeable.  ``forward`` is the autograd path used for training; inference runs in the CUDA
+    library (``PyTorchModel.predict``)."""
 
     def __init__(self, in_channels: int = 3, board_size: int = 15, action_size: int = 15 * 15,
                  n_res_blocks: int = 6, channels: int = 128):
         super().__init__()
+        cells = board_size * board_size
         self.board_size, self.action_size, self.channels = board_size, action_size, channels
-        self.conv = nn.Conv2d(in_channels, channels, kernel_size=3, padding=1, bias=False)
-        self.bn = nn.BatchNorm2d(channels)
-        self.res_blocks = nn.ModuleList([ResidualBlock(channels) for _ in range(n_res_blocks)])
-        self.policy_conv = nn.Conv2d(channels, 2, kernel_size=1, bias=False)
-        self.policy_bn = nn.BatchNorm2d(2)
-        self.policy_fc = nn.Linear(2 * board_size * board_size, action_size)
-        self.value_conv = nn.Conv2d(channels, 1, kernel_size=1, bias=False)
-        self.value_bn = nn.BatchNorm2d(1)
-        self.value_fc1 = nn.Linear(board_size * board_size, 64)
-        self.value_fc2 = nn.Linear(64, 1)
-        for m in self.modules():                       # network.py:75-83
-            if isinstance(m, nn.Conv2d):
-                nn.init.kaiming_normal_(m.weight, nonlinearity="relu")
-            elif isinstance(m, nn.Linear):
-                nn.init.kaiming_uniform_(m.weight, nonlinearity="relu")
-                if m.bias is not None:
-                    nn.init.constant_(m.bias, 0)
+        # stem, tower
+        self.conv, self.bn = _conv3x3(in_channels, channels), nn.BatchNorm2d(channels)
+        self.res_blocks = nn.ModuleList(ResidualBlock(channels) for _ in range(n_res_blocks))
+        # policy head: 1x1 conv to two planes, then a dense layer over ch*cells + pixel
+        self.policy_conv, self.policy_bn = _conv1x1(channels, 2), nn.BatchNorm2d(2)
+        self.policy_fc = nn.Linear(2 * cells, action_size)
+        # value head: 1x1 conv to one plane, 64 hidden units, tanh
+        self.value_conv, self.value_bn = _conv1x1(channels, 1), nn.BatchNorm2d(1)
+        self.value_fc1, self.value_fc2 = nn.Linear(cells, 64), nn.Linear(64, 1)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        """Kaiming-normal convolutions, Kaiming-uniform dense layers with zero bias, in module
+        registration order (network.py:75-83) - the order fixes the random stream."""
+        for layer in self.modules():
+            if isinstance(layer, nn.Conv2d):
+                nn.init.kaiming_normal_(layer.weight, nonlinearity="relu")
+            elif isinstance(layer, nn.Linear):
+                nn.init.kaiming_uniform_(layer.weight, nonlinearity="relu")
+                if layer.bias is not None:
+                    nn.init.constant_(layer.bias, 0)
+
+    def trunk(self, x: torch.Tensor) -> torch.Tensor:
+        h = F.relu(self.bn(self.conv(x)))
+        for block in self.res_blocks:
+            h = block(h)
+        return h
 
     def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        h = F.relu(self.bn(self.conv(x)))
-        for blk in self.res_blocks:
-            h = blk(h)
-        p = F.relu(self.policy_bn(self.policy_conv(h)))
-        logits = self.policy_fc(p.view(p.shape[0], -1))
-        v = F.relu(self.value_bn(self.value_conv(h)))
-        v = F.relu(self.value_fc1(v.view(v.shape[0], -1)))
-        return logits, torch.tanh(self.value_fc2(v))
+        h = self.trunk(x)
+        pol = F.relu(self.policy_bn(self.policy_conv(h))).flatten(1)
+        val = F.relu(self.value_bn(self.value_conv(h))).flatten(1)
+        val = F.relu(self.value_fc1(val))
+        return self.policy_fc(pol), torch.tanh(self.value_fc2(val))
 
 
 def infer_architecture(state_dict) -> Tuple[int, int]:
@@ -130,38 +145,51 @@ class PyTorchModel:
         return self.predict(self.make_batch_from_states(states_list))
 
     # ------------------------------------------------------------------ training step (network.py:199-235)
-    def train_batch(self, states: np.ndarray, target_pis: np.ndarray, target_vs: np.ndarray, epochs: int = 1) -> dict:
+    def _to_device(self, a) -> torch.Tensor:
+        t = a if torch.is_tensor(a) else torch.from_numpy(np.asarray(a, dtype=np.float32))
+        return t.to(self.device, torch.float32)
+
+    def losses(self, states, target_pis, target_vs):
+        """(policy KL-divergence with batchmean reduction on log-softmax, value MSE) as in the reference."""
+        logits, values = self.net(states)
+        return self.policy_loss_fn(F.log_softmax(logits, dim=1), target_pis), self.value_loss_fn(values, target_vs)
+
+    def train_batch(self, states, target_pis, target_vs, epochs: int = 1) -> dict:
+        """``epochs`` Adam steps on one batch: loss = KL + MSE, gradient norm clipped at 3.0.  Accepts numpy
+        arrays (as the reference) or device tensors (no host copy)."""
         self.net.train()
-        to = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.asarray(a, dtype=np.float32))).to(self.device, torch.float32)
-        states_t, pis_t, vs_t = to(states), to(target_pis), to(target_vs)
-        tp = tv = tl = 0.0
+        x, pi, z = self._to_device(states), self._to_device(target_pis), self._to_device(target_vs)
+        sums = np.zeros(3)
         for _ in range(epochs):
             self.optimizer.zero_grad()
-            logits, values = self.net(states_t)
-            policy_loss = self.policy_loss_fn(F.log_softmax(logits, dim=1), pis_t)
-            value_loss = self.value_loss_fn(values, vs_t)
-            loss = policy_loss + value_loss
-            loss.backward()
+            policy_loss, value_loss = self.losses(x, pi, z)
+            total = policy_loss + value_loss
+            total.backward()
             torch.nn.utils.clip_grad_norm_(self.net.parameters(), 3.0)
             self.optimizer.step()
-            tp += float(policy_loss.item()); tv += float(value_loss.item()); tl += float(loss.item())
-        ne = float(epochs)
-        return {"policy_loss": tp / ne, "value_loss": tv / ne, "total_loss": tl / ne}
+            sums += (float(policy_loss.item()), float(value_loss.item()), float(total.item()))
+        p, v, t = (sums / float(epochs)).tolist()
+        return {"policy_loss": p, "value_loss": v, "total_loss": t}
 
     # ------------------------------------------------------------------ checkpoints (network.py:240-258)
+    def checkpoint(self) -> dict:
+        """The reference's checkpoint dictionary (depth and width are not stored there either)."""
+        return {"net": self.net.state_dict(), "opt": self.optimizer.state_dict(),
+                "board_size": self.board_size, "action_size": self.action_size}
+
     def save(self, path: str) -> None:
-        d = os.path.dirname(path)
-        if d:
-            os.makedirs(d, exist_ok=True)
-        torch.save({"net": self.net.state_dict(), "opt": self.optimizer.state_dict(),
-                    "board_size": self.board_size, "action_size": self.action_size}, path)
+        folder = os.path.dirname(path)
+        if folder:
+            os.makedirs(folder, exist_ok=True)
+        torch.save(self.checkpoint(), path)
 
     def load(self, path: str, map_location: Optional[str] = None) -> None:
         state = torch.load(path, map_location=map_location or self.device)
         self.net.load_state_dict(state["net"])
-        if state.get("opt") is not None:
-            try:
-                self.optimizer.load_state_dict(state["opt"])
+        opt = state.get("opt")
+        if opt is not None:
+            try:                                   # optimiser state of another architecture is skipped, as in the reference
+                self.optimizer.load_state_dict(opt)
             except Exception:
                 pass
 

@@ -1,5 +1,11 @@
-"""Drop-in ``Player`` (players/player_alpha.py:7-77): same constructor and ``play`` signature, the
-search and the network run on the B200 engine."""
+"""Drop-in AlphaZero ``Player`` on the B200 engine.
+
+Interface contract (players/player_alpha.py:7-77 of the reference, loaded by name from play.py:19-30):
+``Player(rules, board_size, n_simulations, c_puct, model_path, nn_model)``; ``play(board, turn_number,
+last_opponent_move) -> (row, col)``; attributes ``n_simulations`` and ``model_path`` are read by
+play_loop.py.  Only Gomoku is accepted, as in the reference.  The search tree lives on the GPU and is kept
+between calls (the reference never clears it either).
+"""
 from __future__ import annotations
 
 import numpy as np
@@ -8,36 +14,44 @@ from .games import Gomoku
 from .mcts import MCTS
 from .network import PyTorchModel
 
+DEFAULT_SNAPSHOT = "models/snapshot_iter140_20260109_190822.pt"     # the reference's default path
+
+
+def _as_board(board) -> np.ndarray:
+    """The caller passes either a list of rows or a game object (player_alpha.py:59-62)."""
+    cells = board if isinstance(board, list) else board.board
+    return np.array(cells, dtype=int)
+
+
+def _side_to_move(turn_number: int) -> int:
+    """Player 1 moves on even turns (player_alpha.py:65)."""
+    return 2 if turn_number % 2 else 1
+
 
 class Player:
-    def __init__(self, rules="gomoku", board_size=15, n_simulations=5000, c_puct=1.0,
-                 model_path="models/snapshot_iter140_20260109_190822.pt", nn_model=PyTorchModel):
-        self.rules = rules.lower()
-        self.board_size = board_size
-        self.n_simulations = n_simulations
-        self.c_puct = c_puct
-        self.model_path = model_path
-        self.net = nn_model(board_size=self.board_size)
-        if model_path is not None:
-            print(f"[PlayerAlpha] loading model: {model_path}")
-            self.net.load(model_path)
+    def __init__(self, rules="gomoku", board_size=15, n_simulations=5000, c_puct=1.0, model_path=DEFAULT_SNAPSHOT,
+                 nn_model=PyTorchModel):
+        self.rules, self.board_size = rules.lower(), board_size
+        self.n_simulations, self.c_puct, self.model_path = n_simulations, c_puct, model_path
+        self.net = nn_model(board_size=board_size)
+        if model_path is None:
+            print("[PlayerAlpha] no snapshot given: playing with random weights")
         else:
-            print("[PlayerAlpha] WARNING: no model given, using random weights")
+            print(f"[PlayerAlpha] loading {model_path}")
+            self.net.load(model_path)
         self.net.net.eval()
-        if self.rules != "gomoku":                     # player_alpha.py:35-36
+        if self.rules != "gomoku":
             raise ValueError(f"Unsupported rules: {self.rules}. Only 'gomoku' is supported.")
         self.game_class = Gomoku
-        self.mcts = MCTS(game_class=self.game_class, n_simulations=self.n_simulations, nn_model=self.net,
-                         cpuct=self.c_puct, add_dirichlet_noise=False)
+        self.mcts = MCTS(game_class=Gomoku, n_simulations=n_simulations, nn_model=self.net, cpuct=c_puct,
+                         add_dirichlet_noise=False)
 
     def play(self, board, turn_number, last_opponent_move):
-        """player_alpha.py:51-77: rebuild the position, search, return the argmax move (r, c)."""
-        game = self.game_class(size=self.board_size)
-        if isinstance(board, list):
-            game.board = np.array(board, dtype=int)
-        else:
-            game.board = np.array(board.board, dtype=int).copy()
-        game.current_player = 1 if turn_number % 2 == 0 else 2
-        game.last_move = last_opponent_move
-        pi = self.mcts.run(game, turn_number)
-        return divmod(int(np.argmax(pi)), self.board_size)
+        """Search from the given position and answer with the most visited move."""
+        position = self.game_class(size=self.board_size)
+        position.board = _as_board(board)
+        position.current_player = _side_to_move(turn_number)
+        position.last_move = last_opponent_move
+        visits = self.mcts.run(position, turn_number)
+        best = int(np.argmax(visits))
+        return best // self.board_size, best % self.board_size

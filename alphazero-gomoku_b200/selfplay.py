@@ -37,6 +37,9 @@ class SelfPlay:
         self.net = NetEngine(len(net.res_blocks), net.channels, self.device, max_batch=n_games * queue_len)
         self.net.load_state_dict(net.state_dict())
         self.channels, self.n_layers = net.channels, 2 * len(net.res_blocks)
+        # kernels per evaluated round: stem, one per 3x3 layer, head kernels (the 1x1 head convs are fused into the
+        # last layer up to 128 channels), commit
+        self._round_launches = 1 + self.n_layers + (1 if net.channels <= 128 and self.n_layers else 2) + 1
         check(lib.azg_selfplay_enable(self.engine._h, max_moves))
         dev = self.device
         self.probs = torch.empty((n_games * queue_len, 225), dtype=torch.float32, device=dev)
@@ -69,29 +72,12 @@ class SelfPlay:
     # ------------------------------------------------------------------ one ply for every game
     def search(self):
         """MCTS.run for all games; returns (pi, visits) on the device."""
-        eng = self.engine
-        eng.begin(self.n_sims)
-        launches = 1
-        if self.noise is not None:
-            eng._sync_stream()
-            check(lib.azg_selfplay_noise(eng._h, self.draw, ptr(self.noise)))
-            launches += 1
-        while True:
-            n_leaves, n_more, _ = eng.fill()
-            launches += 2
-            if n_leaves > 0:
-                self.net.forward_leaves(eng, self.probs)
-                eng.commit(self.probs, self.noise)
-                launches += 1 + self.n_layers + 2 + 1           # stem, 3x3 layers, two head kernels, commit
-                self.total_evals += n_leaves
-                self.total_rounds += 1
-            if n_more == 0:
-                break
-        self.total_sims += self.G * self.n_sims
-        self.total_launches += launches + 1
-        return eng.result()
+        self.search_begin()
+        while self.search_round():
+            pass
+        return self.engine.result()
 
-    # the same run split into its asynchronous pieces (used by PipelinedSelfPlay)
+    # the run in its asynchronous pieces (PipelinedSelfPlay interleaves them for two game groups)
     def search_begin(self):
         eng = self.engine
         eng.begin(self.n_sims)
@@ -111,7 +97,7 @@ class SelfPlay:
         if n_leaves > 0:
             self.net.forward_leaves(eng, self.probs)
             eng.commit(self.probs, self.noise)
-            self._launches += 1 + self.n_layers + 2 + 1
+            self._launches += self._round_launches
             self.total_evals += n_leaves
             self.total_rounds += 1
         if n_more == 0:
@@ -176,7 +162,7 @@ class SelfPlay:
         self.last_pi = self._pi
         self.total_sims += self.G * self.n_sims
         self.total_rounds += self._graph_rounds
-        self.total_launches += 2 + self._graph_rounds * (2 + 1 + self.n_layers + 2 + 1) + 5
+        self.total_launches += 2 + self._graph_rounds * (2 + self._round_launches) + 5
         return self._status
 
     def finish_step(self, pi):

@@ -51,10 +51,14 @@ struct Cfg {
   static constexpr bool STREAM = C > 128;
   static constexpr int NBLK = STREAM ? 9 : 9 * KC;        // weight blocks held in shared memory
   static constexpr int BBYTES = NBLK * BBLK;
-  static constexpr int TMEM_COLS = 2 * C;                 // two accumulators
+  // Accumulator ring in TMEM.  Two buffers only hide an epilogue that is SHORTER than the MMAs of a board;
+  // on residual layers its latency is longer (measured 5.9 k vs 4.25 k cycles), so the whole 512 columns
+  // are used: four buffers at 128 channels (MMA of board i+4 waits for the epilogue of board i).
+  static constexpr int NACC = C == 256 ? 2 : 4;
+  static constexpr int TMEM_COLS = NACC * C;              // 256 or 512 columns (a power of two)
   static constexpr int STAGES = MODE == 0 ? (C == 128 ? 4 : 6) : 3;   // activation tiles in flight
   static constexpr int EPI = (MODE == 1 || MODE == 4) ? 8 * 2048 : 0;                // per-warp epilogue staging tiles (32 rows x 64 B)
-  static constexpr int SMEM = 1024 + BBYTES + STAGES * Stage<MODE>::PITCH + EPI + 256;
+  static constexpr int SMEM = 1024 + BBYTES + STAGES * Stage<MODE>::PITCH + EPI + 512;
 };
 
 // Folded BatchNorm shift of the layer, passed by value so the epilogue reads it from the constant
@@ -91,9 +95,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + K::EPI);
   uint64_t* full = bars;                // [kStages]  leader: both CTAs' copies landed
   uint64_t* empty = bars + kStages;     // [kStages]  each CTA: MMAs reading the stage retired
-  uint64_t* tfull = bars + 2 * kStages; // [2]        each CTA: accumulator complete
-  uint64_t* tempty = tfull + 2;         // [2]        leader: both epilogues drained the accumulator
-  uint64_t* bfull = tempty + 2;         // leader: both weight halves resident (resident mode)
+  uint64_t* tfull = bars + 2 * kStages; // [NACC]     each CTA: accumulator complete
+  uint64_t* tempty = tfull + K::NACC;   // [NACC]     leader: both epilogues drained the accumulator
+  uint64_t* bfull = tempty + K::NACC;         // leader: both weight halves resident (resident mode)
   uint64_t* wfull = bfull + 1;          // [9] leader: weight ring slot filled by both CTAs (streaming mode)
   uint64_t* wempty = wfull + 9;         // [9] each CTA: MMAs reading the slot retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wempty + 9);
@@ -114,7 +118,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-      for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 16); }
+      for (int a = 0; a < K::NACC; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 16); }
       ptx::mbar_init(bfull, 1);
       for (int i = 0; i < 9; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1); }
       ptx::fence_barrier_init();
@@ -186,9 +190,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       long long t_full = 0, t_tempty = 0;
       const long long t_begin = clock64();
       for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
-        const int acc = it & 1;
+        const int acc = it % K::NACC;
         long long t0 = clock64();
-        if (!ptx::mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u)) { if (lane == 0) atomicExch(p.error, ERR_TEMPTY); ok = false; break; }
+        if (!ptx::mbar_wait(&tempty[acc], ((uint32_t)(it / K::NACC) & 1u) ^ 1u)) { if (lane == 0) atomicExch(p.error, ERR_TEMPTY); ok = false; break; }
         t_tempty += clock64() - t0;
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C);
@@ -286,7 +290,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     const uint32_t own_sw = (uint32_t)((lane >> 1) & 3);
     const int crow = lane >> 2, cunit = lane & 3;                          // coalesced mapping: row 8i + crow, unit cunit
     for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
-      const int acc = it & 1;
+      const int acc = it % K::NACC;
       const size_t grow0 = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)rank * 128 + (size_t)quad * 32;   // first row of this warp
       const size_t grow = grow0 + (size_t)lane;
       __nv_bfloat16* orow = p.out ? p.out + grow * C : nullptr;
@@ -308,7 +312,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
         }
       }
       const long long t0 = clock64();
-      if (!ptx::mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u)) { atomicExch(p.error, ERR_TFULL); ok = false; break; }
+      if (!ptx::mbar_wait(&tfull[acc], (uint32_t)(it / K::NACC) & 1u)) { atomicExch(p.error, ERR_TFULL); ok = false; break; }
       t_tfull += clock64() - t0;
       ptx::tc_fence_after();
       if (working) {

@@ -122,14 +122,14 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
       (rc = nalloc(n, &n->hidden, (size_t)((max_batch + 31) / 32) * AZG_HIDDEN_TILE)) ||
       (rc = nalloc(n, &n->keys, (size_t)max_batch * 16)) || (rc = nalloc(n, &n->meta, (size_t)max_batch)) ||
       (rc = nalloc(n, &n->n_dev, (size_t)4)) || (rc = nalloc(n, &n->error_dev, (size_t)4)) ||
-      (rc = nalloc(n, &n->prof_dev, (size_t)16))) {
+      (rc = nalloc(n, &n->prof_dev, (size_t)32))) {
     azg_net_destroy(n);
     return rc;
   }
   if (cudaMallocHost((void**)&n->pinned, 64) != cudaSuccess) { azg_net_destroy(n); return azg_fail(AZG_E_NOMEM, "pinned allocation failed"); }
   for (int i = 0; i < 3; ++i) cudaMemset(n->act[i], 0, n->rows * C * 2);      // pad rows must read as zero
   cudaMemset(n->error_dev, 0, 16);
-  cudaMemset(n->prof_dev, 0, 128);
+  cudaMemset(n->prof_dev, 0, 256);
   cudaMemset(n->hidden, 0, (size_t)((max_batch + 31) / 32) * AZG_HIDDEN_TILE * 4);
   {
     const char* pd = getenv("AZG_CONV_PHASES");      // clock the epilogue phases too when profiling
@@ -220,7 +220,7 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
   for (int l = 0; l < n_layers; ++l) {
     ConvArgs a;
     a.n_boards = n_ptr; a.max_boards = max_boards; a.layer = l; a.relu = 1;
-    a.shift_host = n->shift_host.data() + (size_t)l * C; a.error = n->error_dev; a.prof = n->profiling ? n->prof_dev : nullptr; a.prof_detail = n->prof_detail;
+    a.shift_host = n->shift_host.data() + (size_t)l * C; a.error = n->error_dev; a.prof = n->profiling ? n->prof_dev + 16 * (l & 1) : nullptr; a.prof_detail = n->prof_detail;   // [0..15] layers without, [16..31] with residual
     a.head_host = nullptr; a.hidden = nullptr;
     const bool fuse = heads && C <= 128 && l == n_layers - 1 && (l & 1) == 1;     // last conv2: fuse the 1x1 head convs, skip the store
     if (fuse) { a.head_host = n->head_host.data(); a.hidden = n->hidden; fused_heads = true; }
@@ -345,13 +345,14 @@ extern "C" int azg_net_profile_read(azg_net* n, double* trunk_ms, int64_t* launc
 // summed over clusters): {mma wait-full, mma wait-tmem-empty, mma total, producer wait-empty,
 // producer total, epilogue wait-tmem-full, epilogue total, boards, then five epilogue phases of one
 // warp: wait-for-store-drain, residual transpose, tcgen05.ld wait, compute + stage, fence + TMA store,
-// and three reserved}; out must hold 16 values; reading resets them.
+// and three reserved}, once for the layers without residual and once for those with; out must hold 32
+// values; reading resets them.
 extern "C" int azg_net_profile_counters(azg_net* n, uint64_t* out8) {
   if (!n || !out8) return azg_fail(AZG_E_ARG, "null argument");
   AZG_CUDA(cudaSetDevice(n->device));
   AZG_CUDA(cudaDeviceSynchronize());
-  AZG_CUDA(cudaMemcpy(out8, n->prof_dev, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  AZG_CUDA(cudaMemset(n->prof_dev, 0, 128));
+  AZG_CUDA(cudaMemcpy(out8, n->prof_dev, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  AZG_CUDA(cudaMemset(n->prof_dev, 0, 256));
   return AZG_OK;
 }
 

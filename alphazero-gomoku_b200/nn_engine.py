@@ -96,12 +96,15 @@ class NetEngine:
         return ms.value, n.value
 
     def profile_counters(self) -> dict:
-        out = (C.c_uint64 * 16)()
+        out = (C.c_uint64 * 32)()
         check(lib.azg_net_profile_counters(self._h, out))
         keys = ("mma_wait_full", "mma_wait_tmem_empty", "mma_total", "producer_wait_empty", "producer_total",
                 "epilogue_wait_tmem_full", "epilogue_total", "boards", "epi_wait_store_drain", "epi_residual_transpose",
                 "epi_tmem_ld_wait", "epi_compute_stage", "epi_fence_store")
-        return {k: int(out[i]) for i, k in enumerate(keys)}
+        res = {k: int(out[i]) + int(out[16 + i]) for i, k in enumerate(keys)}            # all layers
+        for tag, off in (("plain", 0), ("residual", 16)):                               # and split by layer type
+            res[tag] = {k: int(out[off + i]) for i, k in enumerate(keys)}
+        return res
 
     def check(self):
         check(lib.azg_net_check(self._h, _stream()))

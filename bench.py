@@ -295,7 +295,12 @@ def run_ours(args):
         trunk_ms += t_ms
         conv_launches += n_l
         for k, v in u.net.profile_counters().items():
-            pipe[k] = pipe.get(k, 0) + v
+            if isinstance(v, dict):
+                d = pipe.setdefault(k, {})
+                for kk, vv in v.items():
+                    d[kk] = d.get(kk, 0) + vv
+            else:
+                pipe[k] = pipe.get(k, 0) + v
         u.net.profile(False)
     t_after = totals()
     sims, evals = t_after["total_sims"] - t_before["total_sims"], t_after["total_evals"] - t_before["total_evals"]
@@ -395,7 +400,11 @@ def run_ours(args):
                          "launches": int(conv_launches), "avg_launch_ms": trunk_ms / max(conv_launches, 1),
                          "trunk_share_of_step": trunk_ms / ms if ms else None,
                          "algorithmic_flops_per_position_per_launch": TRUNK_FLOPS[args.channels],
-                         "pipeline_cycles_per_board": {k: round(v / max(pipe["boards"], 1), 1) for k, v in pipe.items() if k != "boards"}},
+                         "pipeline_cycles_per_board": {k: round(v / max(pipe["boards"], 1), 1) for k, v in pipe.items()
+                                                       if k != "boards" and not isinstance(v, dict)},
+                         "pipeline_cycles_per_board_by_layer_type": {
+                             t: {k: round(v / max(pipe[t]["boards"], 1), 1) for k, v in pipe[t].items() if k != "boards"}
+                             for t in ("plain", "residual") if t in pipe}},
             "clocks": clk,
             "search": {"rounds": int(rounds), "game_groups": len(units), "games_in_error": stats["games_in_error"],
                        "error_bits": stats["error_bits"], "max_nodes_per_game": stats["max_nodes"],

@@ -216,7 +216,7 @@ int azg_net_trunk_debug(azg_net* n, const float* planes, int count, int n_layers
 int azg_net_profile(azg_net* n, int enable);
 int azg_net_profile_read(azg_net* n, double* trunk_ms, int64_t* launches);
 /* Cycle counters of the conv3x3 pipeline roles collected while profiling (see net_engine.cu). */
-int azg_net_profile_counters(azg_net* n, uint64_t* out16);
+int azg_net_profile_counters(azg_net* n, uint64_t* out32);
 /* Synchronise and report the tcgen05 pipeline watchdog (0 = healthy). */
 int azg_net_check(azg_net* n, void* stream);
 

@@ -16,3 +16,5 @@ for line in sys.stdin:
           "wait_full", pipe.get("mma_wait_full"), "wait_tempty", pipe.get("mma_wait_tmem_empty"),
           "dropped", d.get("search", {}).get("dropped_trees"), "err", d.get("search", {}).get("games_in_error"),
           "epi", {k[4:]: v for k, v in pipe.items() if k.startswith("epi_")})
+    for t, v in r.get("pipeline_cycles_per_board_by_layer_type", {}).items():
+        print("   ", t, v)

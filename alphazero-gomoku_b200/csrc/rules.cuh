@@ -140,16 +140,28 @@ __device__ __forceinline__ void wpos_play(WPos& q, int rule, int a) {
   q.player = 3 - me;
 }
 
-// 64-bit position hash over stones + side to move (selects the bucket; the full
-// key is always compared, new_mcts_alpha.py:190-197).
+// Position hash over stones + side to move: the low word selects the probe window, the high word is
+// the slot tag (the full key is always compared, new_mcts_alpha.py:190-197).  Each owner lane mixes its
+// word pair into two 32-bit streams (murmur3 finaliser), the streams are XOR-reduced with redux.sync
+// and finalised once more - 32-bit multiplies only.
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+
 __device__ __forceinline__ unsigned long long wpos_hash(const WPos& q) {
   const int l = lane_id();
-  unsigned long long h = 0;
+  uint32_t ha = 0, hb = 0;
   if ((l & 3) == 0) {
-    const unsigned long long v = ((unsigned long long)q.w0 << 32) | q.w1;
-    h = mix64(v + 0x9E3779B97F4A7C15ULL * (unsigned long long)((l >> 2) + 1));
+    const uint32_t k = 0x9E3779B9u * (uint32_t)((l >> 2) + 1);
+    const uint32_t x = q.w0 * 0xcc9e2d51u + k;
+    const uint32_t y = q.w1 * 0x1b873593u + (k ^ 0x7f4a7c15u);
+    ha = fmix32(x ^ __funnelshift_l(y, y, 15));
+    hb = fmix32((y + __funnelshift_l(x, x, 7)) ^ 0x52dce729u);
   }
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) h ^= __shfl_xor_sync(AZG_FULL, h, s);
-  return mix64(h ^ (unsigned long long)q.player);
+  ha = __reduce_xor_sync(AZG_FULL, ha);
+  hb = __reduce_xor_sync(AZG_FULL, hb);
+  const uint32_t lo = fmix32(ha ^ (hb >> 3) ^ (uint32_t)q.player);
+  const uint32_t hi = fmix32(hb + lo * 0x9E3779B9u + 0x85ebca6bu);
+  return ((unsigned long long)hi << 32) | lo;
 }

@@ -172,24 +172,33 @@ __device__ __forceinline__ int puct_select(const azg_dev& e, int g, const NodeDa
   int best_i = 0x7fffffff;
   if (slot64 < 0) {
     // float32: ucb = W/(1+N) + ((cpuct*P)*sqrt_sum)/(1+N)     (new_mcts_alpha.py:136-137)
+    // Unvisited children divide by exactly 1.0f and a zero numerator gives +0, so both cases skip
+    // div.rn (whose zero-numerator slow path was 19 % of this kernel's instructions); results are
+    // bit-identical to the straight formula.
     const float sq = __fsqrt_rn((float)tot);
     float best = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (legal & (1u << j)) {
-        const float n1 = __fadd_rn(1.0f, (float)n[j]);
-        const float q = __fdiv_rn((float)w[j], n1);
-        const float u = __fdiv_rn(__fmul_rn(__fmul_rn(e.cpuct, p[j]), sq), n1);
+        const float x = __fmul_rn(__fmul_rn(e.cpuct, p[j]), sq);
+        float q = (float)w[j], u = x;
+        if (n[j] != 0) {
+          const float n1 = __fadd_rn(1.0f, (float)n[j]);
+          if (w[j] != 0) q = __fdiv_rn(q, n1);
+          if (x != 0.0f) u = __fdiv_rn(x, n1);
+        }
         const float s = __fadd_rn(q, u);
         if (s > best) { best = s; best_i = 8 * l + j; }
       }
     }
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-      const float ob = __shfl_xor_sync(AZG_FULL, best, s);
-      const int oi = __shfl_xor_sync(AZG_FULL, best_i, s);
-      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
-    }
+    // warp argmax, first index on ties: lanes own ascending index ranges, so the lowest lane holding the
+    // maximum wins.  Scores are never NaN and never -0 (q + u with u >= +0), so the usual order-preserving
+    // map float -> uint32 is exact.
+    const uint32_t bits = __float_as_uint(best);
+    const uint32_t key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+    const uint32_t top = __reduce_max_sync(AZG_FULL, key);
+    const int src = __ffs(__ballot_sync(AZG_FULL, key == top)) - 1;
+    best_i = __shfl_sync(AZG_FULL, best_i, src);
   } else {
     // float64 at a noised root: P is float64 there, so numpy promotes the exploration term
     // (SURVEY 0.6); the W/(1+N) term is still rounded to float32 first.
@@ -200,9 +209,14 @@ __device__ __forceinline__ int puct_select(const azg_dev& e, int g, const NodeDa
     for (int j = 0; j < 8; ++j) {
       const int idx = 8 * l + j;
       if ((legal & (1u << j)) && idx < AZG_A) {
-        const float n1 = __fadd_rn(1.0f, (float)n[j]);
-        const float q = __fdiv_rn((float)w[j], n1);
-        const double u = __ddiv_rn(__dmul_rn(__dmul_rn(e.cpuct64, __ldcg(P64 + idx)), sq), (double)n1);
+        const double x = __dmul_rn(__dmul_rn(e.cpuct64, __ldcg(P64 + idx)), sq);
+        float q = (float)w[j];
+        double u = x;
+        if (n[j] != 0) {
+          const float n1 = __fadd_rn(1.0f, (float)n[j]);
+          if (w[j] != 0) q = __fdiv_rn(q, n1);
+          if (x != 0.0) u = __ddiv_rn(x, (double)n1);
+        }
         const double s = __dadd_rn((double)q, u);
         if (s > best) { best = s; best_i = idx; }
       }

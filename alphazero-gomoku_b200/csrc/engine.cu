@@ -131,12 +131,14 @@ extern "C" int64_t azg_memory_bytes(const azg_engine* e) { return e ? e->bytes :
 
 extern "C" int azg_set_roots(azg_engine* e, const azg_pos* roots, const int32_t* mask, int clear_tree) {
   if (!e) return azg_fail(AZG_E_ARG, "null engine");
+  AZG_USE_DEVICE(e->cfg.device);
   azg_reset_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, mask, roots, clear_tree);
   return azg_check_launch("azg_set_roots");
 }
 
 extern "C" int azg_get_roots(azg_engine* e, azg_pos* roots_out) {
   if (!e || !roots_out) return azg_fail(AZG_E_ARG, "null argument");
+  AZG_USE_DEVICE(e->cfg.device);
   AZG_CUDA(cudaMemcpy2DAsync(roots_out, sizeof(azg_pos), &e->dev.ctl[0].root, sizeof(azg_ctl), sizeof(azg_pos), e->dev.G,
                              cudaMemcpyDeviceToDevice, e->stream));
   return AZG_OK;
@@ -144,6 +146,7 @@ extern "C" int azg_get_roots(azg_engine* e, azg_pos* roots_out) {
 
 extern "C" int azg_search_begin_masked(azg_engine* e, const int32_t* plies, int n_sims, const int32_t* mask) {
   if (!e || n_sims < 0) return azg_fail(AZG_E_ARG, "azg_search_begin: bad argument");
+  AZG_USE_DEVICE(e->cfg.device);
   e->dev.n_sims = n_sims;
   azg_begin_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, plies, n_sims, mask);
   return azg_check_launch("azg_search_begin");
@@ -155,6 +158,7 @@ extern "C" int azg_search_begin(azg_engine* e, const int32_t* plies, int n_sims)
 
 extern "C" int azg_search_fill(azg_engine* e, int32_t* n_leaves_host, int32_t* n_active_host, int32_t* n_roots_host) {
   if (!e) return azg_fail(AZG_E_ARG, "null engine");
+  AZG_USE_DEVICE(e->cfg.device);
   azg_fill_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev);
   azg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->dev);
   int rc = azg_check_launch("azg_search_fill");
@@ -179,6 +183,7 @@ extern "C" int azg_search_fill(azg_engine* e, int32_t* n_leaves_host, int32_t* n
 // Host copy of the counters written by the last azg_search_fill (synchronises the engine's stream only).
 extern "C" int azg_search_read_counters(azg_engine* e, int32_t* n_leaves_host, int32_t* n_active_host, int32_t* n_roots_host) {
   if (!e) return azg_fail(AZG_E_ARG, "null engine");
+  AZG_USE_DEVICE(e->cfg.device);
   int32_t* h = (int32_t*)e->pinned;
   AZG_CUDA(cudaMemcpyAsync(h, e->dev.counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   AZG_CUDA(cudaStreamSynchronize(e->stream));
@@ -193,30 +198,36 @@ extern "C" const int32_t* azg_search_counters(const azg_engine* e) { return e ? 
 
 extern "C" int azg_search_leaf_planes(azg_engine* e, float* planes) {
   if (!e || !planes) return azg_fail(AZG_E_ARG, "null argument");
+  AZG_USE_DEVICE(e->cfg.device);
   azg_leaf_planes_kernel<<<1184, 256, 0, e->stream>>>(e->dev, planes);
   return azg_check_launch("azg_search_leaf_planes");
 }
 
 extern "C" int azg_search_commit(azg_engine* e, const float* probs, const double* noise) {
   if (!e || !probs) return azg_fail(AZG_E_ARG, "null argument");
-  azg_commit_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, probs, noise);
+  AZG_USE_DEVICE(e->cfg.device);
+  const int warps = e->dev.queue_len < 32 ? e->dev.queue_len : 32;          // one warp per queued leaf
+  azg_commit_kernel<<<e->dev.G, 32 * warps, 0, e->stream>>>(e->dev, probs, noise);
   return azg_check_launch("azg_search_commit");
 }
 
 extern "C" int azg_search_result(azg_engine* e, float* pi, int32_t* visits) {
   if (!e) return azg_fail(AZG_E_ARG, "null engine");
+  AZG_USE_DEVICE(e->cfg.device);
   azg_finish_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, pi, visits);
   return azg_check_launch("azg_search_result");
 }
 
 extern "C" int azg_search_advance(azg_engine* e, const int32_t* actions, int gc, int reserve, int32_t* status) {
   if (!e) return azg_fail(AZG_E_ARG, "null engine");
+  AZG_USE_DEVICE(e->cfg.device);
   azg_advance_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, actions, gc, reserve, status);
   return azg_check_launch("azg_search_advance");
 }
 
 extern "C" int azg_search_stats(azg_engine* e, uint64_t* out_host) {
   if (!e || !out_host) return azg_fail(AZG_E_ARG, "null argument");
+  AZG_USE_DEVICE(e->cfg.device);
   azg_stats_kernel<<<1, 256, 0, e->stream>>>(e->dev, e->stats_dev);
   int rc = azg_check_launch("azg_search_stats");
   if (rc) return rc;

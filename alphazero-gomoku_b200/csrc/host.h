@@ -11,3 +11,7 @@ int azg_check_launch(const char* what);           // cudaGetLastError -> AZG_E_C
     cudaError_t _e = (x);                                                  \
     if (_e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(_e)); \
   } while (0)
+
+// Every entry point that launches work makes the handle's device current first (callers may drive several
+// GPUs from one thread); cudaSetDevice on the already-current device is a cheap no-op.
+#define AZG_USE_DEVICE(dev) AZG_CUDA(cudaSetDevice(dev))

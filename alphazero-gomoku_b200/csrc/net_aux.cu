@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(256) head1_kernel(HeadArgs a) {
 // ------------------------------------------------------------------------------------------------
 // 16 boards (half a feature tile) per block: 62 KB of shared memory, three blocks per SM.
 constexpr int kH2B = 16;
+constexpr int kPolSlice = 60, kValSlice = 30;      // K slices of the two dense layers: 8 slices each (450 = 7*60+30, 225 = 7*30+15)
 constexpr int kHead2Smem = (AZG_HID * kH2B + kH2B * 228 + kH2B * 64) * 4;
 
 __global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
@@ -312,21 +313,31 @@ __global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
       const float bias = a.pol_b[tid];
 #pragma unroll
       for (int b = 0; b < kH2B; ++b) acc[b] = bias;
-      for (int k0 = 0; k0 < 450; k0 += 10) {
-        float wv[10];                                   // ten weight loads in flight per thread
+      // K is summed in slices of kPolSlice (partial chain from 0, then added to the total in slice order):
+      // head2_small_kernel splits the same slices over its warps, so both kernels give identical bits
+      for (int s0 = 0; s0 < 450; s0 += kPolSlice) {
+        float part[kH2B];
 #pragma unroll
-        for (int u = 0; u < 10; ++u) wv[u] = __ldg(a.pol_wt + (size_t)(k0 + u) * 225 + tid);
+        for (int b = 0; b < kH2B; ++b) part[b] = 0.f;
+        const int s1 = s0 + kPolSlice < 450 ? s0 + kPolSlice : 450;
+        for (int k0 = s0; k0 < s1; k0 += 10) {
+          float wv[10];                                   // ten weight loads in flight per thread
 #pragma unroll
-        for (int u = 0; u < 10; ++u) {
-          const float w = wv[u];
-          const float4* h = reinterpret_cast<const float4*>(s_h + (k0 + u) * kH2B);
+          for (int u = 0; u < 10; ++u) wv[u] = __ldg(a.pol_wt + (size_t)(k0 + u) * 225 + tid);
 #pragma unroll
-          for (int q = 0; q < kH2B / 4; ++q) {
-            const float4 hv = h[q];
-            acc[4 * q] = fmaf(w, hv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(w, hv.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(w, hv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, hv.w, acc[4 * q + 3]);
+          for (int u = 0; u < 10; ++u) {
+            const float w = wv[u];
+            const float4* h = reinterpret_cast<const float4*>(s_h + (k0 + u) * kH2B);
+#pragma unroll
+            for (int q = 0; q < kH2B / 4; ++q) {
+              const float4 hv = h[q];
+              part[4 * q] = fmaf(w, hv.x, part[4 * q]); part[4 * q + 1] = fmaf(w, hv.y, part[4 * q + 1]);
+              part[4 * q + 2] = fmaf(w, hv.z, part[4 * q + 2]); part[4 * q + 3] = fmaf(w, hv.w, part[4 * q + 3]);
+            }
           }
         }
+#pragma unroll
+        for (int b = 0; b < kH2B; ++b) acc[b] += part[b];
       }
 #pragma unroll
       for (int b = 0; b < kH2B; ++b) s_lg[b * 228 + tid] = acc[b];
@@ -337,21 +348,29 @@ __global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
       const float bias = a.v1_b[tid];
 #pragma unroll
       for (int b = 0; b < kH2B; ++b) acc[b] = bias;
-      for (int k0 = 0; k0 < 225; k0 += 5) {
-        float wv[5];
+      for (int s0 = 0; s0 < 225; s0 += kValSlice) {
+        float part[kH2B];
 #pragma unroll
-        for (int u = 0; u < 5; ++u) wv[u] = __ldg(a.v1_wt + (size_t)(k0 + u) * 64 + tid);
+        for (int b = 0; b < kH2B; ++b) part[b] = 0.f;
+        const int s1 = s0 + kValSlice < 225 ? s0 + kValSlice : 225;
+        for (int k0 = s0; k0 < s1; k0 += 5) {
+          float wv[5];
 #pragma unroll
-        for (int u = 0; u < 5; ++u) {
-          const float w = wv[u];
-          const float4* h = reinterpret_cast<const float4*>(s_h + (450 + k0 + u) * kH2B);
+          for (int u = 0; u < 5; ++u) wv[u] = __ldg(a.v1_wt + (size_t)(k0 + u) * 64 + tid);
 #pragma unroll
-          for (int q = 0; q < kH2B / 4; ++q) {
-            const float4 hv = h[q];
-            acc[4 * q] = fmaf(w, hv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(w, hv.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(w, hv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, hv.w, acc[4 * q + 3]);
+          for (int u = 0; u < 5; ++u) {
+            const float w = wv[u];
+            const float4* h = reinterpret_cast<const float4*>(s_h + (450 + k0 + u) * kH2B);
+#pragma unroll
+            for (int q = 0; q < kH2B / 4; ++q) {
+              const float4 hv = h[q];
+              part[4 * q] = fmaf(w, hv.x, part[4 * q]); part[4 * q + 1] = fmaf(w, hv.y, part[4 * q + 1]);
+              part[4 * q + 2] = fmaf(w, hv.z, part[4 * q + 2]); part[4 * q + 3] = fmaf(w, hv.w, part[4 * q + 3]);
+            }
           }
         }
+#pragma unroll
+        for (int b = 0; b < kH2B; ++b) acc[b] += part[b];
       }
 #pragma unroll
       for (int b = 0; b < kH2B; ++b) s_v[b * 64 + tid] = fmaxf(acc[b], 0.f);
@@ -393,6 +412,128 @@ __global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
   }
 }
 
+// Small batches (the single-game path: <= 32 leaves per round): two boards per block, the K slices of the
+// dense layers spread over the eight warps, so a round pays one slice of dependent weight loads instead of
+// eight.  Same slices, same order of additions as head2_kernel: identical results.
+constexpr int kSB = 2;
+constexpr int kHead2SmallMax = 296;     // up to one block per SM pair slot: beyond that head2_kernel's 16-board tiles win
+__global__ void __launch_bounds__(256) head2_small_kernel(HeadArgs a) {
+  __shared__ float s_h[AZG_HID * kSB];             // [k][board]
+  __shared__ float s_part[8][kSB][228];
+  __shared__ float s_vpart[8][kSB][64];
+  __shared__ float s_lg[kSB][228];
+  __shared__ float s_v[kSB][64];
+  int n = *a.n_boards;
+  if (n > a.max_boards) n = a.max_boards;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_units = (n + kSB - 1) / kSB;
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int b0 = unit * kSB;
+    __syncthreads();
+    for (int i = tid; i < AZG_HID * kSB; i += 256) {
+      const int k = i / kSB, b = b0 + i % kSB;
+      s_h[i] = a.hidden[(size_t)(b >> 5) * (AZG_HID * 32) + (size_t)k * 32 + (b & 31)];
+    }
+    __syncthreads();
+    {   // policy_fc slice `warp`: outputs lane + 32 j
+      float part[8][kSB];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int b = 0; b < kSB; ++b) part[j][b] = 0.f;
+      const int s0 = warp * kPolSlice, s1 = s0 + kPolSlice < 450 ? s0 + kPolSlice : 450;
+#pragma unroll 2
+      for (int k = s0; k < s1; ++k) {
+        const float* wrow = a.pol_wt + (size_t)k * 225;
+        float wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[j] = lane + 32 * j < 225 ? __ldg(wrow + lane + 32 * j) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int b = 0; b < kSB; ++b) part[j][b] = fmaf(wv[j], s_h[k * kSB + b], part[j][b]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (lane + 32 * j < 225)
+#pragma unroll
+          for (int b = 0; b < kSB; ++b) s_part[warp][b][lane + 32 * j] = part[j][b];
+    }
+    {   // value_fc1 slice `warp`: outputs lane, lane + 32
+      float part[2][kSB];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int b = 0; b < kSB; ++b) part[j][b] = 0.f;
+      const int s0 = warp * kValSlice, s1 = s0 + kValSlice < 225 ? s0 + kValSlice : 225;
+#pragma unroll 5
+      for (int k = s0; k < s1; ++k) {
+        const float w0 = __ldg(a.v1_wt + (size_t)k * 64 + lane), w1 = __ldg(a.v1_wt + (size_t)k * 64 + 32 + lane);
+#pragma unroll
+        for (int b = 0; b < kSB; ++b) {
+          part[0][b] = fmaf(w0, s_h[(450 + k) * kSB + b], part[0][b]);
+          part[1][b] = fmaf(w1, s_h[(450 + k) * kSB + b], part[1][b]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int b = 0; b < kSB; ++b) s_vpart[warp][b][lane + 32 * j] = part[j][b];
+    }
+    __syncthreads();
+    if (tid < 225) {
+#pragma unroll
+      for (int b = 0; b < kSB; ++b) {
+        float acc = a.pol_b[tid];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += s_part[w][b][tid];
+        s_lg[b][tid] = acc;
+      }
+    }
+    if (tid < 64) {
+#pragma unroll
+      for (int b = 0; b < kSB; ++b) {
+        float acc = a.v1_b[tid];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += s_vpart[w][b][tid];
+        s_v[b][tid] = fmaxf(acc, 0.f);
+      }
+    }
+    __syncthreads();
+    if (warp < kSB && b0 + warp < n) {          // softmax over all 225 logits (network.py:180), one board per warp
+      const int gb = b0 + warp;
+      float v[8], mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int o = lane + 32 * j;
+        v[j] = o < 225 ? s_lg[warp][o] : -INFINITY;
+        mx = fmaxf(mx, v[j]);
+      }
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (a.logits && lane + 32 * j < 225) a.logits[(size_t)gb * 225 + lane + 32 * j] = v[j];
+        v[j] = lane + 32 * j < 225 ? expf(v[j] - mx) : 0.f;
+        sum += v[j];
+      }
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (lane + 32 * j < 225) a.probs[(size_t)gb * 225 + lane + 32 * j] = v[j] * inv;
+    }
+    if (a.values && tid >= 64 && tid < 64 + kSB && b0 + (tid - 64) < n) {     // value_fc2 + tanh (network.py:114-115)
+      const int b = tid - 64;
+      float acc = a.v2_b[0];
+      for (int o = 0; o < 64; ++o) acc = fmaf(s_v[b][o], a.v2_w[o], acc);
+      a.values[b0 + b] = tanhf(acc);
+    }
+  }
+}
+
 int azg_heads_launch(int C, const HeadArgs& a, int n_sm, cudaStream_t stream, bool skip_head1) {
   int grid = n_sm * 4;
   if (grid > a.max_boards) grid = a.max_boards;
@@ -405,6 +546,11 @@ int azg_heads_launch(int C, const HeadArgs& a, int n_sm, cudaStream_t stream, bo
     else return azg_fail(AZG_E_ARG, "heads: channels must be 64, 128 or 256");
     rc = azg_check_launch("head1_kernel");
     if (rc) return rc;
+  }
+  if (a.max_boards <= kHead2SmallMax) {
+    const int units = (a.max_boards + kSB - 1) / kSB;
+    head2_small_kernel<<<units, 256, 0, stream>>>(a);
+    return azg_check_launch("head2_small_kernel");
   }
   cudaError_t e = cudaFuncSetAttribute(head2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHead2Smem);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));

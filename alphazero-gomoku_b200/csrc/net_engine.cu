@@ -310,6 +310,8 @@ extern "C" int azg_net_forward_leaves(azg_net* n, azg_engine* e, float* probs, f
   if (!n || !e || !probs) return azg_fail(AZG_E_ARG, "azg_net_forward_leaves: null argument");
   const int cap = e->dev.G * e->dev.queue_len;
   if (cap > n->max_batch) return azg_fail(AZG_E_ARG, "azg_net_forward_leaves: network max_batch is smaller than games*queue_len");
+  if (e->cfg.device != n->device) return azg_fail(AZG_E_ARG, "azg_net_forward_leaves: engine and network live on different devices");
+  AZG_CUDA(cudaSetDevice(n->device));
   StemArgs st = {};
   st.keys = e->dev.key; st.meta = e->dev.meta; st.leaf_game = e->dev.leaf_game; st.leaf_node = e->dev.leaf_node;
   st.slab_stride = e->dev.cap;
@@ -359,5 +361,6 @@ extern "C" int azg_net_profile_counters(azg_net* n, uint64_t* out8) {
 // Watchdog status of the tcgen05 pipeline (0 = healthy); synchronises the stream.
 extern "C" int azg_net_check(azg_net* n, void* stream_) {
   if (!n) return azg_fail(AZG_E_ARG, "null network");
+  AZG_CUDA(cudaSetDevice(n->device));
   return check_watchdog(n, (cudaStream_t)stream_);
 }

@@ -248,12 +248,14 @@ extern "C" int azg_selfplay_enable(azg_engine* e, int max_plies) {
 
 extern "C" int azg_selfplay_noise(azg_engine* e, uint64_t draw, double* noise) {
   if (!e || !noise) return azg_fail(AZG_E_ARG, "null argument");
+  AZG_USE_DEVICE(e->cfg.device);
   noise_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, e->sp, draw, noise);
   return azg_check_launch("noise_kernel");
 }
 
 extern "C" int azg_selfplay_choose(azg_engine* e, const float* pi, float temp_threshold, uint64_t draw, int32_t* actions) {
   if (!e || !pi || !actions || !e->sp.ex_key) return azg_fail(AZG_E_ARG, "azg_selfplay_choose: bad argument (call azg_selfplay_enable first)");
+  AZG_USE_DEVICE(e->cfg.device);
   choose_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev, e->sp, pi, temp_threshold, draw, actions);
   return azg_check_launch("choose_kernel");
 }
@@ -261,6 +263,7 @@ extern "C" int azg_selfplay_choose(azg_engine* e, const float* pi, float temp_th
 extern "C" int azg_selfplay_finish(azg_engine* e, const int32_t* status, int max_moves, int use_symmetries, float* out,
                                    int64_t capacity, uint64_t* cursor, int32_t* done_mask, int32_t* winners) {
   if (!e || !status || !done_mask || !e->sp.ex_key || (out && !cursor)) return azg_fail(AZG_E_ARG, "azg_selfplay_finish: bad argument");
+  AZG_USE_DEVICE(e->cfg.device);
   finish_games_kernel<<<e->dev.G, 256, 0, e->stream>>>(e->dev, e->sp, status, max_moves, use_symmetries ? 8 : 1, out,
                                                         (long long)capacity, (unsigned long long*)cursor, done_mask, winners);
   return azg_check_launch("finish_games_kernel");

@@ -434,27 +434,30 @@ __device__ __forceinline__ T numpy_sum225(const T* sm) {
   return lo + hi;
 }
 
-extern "C" __global__ void __launch_bounds__(128)
+// One block per game, one warp per queued leaf (the leaves of a queue are distinct nodes, so they commit
+// independently; at most one of them is the root, which alone may take a float64 slot).
+extern "C" __global__ void __launch_bounds__(1024)
 azg_commit_kernel(azg_dev e, const float* __restrict__ probs, const double* __restrict__ noise) {
-  __shared__ float sm_f[4][AZG_ROW];
-  __shared__ double sm_d[4][AZG_ROW];
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (g >= e.G) return;
+  __shared__ float sm_f[32][AZG_ROW];
+  __shared__ double sm_d[AZG_ROW];
+  __shared__ int s_err;
+  const int g = blockIdx.x;
   const int l = lane_id();
-  const int wib = threadIdx.x >> 5;
+  const int wib = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   azg_ctl* ctl = e.ctl + g;
   const int state = ctl->state;
-  if (state != AZG_ST_NEED_EVAL && state != AZG_ST_NEED_FINAL) return;
+  if (state != AZG_ST_NEED_EVAL && state != AZG_ST_NEED_FINAL) return;      // block-uniform
   const int n_pending = ctl->n_pending;
   const int leaf_off = ctl->leaf_off;
   const int root_node = ctl->root_node;
   const bool noisy_run = e.noise_on && ctl->ply < e.noise_plies && noise != nullptr;
-  int p64_used = ctl->p64_used;
-  int err = 0;
+  const int p64_used = ctl->p64_used;
+  if (threadIdx.x == 0) s_err = 0;
+  __syncthreads();                                                          // every read of ctl precedes the final update
   float* smf = sm_f[wib];
-  double* smd = sm_d[wib];
+  double* smd = sm_d;
 
-  for (int i = 0; i < n_pending; ++i) {
+  for (int i = wib; i < n_pending; i += n_warps) {
     const int node = ctl->pending[i];
     const size_t off = azg_node_off(e, g, node);
     const size_t base = off * AZG_ROW;
@@ -486,9 +489,9 @@ azg_commit_kernel(azg_dev e, const float* __restrict__ probs, const double* __re
     if (noisy_run && node == root_node) {                                   // root Dirichlet mix (:171-174)
       int slot = -1;
       for (int s = 0; s < AZG_P64_SLOTS; ++s) if (!(p64_used & (1 << s))) { slot = s; break; }
-      if (slot < 0) { err |= AZG_ERR_P64; }
+      if (slot < 0) { if (l == 0) atomicOr(&s_err, AZG_ERR_P64); }
       else {
-        p64_used |= 1 << slot;
+        if (l == 0) ctl->p64_used = p64_used | (1 << slot);                 // only this warp touches the field
         meta |= (uint32_t)(slot + 1) << 4;
         const double* nz = noise + (size_t)g * AZG_A;
         const float keep = (float)(1.0 - e.eps);                            // (1-eps)*p stays float32 (NEP 50)
@@ -526,10 +529,11 @@ azg_commit_kernel(azg_dev e, const float* __restrict__ probs, const double* __re
     }
     if (l == 0) e.meta[off] = meta;
   }
-  if (l == 0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int err = s_err;
     ctl->evals += (unsigned long long)n_pending;
     ctl->n_pending = 0;
-    ctl->p64_used = p64_used;
     if (err) { ctl->err |= err; ctl->state = AZG_ST_ERROR; }
     else ctl->state = (state == AZG_ST_NEED_FINAL) ? AZG_ST_DONE : AZG_ST_RUN;
   }

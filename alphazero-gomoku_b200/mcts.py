@@ -55,6 +55,7 @@ class MCTS:
         self.last_visits = None         # int32[225] root visit counts of the last run (N[root] in the reference)
         self.n_evals = 0
         self._fresh = True
+        self._probs = None
 
     # ------------------------------------------------------------------ reference helpers
     def symmetries(self, state, pi):
@@ -96,19 +97,62 @@ class MCTS:
                         reserve=self.n_simulations + self.n_simulations // max(self.batch_size, 1) + 8)
         self._fresh = False
         eng.begin(self.n_simulations, torch.tensor([int(move_number)], dtype=torch.int32, device=self.device))
+        net = self._device_net()
+        if net is not None:
+            self._run_on_device(net, move_number)
+        else:
+            self._run_with_host_model(move_number)
+        pi, visits = eng.result()
+        self.last_visits = visits[0].cpu().numpy()
+        return pi[0].cpu().numpy()
+
+    def _root_noise(self, n_roots, move_number):
+        """numpy's global generator is advanced exactly when the reference advances it: once per run whose
+        root is evaluated while noise applies (new_mcts_alpha.py:170-172)."""
+        if not (n_roots and self.add_dirichlet_noise and move_number < self.apply_dirichlet_n_first_moves):
+            return None
+        d = np.random.dirichlet([self.dirichlet_alpha] * self.action_size)
+        return torch.from_numpy(np.ascontiguousarray(d, dtype=np.float64)[None, :]).to(self.device)
+
+    def _run_with_host_model(self, move_number):
+        """Any ``predict``-style evaluator: one host round trip per queue flush, as in the reference."""
+        eng = self.engine
         while True:
             n_leaves, n_more, n_roots = eng.fill()
             if n_leaves > 0:
                 probs = self._evaluate(eng.leaf_planes(n_leaves))
-                noise = None
-                if n_roots and self.add_dirichlet_noise and move_number < self.apply_dirichlet_n_first_moves:
-                    # drawn from numpy's global generator exactly when the reference draws (:171-172)
-                    d = np.random.dirichlet([self.dirichlet_alpha] * self.action_size)
-                    noise = torch.from_numpy(np.ascontiguousarray(d, dtype=np.float64)[None, :]).to(self.device)
-                eng.commit(probs.contiguous(), noise)
+                eng.commit(probs.contiguous(), self._root_noise(n_roots, move_number))
                 self.n_evals += n_leaves
             if n_more == 0:
                 break
-        pi, visits = eng.result()
-        self.last_visits = visits[0].cpu().numpy()
-        return pi[0].cpu().numpy()
+
+    def _device_net(self):
+        """The CUDA leaf evaluator of this package's ``PyTorchModel`` (None for any other evaluator)."""
+        ensure = getattr(self.nn_model, "_ensure_engine", None)
+        if ensure is None:
+            return None
+        net = ensure()
+        same_gpu = (net.device.index or 0) == (self.device.index or 0)
+        return net if net.max_batch >= self.batch_size and same_gpu else None
+
+    ROUNDS_PER_SYNC = 8
+
+    def _run_on_device(self, net, move_number):
+        """Latency path: the leaf batch never leaves the GPU and the host looks at the counters
+        only every ``ROUNDS_PER_SYNC`` rounds; rounds launched after the run has finished are no-ops (every
+        kernel takes its work count from device memory).  The first round is synchronous because the root
+        can only be evaluated there, and the reference draws its Dirichlet noise on the host."""
+        eng = self.engine
+        if self._probs is None:
+            self._probs = torch.empty((self.batch_size, 225), dtype=torch.float32, device=self.device)
+        n_leaves, n_more, n_roots = eng.fill()
+        if n_leaves > 0:
+            net.forward_leaves(eng, self._probs)
+            eng.commit(self._probs, self._root_noise(n_roots, move_number))
+        while n_more:
+            for _ in range(self.ROUNDS_PER_SYNC):
+                eng.fill_async()
+                net.forward_leaves(eng, self._probs)
+                eng.commit(self._probs, None)
+            _, n_more, _ = eng.read_counters()
+        self.n_evals = eng.stats()["evals"]

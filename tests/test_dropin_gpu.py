@@ -98,3 +98,39 @@ def test_batched_arena_equals_game_by_game():
     serial = tr.evaluate_models_serial(a, b, "gomoku", n_games=6, n_simulations=40, cpuct=1.0)
     assert batched == serial, (batched, serial)
     assert 0 <= batched[0] + batched[2] <= 6
+
+
+@pytest.mark.parametrize("noise", [False, True])
+def test_mcts_device_path_equals_host_model_path(noise):
+    """MCTS.run with this package's PyTorchModel keeps the leaf batch on the GPU and syncs every few rounds;
+    with the same network hidden behind a bare ``predict`` it takes the reference's host round trip per
+    queue flush.  Both must give the same visit counts, move after move (tree reuse + GC included), and
+    advance numpy's generator identically."""
+    import alphazero_gomoku_b200 as m
+    from alphazero_gomoku_b200.games import Gomoku
+    from alphazero_gomoku_b200.network import PyTorchModel
+
+    torch.manual_seed(5)
+    model = PyTorchModel(n_res_blocks=2, channels=64, device="cuda:0")
+
+    class HostOnly:
+        def predict(self, X):
+            return model.predict(X)
+
+    runs = []
+    for evaluator in (model, HostOnly()):
+        np.random.seed(7)
+        mcts = m.MCTS(Gomoku, 300, evaluator, add_dirichlet_noise=noise, dirichlet_alpha=0.3, epsilon=0.25)
+        game = Gomoku(15)
+        seq = []
+        for ply in range(5):
+            pi = mcts.run(game, ply)
+            seq.append((pi.copy(), mcts.last_visits.copy(), mcts.n_evals))
+            a = int(np.argmax(pi))
+            game.do_move((a // 15, a % 15))
+        seq.append(np.random.random())
+        runs.append(seq)
+        mcts.engine.close()
+    for (pa, va, ea), (pb, vb, eb) in zip(runs[0][:-1], runs[1][:-1]):
+        assert np.array_equal(va, vb) and np.array_equal(pa, pb) and ea == eb
+    assert runs[0][-1] == runs[1][-1]

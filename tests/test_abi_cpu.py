@@ -43,3 +43,25 @@ def test_no_cpu_fallback():
     assert m.lib.azg_device_count() == 0
     with pytest.raises(m.AzgError):
         m.SearchEngine(m.GOMOKU, 1)
+
+
+def test_argument_errors_are_codes_with_text():
+    """Error behaviour of the boundary: negative return code + azg_last_error() text, never an exception
+    or a crash from C (checked on paths that return before touching the device)."""
+    import alphazero_gomoku_b200 as m
+    from alphazero_gomoku_b200 import _lib
+    lib = m.lib
+    h = ctypes.c_void_p()
+    assert lib.azg_create(None, ctypes.byref(h)) < 0
+    assert b"null" in lib.azg_last_error()
+    cfg = _lib.azg_config()
+    cfg.n_games, cfg.queue_len, cfg.node_capacity, cfg.rule = 4, 65, 1024, 0          # queue_len > AZG_MAX_QUEUE
+    assert lib.azg_create(ctypes.byref(cfg), ctypes.byref(h)) < 0 and b"queue_len" in lib.azg_last_error()
+    cfg.queue_len, cfg.rule = 32, 7
+    assert lib.azg_create(ctypes.byref(cfg), ctypes.byref(h)) < 0
+    assert lib.azg_net_create(0, 6, 100, 64, ctypes.byref(h)) < 0 and b"channels" in lib.azg_last_error()
+    assert lib.azg_net_create(0, -1, 128, 64, ctypes.byref(h)) < 0
+    for fn in (lib.azg_search_fill, lib.azg_search_read_counters):
+        assert fn(None, None, None, None) < 0
+    assert lib.azg_search_commit(None, None, None) < 0
+    assert lib.azg_destroy(None) == 0 and lib.azg_net_destroy(None) == 0              # destroying nothing is fine

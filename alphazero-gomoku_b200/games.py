@@ -119,6 +119,14 @@ class _Game:
     def get_encoded_state(self) -> np.ndarray:
         return self._query(want_planes=True)[1][0]
 
+    def display(self) -> None:
+        """Text rendering of the position (the reference prints a coloured grid; same information)."""
+        marks = ".XO"
+        print("    " + " ".join(f"{c + 1:2}" for c in range(self.size)))
+        for r in range(self.size):
+            print(f"{r + 1:2}   " + "  ".join(marks[int(v)] for v in self.board[r]))
+        print(f"to move: {marks[self.current_player]}  last: {self.last_move}")
+
 
 class Gomoku(_Game):
     RULE = 0

@@ -75,6 +75,11 @@ class MCTS:
         self.engine.clear()
         self._fresh = True
 
+    def search(self, game_state, move_number):
+        """The reference's per-simulation recursion (new_mcts_alpha.py:102-151) has no host-side counterpart:
+        simulations run inside ``azg_fill_kernel``, ``n_simulations`` per ``run``."""
+        raise NotImplementedError("MCTS.search is internal to the CUDA engine; call run(game_state, move_number)")
+
     # ------------------------------------------------------------------ evaluation
     def _evaluate(self, planes: torch.Tensor) -> torch.Tensor:
         fast = getattr(self.nn_model, "predict_device", None)

@@ -93,6 +93,12 @@ class AlphaZeroNet(nn.Module):
         val = F.relu(self.value_fc1(val))
         return self.policy_fc(pol), torch.tanh(self.value_fc2(val))
 
+    def predict(self, state):
+        """(logits, value) of ONE encoded state through the autograd module, as network.py:119-129.  The search
+        never calls this (it uses ``PyTorchModel.predict``, which runs in the CUDA library)."""
+        x = torch.as_tensor(state, dtype=torch.float32, device=next(self.parameters()).device).unsqueeze(0)
+        return self(x)
+
 
 def infer_architecture(state_dict) -> Tuple[int, int]:
     """(n_res_blocks, channels) of a reference-layout state_dict."""

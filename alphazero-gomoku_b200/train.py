@@ -244,6 +244,21 @@ def evaluate_models(model_new: PyTorchModel, model_best: PyTorchModel, game_name
     return new_wins, new_wins / float(n_games), draws
 
 
+def evaluate_models_mp(model_new: PyTorchModel, model_best: PyTorchModel, board_size: int, action_size: int, n_games: int,
+                       n_simulations: int, cpuct: float, *, model_dir: str, num_workers: int, games_per_task: int = 1,
+                       device: str = "cpu", base_seed: int = 54321, torch_threads: int = 1) -> Tuple[int, float, int]:
+    """Signature of the reference's process-pool arena (train.py:492-569).  The pool, the checkpoint hand-off
+    and the per-task seeds are replaced by device batching: all games advance in lock step on the GPU, so
+    ``model_dir`` / ``num_workers`` / ``games_per_task`` / ``device`` / ``torch_threads`` are accepted and ignored;
+    ``base_seed`` seeds the first-stone draws."""
+    state = random.getstate()
+    random.seed(base_seed)
+    try:
+        return evaluate_models(model_new, model_best, "gomoku", n_games=n_games, n_simulations=n_simulations, cpuct=cpuct)
+    finally:
+        random.setstate(state)
+
+
 def evaluate_models_serial(model_new: PyTorchModel, model_best: PyTorchModel, game_name: str, n_games: int = 20,
                            n_simulations: int = 100, cpuct: float = 1.0) -> Tuple[int, float, int]:
     """The reference's loop verbatim in shape (one game at a time through the drop-in ``MCTS``); kept as

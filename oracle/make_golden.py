@@ -395,12 +395,61 @@ def build_net():
     np.savez_compressed(os.path.join(OUT, "net_outputs.npz"), **out)
 
 
+def build_api():
+    """Public surface of the reference classes/functions behind the drop-in boundary: member names
+    and, for callables, parameter names with their defaults -> tests/golden/api_surface.json."""
+    import importlib
+    import inspect
+    import json
+
+    def params(fn):
+        out = []
+        try:
+            sig = inspect.signature(fn)
+        except (TypeError, ValueError):
+            return None
+        for name, prm in sig.parameters.items():
+            d = prm.default
+            out.append([name, None if d is inspect._empty else repr(d) if not inspect.isclass(d) else d.__name__,
+                        d is not inspect._empty])
+        return out
+
+    def surface(cls):
+        members = {}
+        for name, obj in inspect.getmembers(cls):
+            if name.startswith("_") and name != "__init__":
+                continue
+            members[name] = params(obj) if callable(obj) else "attribute"
+        return members
+
+    train = importlib.import_module("train")
+    api = {
+        "MCTS": surface(MCTS),
+        "PyTorchModel": surface(importlib.import_module("network").PyTorchModel),
+        "AlphaZeroNet": surface(importlib.import_module("network").AlphaZeroNet),
+        "Gomoku": surface(Gomoku),
+        "Pente": surface(Pente),
+        "Player": surface(importlib.import_module("players.player_alpha").Player),
+        "train": {n: params(o) for n, o in inspect.getmembers(train)
+                  if inspect.isfunction(o) and o.__module__ == "train" and not n.startswith("_")},
+        "train_classes": {n: surface(o) for n, o in inspect.getmembers(train)
+                          if inspect.isclass(o) and o.__module__ == "train"},
+    }
+    # torch.nn.Module's own members are not the reference's surface
+    import torch
+    for k in set(dir(torch.nn.Module)):
+        api["AlphaZeroNet"].pop(k, None) if k not in ("forward", "__init__") else None
+    with open(os.path.join(OUT, "api_surface.json"), "w") as f:
+        json.dump(api, f, indent=1, sort_keys=True)
+    print("api surface:", {k: len(v) for k, v in api.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["rules", "search", "noise", "misc", "net"]
+    which = sys.argv[1:] or ["rules", "search", "noise", "misc", "net", "api"]
     for w in which:
         print(f"== {w}")
-        {"rules": build_rules, "search": build_search, "noise": build_noise, "misc": build_misc, "net": build_net}[w]()
+        {"rules": build_rules, "search": build_search, "noise": build_noise, "misc": build_misc, "net": build_net, "api": build_api}[w]()
 
 
 if __name__ == "__main__":

@@ -89,3 +89,44 @@ def test_mcts_symmetries_reference_order():
     out = MCTS.symmetries(None, z["planes"], z["pi"])
     for i, (s, g) in enumerate(out):
         assert np.array_equal(s, z["sym_planes"][i]) and np.array_equal(g, z["sym_pi"][i])
+
+
+def test_public_surface_matches_reference_fixture():
+    """Every public member of the reference classes behind the drop-in boundary exists here with the same
+    parameter names, order and defaults (tests/golden/api_surface.json, written by oracle/make_golden.py
+    from the reference itself).  Extra engine-specific keyword arguments may follow the reference's."""
+    import inspect
+    import json
+    import os
+    from conftest import ROOT
+    import alphazero_gomoku_b200 as m
+    from alphazero_gomoku_b200 import games, network, players, train
+
+    api = json.load(open(os.path.join(ROOT, "tests", "golden", "api_surface.json")))
+    ours = {"MCTS": m.MCTS, "PyTorchModel": network.PyTorchModel, "AlphaZeroNet": network.AlphaZeroNet,
+            "Gomoku": games.Gomoku, "Pente": games.Pente, "Player": players.Player}
+
+    def check_params(where, fn, ref_params):
+        mine = list(inspect.signature(fn).parameters.items())
+        assert len(mine) >= len(ref_params), where
+        for (name, prm), (rname, rdefault, has_default) in zip(mine, ref_params):
+            assert name == rname, (where, name, rname)
+            if has_default:
+                d = prm.default
+                assert d is not inspect._empty, (where, name)
+                got = d.__name__ if inspect.isclass(d) else repr(d)
+                assert got == rdefault, (where, name, got, rdefault)
+
+    for cls_name, cls in ours.items():
+        for member, ref_params in api[cls_name].items():
+            assert hasattr(cls, member), f"{cls_name}.{member} missing"
+            if isinstance(ref_params, list):
+                check_params(f"{cls_name}.{member}", getattr(cls, member), ref_params)
+    for fn_name, ref_params in api["train"].items():
+        assert hasattr(train, fn_name), f"train.{fn_name} missing"
+        check_params(f"train.{fn_name}", getattr(train, fn_name), ref_params)
+    for cls_name, members in api["train_classes"].items():
+        for member, ref_params in members.items():
+            assert hasattr(getattr(train, cls_name), member), f"train.{cls_name}.{member} missing"
+            if isinstance(ref_params, list):
+                check_params(f"train.{cls_name}.{member}", getattr(getattr(train, cls_name), member), ref_params)

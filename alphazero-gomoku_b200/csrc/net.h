@@ -9,7 +9,9 @@
 #define AZG_NET_FRONT 32          // zero rows in front of the first board of an activation buffer
 #define AZG_NET_BACK 32           // zero rows behind the last board
 #define AZG_NET_MAX_BLOCKS 40
-#define AZG_HIDDEN_TILE (676 * 32)   // floats per 32-board tile of head features
+#define AZG_HEAD_PITCH 704         // floats per board of head features: 450 policy (ch*225+pixel), 225 value, zero pad
+#define AZG_HEAD_WP_K 480          // K extent of the padded policy_fc matrix [240][480] (450 real columns)
+#define AZG_HEAD_WV_K 256          // K extent of the padded value_fc1 matrix [64][256]: column j is feature 448 + j
 
 struct ConvArgs {
   const int* n_boards;            // device: positions in this batch
@@ -20,7 +22,7 @@ struct ConvArgs {
   const __nv_bfloat16* residual;  // padded activation buffer added before the ReLU, or null
   __nv_bfloat16* out;             // padded activation buffer (null: do not store, fused-heads layer only)
   const float* head_host;         // HOST [3*C + 6]: fused 1x1 head weights, BN scale[3], shift[3]; null = plain layer
-  float* hidden;                  // head features, tiled [b/32][676][32] (fused-heads layer only)
+  float* hidden;                  // head features [board][AZG_HEAD_PITCH] (fused-heads layer only)
   int* error;                     // device flag set by the pipeline watchdogs
   unsigned long long* prof;       // optional device counters [16] (cycles spent waiting per role), or null
   int prof_detail;                // also clock the phases of one epilogue warp (slightly intrusive)
@@ -54,10 +56,8 @@ struct HeadArgs {
   const float* w1;                // [3][C]: policy conv rows 0-1, value conv row 2 (1x1)
   const float* scale1;            // [3] folded BN of the two head convs
   const float* shift1;            // [3]
-  float* hidden;                  // [max_boards][676]: 450 policy features (ch*225+pixel) then 225 value features
-  const float* pol_wt;            // [450][225] policy_fc.weight transposed
-  const float* pol_b;             // [225]
-  const float* v1_wt;             // [225][64] value_fc1.weight transposed
+  float* hidden;                  // [boards][AZG_HEAD_PITCH]: 450 policy features (ch*225+pixel), 225 value features, zeros
+  const float* pol_b;             // [240] policy_fc.bias, zero padded
   const float* v1_b;              // [64]
   const float* v2_w;              // [64]
   const float* v2_b;              // [1]
@@ -65,7 +65,13 @@ struct HeadArgs {
   float* values;                  // [n] (may be null)
   float* logits;                  // [n][225] optional raw logits (may be null)
 };
-int azg_heads_launch(int C, const HeadArgs& a, int n_sm, cudaStream_t stream, bool skip_head1);
+// 1x1 head convs (unless already fused into the last trunk layer) + the dense part on tensor cores (net_heads.cu).
+// tm_hid: fp32 [rows][AZG_HEAD_PITCH], box {32, 128}; tm_wp: fp32 [240][AZG_HEAD_WP_K], box {32, 240};
+// tm_wv: fp32 [64][AZG_HEAD_WV_K], box {32, 64}; all SWIZZLE_128B.
+int azg_heads_launch(int C, const HeadArgs& a, const CUtensorMap& tm_hid, const CUtensorMap& tm_wp, const CUtensorMap& tm_wv,
+                     int* error, int n_sm, cudaStream_t stream, bool skip_head1);
+int azg_heads_gemm_launch(const CUtensorMap& tm_hid, const CUtensorMap& tm_wp, const CUtensorMap& tm_wv, const HeadArgs& a,
+                          int* error, int n_sm, cudaStream_t stream);
 
 struct PackArgs {
   int C, n_blocks;

@@ -34,13 +34,6 @@ __global__ void pack_stem_kernel(const float* w, const float* scale, int C, floa
   out[i] = w[((size_t)c * 3 + plane) * 9 + tap] * scale[c];
 }
 
-__global__ void transpose_kernel(const float* in, int rows, int cols, float* out) {   // out[c][r] = in[r][c]
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * cols) return;
-  const int r = i / cols, c = i % cols;
-  out[(size_t)c * rows + r] = in[i];
-}
-
 int azg_pack_launch_fold(const float* g, const float* b, const float* m, const float* v, int n, float* scale, float* shift,
                          cudaStream_t s) {
   fold_bn_kernel<<<(n + 127) / 128, 128, 0, s>>>(g, b, m, v, n, scale, shift);
@@ -54,10 +47,7 @@ int azg_pack_launch_stem(const float* w, const float* scale, int C, float* out, 
   pack_stem_kernel<<<(27 * C + 255) / 256, 256, 0, s>>>(w, scale, C, out);
   return azg_check_launch("pack_stem");
 }
-int azg_pack_launch_transpose(const float* in, int rows, int cols, float* out, cudaStream_t s) {
-  transpose_kernel<<<(rows * cols + 255) / 256, 256, 0, s>>>(in, rows, cols, out);
-  return azg_check_launch("transpose");
-}
+
 
 // ------------------------------------------------------------------------------------------------
 // float planes -> packed stones (PyTorchModel.predict entry, network.py:168-183)
@@ -93,7 +83,11 @@ int azg_planes_to_keys_launch(const float* planes, int n, uint32_t* keys, uint32
 // instruction writes one full pixel row (C*2 bytes, coalesced).
 // Row-pattern tables: for tap row d (dr = d-1) and the 6-bit pattern of its three neighbour states
 // (2 bits each: 0 off-board, 1 empty, 2 mover, 3 opponent) the summed weight vector of that row is
-// precomputed in shared memory, so a pixel costs three 16-byte table reads instead of nine.
+// precomputed in shared memory, so a pixel costs at most three 16-byte table reads instead of nine.
+// The tables hold the DIFFERENCE to the all-empty in-board row (pattern 0b010101), and each lane keeps
+// shift + "nine empty neighbours" in registers: a tap row without stones or border costs no read at all
+// (the kernel is bound by shared-memory bandwidth, then by the HBM writes).
+constexpr uint32_t kRowEmpty = 0x15u;
 template <int CT>
 __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
   // CT channels in total; a block computes a slab of C = min(CT, 128) of them (blockIdx.y selects it)
@@ -102,29 +96,32 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
   const int cbase = blockIdx.y * C;
   a.w += cbase; a.shift += cbase; a.out += cbase;
   extern __shared__ __align__(16) float s_rows[];   // [3][64][C]
-  __shared__ __align__(16) float s_empty[C];         // shift + all nine taps on empty in-board cells
-  __shared__ __align__(16) float s_shift[C];
+  __shared__ __align__(16) float s_empty[C];
   __shared__ uint8_t s_state[256];                   // 0 off-board / pad, 1 empty, 2 mover stone, 3 opponent stone
   __shared__ uint32_t s_code[256];                   // the nine neighbour states of each padded pixel, 2 bits per tap
   for (int i = threadIdx.x; i < 3 * 64 * C; i += 256) {
     const int c = i % C, combo = (i / C) & 63, d = i / (64 * C);
-    float v = 0.f;
+    float v = 0.f, e = 0.f;
 #pragma unroll
     for (int dc = 0; dc < 3; ++dc) {
+      const int tap = d * 3 + dc;
+      e += a.w[(tap * 3 + 2) * CT + c];
       const int st = (combo >> (2 * dc)) & 3;
       if (st == 0) continue;
-      const int tap = d * 3 + dc;
       v += a.w[(tap * 3 + 2) * CT + c];
       if (st >= 2) v += a.w[(tap * 3 + (st - 2)) * CT + c];
     }
-    s_rows[i] = v;
+    s_rows[i] = v - e;
   }
   for (int i = threadIdx.x; i < C; i += 256) {
     float e = a.shift[i];
     for (int tap = 0; tap < 9; ++tap) e += a.w[(tap * 3 + 2) * CT + i];
     s_empty[i] = e;
-    s_shift[i] = a.shift[i];
   }
+  __syncthreads();
+  float base[CPL];                                     // shift + all nine taps on empty in-board cells
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) base[j] = s_empty[(threadIdx.x & 31) * CPL + j];
   int n = *a.n_boards;
   if (n > a.max_boards) n = a.max_boards;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -167,17 +164,17 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
       if (code == 0xffffffffu) {
 #pragma unroll
         for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
-      } else if (code == 0x15555u) {                       // nine empty in-board neighbours
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) acc[j] = fmaxf(s_empty[lane * CPL + j], 0.f);
       } else {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) acc[j] = s_shift[lane * CPL + j];
+        for (int j = 0; j < CPL; ++j) acc[j] = base[j];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const float* w = s_rows + (size_t)(d * 64 + ((code >> (6 * d)) & 63u)) * C + lane * CPL;
+          const uint32_t pat = (code >> (6 * d)) & 63u;
+          if (pat != kRowEmpty) {                          // warp-uniform: the code belongs to the pixel
+            const float* w = s_rows + (size_t)(d * 64 + pat) * C + lane * CPL;
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) acc[j] += w[j];
+            for (int j = 0; j < CPL; ++j) acc[j] += w[j];
+          }
         }
 #pragma unroll
         for (int j = 0; j < CPL; ++j) acc[j] = fmaxf(acc[j], 0.f);
@@ -222,9 +219,8 @@ int azg_stem_launch(int C, const StemArgs& a, int n_sm, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 // heads, part 1: the three 1x1 convolutions (policy 2 channels, value 1) + BN + ReLU
 // ------------------------------------------------------------------------------------------------
-// Output is tiled for part 2: hidden[(b/32)][k][b%32], k = ch*225 + pixel (policy, the
+// Output feeds the dense part (net_heads.cu): hidden[b][k], k = ch*225 + pixel (policy, the
 // reference's view(B, 2*225) order, network.py:105) then 450 + pixel (value).
-#define AZG_HID 676      // 675 features + 1 pad
 template <int C>
 __global__ void __launch_bounds__(256) head1_kernel(HeadArgs a) {
   constexpr int CPL = C / 32;
@@ -240,7 +236,7 @@ __global__ void __launch_bounds__(256) head1_kernel(HeadArgs a) {
   const float sh0 = a.shift1[0], sh1 = a.shift1[1], sh2 = a.shift1[2];
   for (int b = blockIdx.x; b < n; b += gridDim.x) {
     const __nv_bfloat16* act = a.act + ((size_t)AZG_NET_FRONT + (size_t)b * 256) * C;
-    float* hid = a.hidden + (size_t)(b >> 5) * (AZG_HID * 32) + (b & 31);
+    float* hid = a.hidden + (size_t)b * AZG_HEAD_PITCH;
     // four pixels per iteration so that four row loads are in flight per warp
     for (int p0 = warp * 4; p0 < 225; p0 += 32) {
       float x[4][CPL];
@@ -274,288 +270,27 @@ __global__ void __launch_bounds__(256) head1_kernel(HeadArgs a) {
           d2 += __shfl_xor_sync(0xffffffffu, d2, s);
         }
         if (lane == 0 && pix < 225) {
-          hid[(size_t)pix * 32] = fmaxf(fmaf(d0, sc0, sh0), 0.f);
-          hid[(size_t)(225 + pix) * 32] = fmaxf(fmaf(d1, sc1, sh1), 0.f);
-          hid[(size_t)(450 + pix) * 32] = fmaxf(fmaf(d2, sc2, sh2), 0.f);
+          hid[pix] = fmaxf(fmaf(d0, sc0, sh0), 0.f);
+          hid[225 + pix] = fmaxf(fmaf(d1, sc1, sh1), 0.f);
+          hid[450 + pix] = fmaxf(fmaf(d2, sc2, sh2), 0.f);
         }
       }
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// heads, part 2: policy_fc + softmax, value_fc1 + ReLU + value_fc2 + tanh, 16 boards per block
-// ------------------------------------------------------------------------------------------------
-// 16 boards (half a feature tile) per block: 62 KB of shared memory, three blocks per SM.
-constexpr int kH2B = 16;
-constexpr int kPolSlice = 60, kValSlice = 30;      // K slices of the two dense layers: 8 slices each (450 = 7*60+30, 225 = 7*30+15)
-constexpr int kHead2Smem = (AZG_HID * kH2B + kH2B * 228 + kH2B * 64) * 4;
-
-__global__ void __launch_bounds__(256) head2_kernel(HeadArgs a) {
-  extern __shared__ float sm[];
-  float* s_h = sm;                         // [676][16]
-  float* s_lg = sm + AZG_HID * kH2B;       // [16][228] logits
-  float* s_v = s_lg + kH2B * 228;          // [16][64]
-  int n = *a.n_boards;
-  if (n > a.max_boards) n = a.max_boards;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_units = (n + kH2B - 1) / kH2B;
-  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int tile = unit >> 1, half = unit & 1, b0 = unit * kH2B;
-    __syncthreads();
-    const float4* src = reinterpret_cast<const float4*>(a.hidden + (size_t)tile * (AZG_HID * 32) + half * kH2B);
-    float4* dst = reinterpret_cast<float4*>(s_h);
-    for (int i = tid; i < AZG_HID * 4; i += 256) dst[i] = src[(i >> 2) * 8 + (i & 3)];     // row k: 16 of the 32 boards
-    __syncthreads();
-    // policy_fc (network.py:106): logits[b][o] = bias[o] + sum_k W[o][k] h[b][k]
-    if (tid < 225) {
-      float acc[kH2B];
-      const float bias = a.pol_b[tid];
-#pragma unroll
-      for (int b = 0; b < kH2B; ++b) acc[b] = bias;
-      // K is summed in slices of kPolSlice (partial chain from 0, then added to the total in slice order):
-      // head2_small_kernel splits the same slices over its warps, so both kernels give identical bits
-      for (int s0 = 0; s0 < 450; s0 += kPolSlice) {
-        float part[kH2B];
-#pragma unroll
-        for (int b = 0; b < kH2B; ++b) part[b] = 0.f;
-        const int s1 = s0 + kPolSlice < 450 ? s0 + kPolSlice : 450;
-        for (int k0 = s0; k0 < s1; k0 += 10) {
-          float wv[10];                                   // ten weight loads in flight per thread
-#pragma unroll
-          for (int u = 0; u < 10; ++u) wv[u] = __ldg(a.pol_wt + (size_t)(k0 + u) * 225 + tid);
-#pragma unroll
-          for (int u = 0; u < 10; ++u) {
-            const float w = wv[u];
-            const float4* h = reinterpret_cast<const float4*>(s_h + (k0 + u) * kH2B);
-#pragma unroll
-            for (int q = 0; q < kH2B / 4; ++q) {
-              const float4 hv = h[q];
-              part[4 * q] = fmaf(w, hv.x, part[4 * q]); part[4 * q + 1] = fmaf(w, hv.y, part[4 * q + 1]);
-              part[4 * q + 2] = fmaf(w, hv.z, part[4 * q + 2]); part[4 * q + 3] = fmaf(w, hv.w, part[4 * q + 3]);
-            }
-          }
-        }
-#pragma unroll
-        for (int b = 0; b < kH2B; ++b) acc[b] += part[b];
-      }
-#pragma unroll
-      for (int b = 0; b < kH2B; ++b) s_lg[b * 228 + tid] = acc[b];
-    }
-    // value_fc1 + ReLU (network.py:113)
-    if (tid < 64) {
-      float acc[kH2B];
-      const float bias = a.v1_b[tid];
-#pragma unroll
-      for (int b = 0; b < kH2B; ++b) acc[b] = bias;
-      for (int s0 = 0; s0 < 225; s0 += kValSlice) {
-        float part[kH2B];
-#pragma unroll
-        for (int b = 0; b < kH2B; ++b) part[b] = 0.f;
-        const int s1 = s0 + kValSlice < 225 ? s0 + kValSlice : 225;
-        for (int k0 = s0; k0 < s1; k0 += 5) {
-          float wv[5];
-#pragma unroll
-          for (int u = 0; u < 5; ++u) wv[u] = __ldg(a.v1_wt + (size_t)(k0 + u) * 64 + tid);
-#pragma unroll
-          for (int u = 0; u < 5; ++u) {
-            const float w = wv[u];
-            const float4* h = reinterpret_cast<const float4*>(s_h + (450 + k0 + u) * kH2B);
-#pragma unroll
-            for (int q = 0; q < kH2B / 4; ++q) {
-              const float4 hv = h[q];
-              part[4 * q] = fmaf(w, hv.x, part[4 * q]); part[4 * q + 1] = fmaf(w, hv.y, part[4 * q + 1]);
-              part[4 * q + 2] = fmaf(w, hv.z, part[4 * q + 2]); part[4 * q + 3] = fmaf(w, hv.w, part[4 * q + 3]);
-            }
-          }
-        }
-#pragma unroll
-        for (int b = 0; b < kH2B; ++b) acc[b] += part[b];
-      }
-#pragma unroll
-      for (int b = 0; b < kH2B; ++b) s_v[b * 64 + tid] = fmaxf(acc[b], 0.f);
-    }
-    __syncthreads();
-    // softmax over all 225 logits (network.py:180), 2 boards per warp
-    for (int bb = 0; bb < kH2B / 8; ++bb) {
-      const int b = warp * (kH2B / 8) + bb, gb = b0 + b;
-      if (gb >= n) break;
-      float v[8], mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int o = lane + 32 * j;
-        v[j] = o < 225 ? s_lg[b * 228 + o] : -INFINITY;
-        mx = fmaxf(mx, v[j]);
-      }
-#pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (a.logits && lane + 32 * j < 225) a.logits[(size_t)gb * 225 + lane + 32 * j] = v[j];
-        v[j] = lane + 32 * j < 225 ? expf(v[j] - mx) : 0.f;
-        sum += v[j];
-      }
-#pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
-      const float inv = 1.0f / sum;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (lane + 32 * j < 225) a.probs[(size_t)gb * 225 + lane + 32 * j] = v[j] * inv;
-    }
-    // value_fc2 + tanh (network.py:114-115)
-    if (a.values && tid < kH2B && b0 + tid < n) {
-      float acc = a.v2_b[0];
-      for (int o = 0; o < 64; ++o) acc = fmaf(s_v[tid * 64 + o], a.v2_w[o], acc);
-      a.values[b0 + tid] = tanhf(acc);
-    }
-  }
-}
-
-// Small batches (the single-game path: <= 32 leaves per round): two boards per block, the K slices of the
-// dense layers spread over the eight warps, so a round pays one slice of dependent weight loads instead of
-// eight.  Same slices, same order of additions as head2_kernel: identical results.
-constexpr int kSB = 2;
-constexpr int kHead2SmallMax = 296;     // up to one block per SM pair slot: beyond that head2_kernel's 16-board tiles win
-__global__ void __launch_bounds__(256) head2_small_kernel(HeadArgs a) {
-  __shared__ float s_h[AZG_HID * kSB];             // [k][board]
-  __shared__ float s_part[8][kSB][228];
-  __shared__ float s_vpart[8][kSB][64];
-  __shared__ float s_lg[kSB][228];
-  __shared__ float s_v[kSB][64];
-  int n = *a.n_boards;
-  if (n > a.max_boards) n = a.max_boards;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_units = (n + kSB - 1) / kSB;
-  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int b0 = unit * kSB;
-    __syncthreads();
-    for (int i = tid; i < AZG_HID * kSB; i += 256) {
-      const int k = i / kSB, b = b0 + i % kSB;
-      s_h[i] = a.hidden[(size_t)(b >> 5) * (AZG_HID * 32) + (size_t)k * 32 + (b & 31)];
-    }
-    __syncthreads();
-    {   // policy_fc slice `warp`: outputs lane + 32 j
-      float part[8][kSB];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int b = 0; b < kSB; ++b) part[j][b] = 0.f;
-      const int s0 = warp * kPolSlice, s1 = s0 + kPolSlice < 450 ? s0 + kPolSlice : 450;
-#pragma unroll 2
-      for (int k = s0; k < s1; ++k) {
-        const float* wrow = a.pol_wt + (size_t)k * 225;
-        float wv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) wv[j] = lane + 32 * j < 225 ? __ldg(wrow + lane + 32 * j) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-          for (int b = 0; b < kSB; ++b) part[j][b] = fmaf(wv[j], s_h[k * kSB + b], part[j][b]);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (lane + 32 * j < 225)
-#pragma unroll
-          for (int b = 0; b < kSB; ++b) s_part[warp][b][lane + 32 * j] = part[j][b];
-    }
-    {   // value_fc1 slice `warp`: outputs lane, lane + 32
-      float part[2][kSB];
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int b = 0; b < kSB; ++b) part[j][b] = 0.f;
-      const int s0 = warp * kValSlice, s1 = s0 + kValSlice < 225 ? s0 + kValSlice : 225;
-#pragma unroll 5
-      for (int k = s0; k < s1; ++k) {
-        const float w0 = __ldg(a.v1_wt + (size_t)k * 64 + lane), w1 = __ldg(a.v1_wt + (size_t)k * 64 + 32 + lane);
-#pragma unroll
-        for (int b = 0; b < kSB; ++b) {
-          part[0][b] = fmaf(w0, s_h[(450 + k) * kSB + b], part[0][b]);
-          part[1][b] = fmaf(w1, s_h[(450 + k) * kSB + b], part[1][b]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int b = 0; b < kSB; ++b) s_vpart[warp][b][lane + 32 * j] = part[j][b];
-    }
-    __syncthreads();
-    if (tid < 225) {
-#pragma unroll
-      for (int b = 0; b < kSB; ++b) {
-        float acc = a.pol_b[tid];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) acc += s_part[w][b][tid];
-        s_lg[b][tid] = acc;
-      }
-    }
-    if (tid < 64) {
-#pragma unroll
-      for (int b = 0; b < kSB; ++b) {
-        float acc = a.v1_b[tid];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) acc += s_vpart[w][b][tid];
-        s_v[b][tid] = fmaxf(acc, 0.f);
-      }
-    }
-    __syncthreads();
-    if (warp < kSB && b0 + warp < n) {          // softmax over all 225 logits (network.py:180), one board per warp
-      const int gb = b0 + warp;
-      float v[8], mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int o = lane + 32 * j;
-        v[j] = o < 225 ? s_lg[warp][o] : -INFINITY;
-        mx = fmaxf(mx, v[j]);
-      }
-#pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (a.logits && lane + 32 * j < 225) a.logits[(size_t)gb * 225 + lane + 32 * j] = v[j];
-        v[j] = lane + 32 * j < 225 ? expf(v[j] - mx) : 0.f;
-        sum += v[j];
-      }
-#pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
-      const float inv = 1.0f / sum;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (lane + 32 * j < 225) a.probs[(size_t)gb * 225 + lane + 32 * j] = v[j] * inv;
-    }
-    if (a.values && tid >= 64 && tid < 64 + kSB && b0 + (tid - 64) < n) {     // value_fc2 + tanh (network.py:114-115)
-      const int b = tid - 64;
-      float acc = a.v2_b[0];
-      for (int o = 0; o < 64; ++o) acc = fmaf(s_v[b][o], a.v2_w[o], acc);
-      a.values[b0 + b] = tanhf(acc);
-    }
-  }
-}
-
-int azg_heads_launch(int C, const HeadArgs& a, int n_sm, cudaStream_t stream, bool skip_head1) {
-  int grid = n_sm * 4;
-  if (grid > a.max_boards) grid = a.max_boards;
-  if (grid < 1) grid = 1;
-  int rc = AZG_OK;
+int azg_heads_launch(int C, const HeadArgs& a, const CUtensorMap& tm_hid, const CUtensorMap& tm_wp, const CUtensorMap& tm_wv,
+                     int* error, int n_sm, cudaStream_t stream, bool skip_head1) {
   if (!skip_head1) {          // the 1x1 convs are normally fused into the last trunk layer's epilogue
+    int grid = n_sm * 4;
+    if (grid > a.max_boards) grid = a.max_boards;
+    if (grid < 1) grid = 1;
     if (C == 64) head1_kernel<64><<<grid, 256, 0, stream>>>(a);
     else if (C == 128) head1_kernel<128><<<grid, 256, 0, stream>>>(a);
     else if (C == 256) head1_kernel<256><<<grid, 256, 0, stream>>>(a);
     else return azg_fail(AZG_E_ARG, "heads: channels must be 64, 128 or 256");
-    rc = azg_check_launch("head1_kernel");
+    const int rc = azg_check_launch("head1_kernel");
     if (rc) return rc;
   }
-  if (a.max_boards <= kHead2SmallMax) {
-    const int units = (a.max_boards + kSB - 1) / kSB;
-    head2_small_kernel<<<units, 256, 0, stream>>>(a);
-    return azg_check_launch("head2_small_kernel");
-  }
-  cudaError_t e = cudaFuncSetAttribute(head2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHead2Smem);
-  if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
-  int tiles = (a.max_boards + kH2B - 1) / kH2B;
-  int grid2 = tiles < 3 * n_sm ? tiles : 3 * n_sm;
-  head2_kernel<<<grid2, 256, kHead2Smem, stream>>>(a);
-  return azg_check_launch("head2_kernel");
+  return azg_heads_gemm_launch(tm_hid, tm_wp, tm_wv, a, error, n_sm, stream);
 }

@@ -414,10 +414,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
         if constexpr (HEADS) {
           if (!pad) {
             const int pix = ((qi >> 4) - 1) * 15 + (qi & 15);
-            float* hid = p.hidden + (size_t)(b >> 5) * AZG_HIDDEN_TILE + (b & 31);
-            hid[(size_t)pix * 32] = fmaxf(fmaf(d0, head.scale[0], head.shift[0]), 0.f);
-            hid[(size_t)(225 + pix) * 32] = fmaxf(fmaf(d1, head.scale[1], head.shift[1]), 0.f);
-            hid[(size_t)(450 + pix) * 32] = fmaxf(fmaf(d2, head.scale[2], head.shift[2]), 0.f);
+            float* hid = p.hidden + (size_t)b * AZG_HEAD_PITCH + pix;        // consecutive lanes = consecutive pixels
+            hid[0] = fmaxf(fmaf(d0, head.scale[0], head.shift[0]), 0.f);
+            hid[225] = fmaxf(fmaf(d1, head.scale[1], head.shift[1]), 0.f);
+            hid[450] = fmaxf(fmaf(d2, head.scale[2], head.shift[2]), 0.f);
           }
         }
       }

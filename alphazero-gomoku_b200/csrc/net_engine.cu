@@ -11,7 +11,6 @@
 int azg_pack_launch_fold(const float*, const float*, const float*, const float*, int, float*, float*, cudaStream_t);
 int azg_pack_launch_conv3(const float*, const float*, int, int, __nv_bfloat16*, cudaStream_t);
 int azg_pack_launch_stem(const float*, const float*, int, float*, cudaStream_t);
-int azg_pack_launch_transpose(const float*, int, int, float*, cudaStream_t);
 
 struct azg_net {
   int device = 0, n_blocks = 0, C = 0, max_batch = 0, n_sm = 0, loaded = 0, conv_mode = 0, prof_detail = 0;
@@ -21,7 +20,8 @@ struct azg_net {
   float *scale3 = nullptr, *shift3 = nullptr;                         // [2*n_blocks][C]
   float *stem_w = nullptr, *stem_scale = nullptr, *stem_shift = nullptr;
   float *head_w1 = nullptr, *head_scale1 = nullptr, *head_shift1 = nullptr;
-  float *pol_wt = nullptr, *pol_b = nullptr, *v1_wt = nullptr, *v1_b = nullptr, *v2_w = nullptr, *v2_b = nullptr;
+  float *pol_w = nullptr, *pol_b = nullptr, *v1_w = nullptr, *v1_b = nullptr, *v2_w = nullptr, *v2_b = nullptr;   // pol_w [240][480], v1_w [64][256]: padded, see net.h
+  size_t hid_rows = 0;                   // rows of `hidden` (max_batch rounded up to the 128-board GEMM tile)
   __nv_bfloat16* act[3] = {nullptr, nullptr, nullptr};
   float* hidden = nullptr;
   uint32_t *keys = nullptr, *meta = nullptr;
@@ -29,6 +29,7 @@ struct azg_net {
   unsigned long long* prof_dev = nullptr;
   int* pinned = nullptr;
   CUtensorMap tm_act[3], tm_w, tm_st[3];      // tm_st: 32x32 SWIZZLE_64B store boxes over the activation buffers
+  CUtensorMap tm_hid, tm_wp, tm_wv;          // fp32 operand maps of the heads GEMM
   // optional timing of the 3x3 trunk (one CUDA-event pair per forward pass, on the launch stream)
   int profiling = 0;
   std::vector<cudaEvent_t> ev;          // start/stop pairs
@@ -53,18 +54,20 @@ static encode_fn get_encode() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows][cols] tensor, box {box_cols columns, box_rows}, 128-byte swizzle for 64-column
-// boxes (operand tiles) and 64-byte swizzle for 32-column boxes (epilogue store tiles).
-static int make_map(CUtensorMap* m, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols = 64) {
+// 2-D row-major [rows][cols] tensor (bf16, or fp32 when `f32`), box {box_cols columns, box_rows}: 128-byte swizzle
+// when the box row is 128 bytes (operand tiles), 64-byte swizzle for the 64-byte rows of the epilogue store tiles.
+static int make_map(CUtensorMap* m, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols = 64,
+                    bool f32 = false) {
   encode_fn enc = get_encode();
   if (!enc) return azg_fail(AZG_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const uint32_t esz = f32 ? 4u : 2u;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
+  cuuint64_t strides[1] = {cols * esz};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return azg_fail(AZG_E_CUDA, "cuTensorMapEncodeTiled failed");
   return AZG_OK;
 }
@@ -80,8 +83,8 @@ extern "C" int azg_net_destroy(azg_net* n) {
   if (!n) return AZG_OK;
   cudaSetDevice(n->device);
   cudaFree(n->w3); cudaFree(n->scale3); cudaFree(n->shift3); cudaFree(n->stem_w); cudaFree(n->stem_scale); cudaFree(n->stem_shift);
-  cudaFree(n->head_w1); cudaFree(n->head_scale1); cudaFree(n->head_shift1); cudaFree(n->pol_wt); cudaFree(n->pol_b);
-  cudaFree(n->v1_wt); cudaFree(n->v1_b); cudaFree(n->v2_w); cudaFree(n->v2_b);
+  cudaFree(n->head_w1); cudaFree(n->head_scale1); cudaFree(n->head_shift1); cudaFree(n->pol_w); cudaFree(n->pol_b);
+  cudaFree(n->v1_w); cudaFree(n->v1_b); cudaFree(n->v2_w); cudaFree(n->v2_b);
   for (int i = 0; i < 3; ++i) cudaFree(n->act[i]);
   cudaFree(n->hidden); cudaFree(n->keys); cudaFree(n->meta); cudaFree(n->n_dev); cudaFree(n->error_dev); cudaFree(n->prof_dev);
   if (n->pinned) cudaFreeHost(n->pinned);
@@ -109,17 +112,18 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
   cudaDeviceGetAttribute(&n->n_sm, cudaDevAttrMultiProcessorCount, device);
   const size_t C = channels, L = 2 * (size_t)n_blocks;
   n->rows = AZG_NET_FRONT + (size_t)max_batch * 256 + AZG_NET_BACK;
+  n->hid_rows = ((size_t)max_batch + 127) / 128 * 128;
   int rc = AZG_OK;
   if ((rc = nalloc(n, &n->w3, (L ? L : 1) * 9 * C * C)) || (rc = nalloc(n, &n->scale3, (L ? L : 1) * C)) ||
       (rc = nalloc(n, &n->shift3, (L ? L : 1) * C)) || (rc = nalloc(n, &n->stem_w, 27 * C)) ||
       (rc = nalloc(n, &n->stem_scale, C)) || (rc = nalloc(n, &n->stem_shift, C)) || (rc = nalloc(n, &n->head_w1, 3 * C)) ||
       (rc = nalloc(n, &n->head_scale1, (size_t)4)) || (rc = nalloc(n, &n->head_shift1, (size_t)4)) ||
-      (rc = nalloc(n, &n->pol_wt, (size_t)450 * 225)) || (rc = nalloc(n, &n->pol_b, (size_t)225)) ||
-      (rc = nalloc(n, &n->v1_wt, (size_t)225 * 64)) || (rc = nalloc(n, &n->v1_b, (size_t)64)) ||
+      (rc = nalloc(n, &n->pol_w, (size_t)240 * AZG_HEAD_WP_K)) || (rc = nalloc(n, &n->pol_b, (size_t)240)) ||
+      (rc = nalloc(n, &n->v1_w, (size_t)64 * AZG_HEAD_WV_K)) || (rc = nalloc(n, &n->v1_b, (size_t)64)) ||
       (rc = nalloc(n, &n->v2_w, (size_t)64)) || (rc = nalloc(n, &n->v2_b, (size_t)1)) ||
       (rc = nalloc(n, &n->act[0], n->rows * C)) || (rc = nalloc(n, &n->act[1], n->rows * C)) ||
       (rc = nalloc(n, &n->act[2], n->rows * C)) ||
-      (rc = nalloc(n, &n->hidden, (size_t)((max_batch + 31) / 32) * AZG_HIDDEN_TILE)) ||
+      (rc = nalloc(n, &n->hidden, n->hid_rows * AZG_HEAD_PITCH)) ||
       (rc = nalloc(n, &n->keys, (size_t)max_batch * 16)) || (rc = nalloc(n, &n->meta, (size_t)max_batch)) ||
       (rc = nalloc(n, &n->n_dev, (size_t)4)) || (rc = nalloc(n, &n->error_dev, (size_t)4)) ||
       (rc = nalloc(n, &n->prof_dev, (size_t)32))) {
@@ -130,7 +134,10 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
   for (int i = 0; i < 3; ++i) cudaMemset(n->act[i], 0, n->rows * C * 2);      // pad rows must read as zero
   cudaMemset(n->error_dev, 0, 16);
   cudaMemset(n->prof_dev, 0, 256);
-  cudaMemset(n->hidden, 0, (size_t)((max_batch + 31) / 32) * AZG_HIDDEN_TILE * 4);
+  cudaMemset(n->hidden, 0, n->hid_rows * AZG_HEAD_PITCH * 4);        // the pad columns stay zero (finite) for ever
+  cudaMemset(n->pol_w, 0, (size_t)240 * AZG_HEAD_WP_K * 4);           // zero rows 225..239 and columns 450..479
+  cudaMemset(n->pol_b, 0, 240 * 4);
+  cudaMemset(n->v1_w, 0, (size_t)64 * AZG_HEAD_WV_K * 4);
   {
     const char* pd = getenv("AZG_CONV_PHASES");      // clock the epilogue phases too when profiling
     n->prof_detail = pd ? atoi(pd) : 0;
@@ -147,6 +154,9 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
   for (int i = 0; i < 3; ++i)
     if ((rc = make_map(&n->tm_st[i], n->act[i], n->rows, C, 32, 32))) { azg_net_destroy(n); return rc; }
   if ((rc = make_map(&n->tm_w, n->w3, (L ? L : 1) * 9 * C, C, (uint32_t)(C / 2)))) { azg_net_destroy(n); return rc; }
+  if ((rc = make_map(&n->tm_hid, n->hidden, n->hid_rows, AZG_HEAD_PITCH, 128, 32, true)) ||
+      (rc = make_map(&n->tm_wp, n->pol_w, 240, AZG_HEAD_WP_K, 240, 32, true)) ||
+      (rc = make_map(&n->tm_wv, n->v1_w, 64, AZG_HEAD_WV_K, 64, 32, true))) { azg_net_destroy(n); return rc; }
   cudaError_t ce = cudaDeviceSynchronize();
   if (ce != cudaSuccess) { azg_net_destroy(n); return azg_fail(AZG_E_CUDA, cudaGetErrorString(ce)); }
   *out = n;
@@ -174,8 +184,12 @@ extern "C" int azg_net_load(azg_net* n, const azg_net_weights* w, void* stream_)
   AZG_CUDA(cudaMemcpyAsync(n->head_w1 + 2 * C, w->value_conv_w, C * sizeof(float), cudaMemcpyDeviceToDevice, s));
   if ((rc = azg_pack_launch_fold(w->policy_bn[0], w->policy_bn[1], w->policy_bn[2], w->policy_bn[3], 2, n->head_scale1, n->head_shift1, s))) return rc;
   if ((rc = azg_pack_launch_fold(w->value_bn[0], w->value_bn[1], w->value_bn[2], w->value_bn[3], 1, n->head_scale1 + 2, n->head_shift1 + 2, s))) return rc;
-  if ((rc = azg_pack_launch_transpose(w->policy_fc_w, 225, 450, n->pol_wt, s))) return rc;
-  if ((rc = azg_pack_launch_transpose(w->value_fc1_w, 64, 225, n->v1_wt, s))) return rc;
+  // dense head layers: the reference's [out][in] matrices are already the K-major B operands of the heads GEMM;
+  // value_fc1's feature j sits in hidden column 450 + j = padded column 2 + j (the value GEMM starts at column 448)
+  AZG_CUDA(cudaMemcpy2DAsync(n->pol_w, AZG_HEAD_WP_K * sizeof(float), w->policy_fc_w, 450 * sizeof(float), 450 * sizeof(float), 225,
+                             cudaMemcpyDeviceToDevice, s));
+  AZG_CUDA(cudaMemcpy2DAsync(n->v1_w + 2, AZG_HEAD_WV_K * sizeof(float), w->value_fc1_w, 225 * sizeof(float), 225 * sizeof(float), 64,
+                             cudaMemcpyDeviceToDevice, s));
   AZG_CUDA(cudaMemcpyAsync(n->pol_b, w->policy_fc_b, 225 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   AZG_CUDA(cudaMemcpyAsync(n->v1_b, w->value_fc1_b, 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   AZG_CUDA(cudaMemcpyAsync(n->v2_w, w->value_fc2_w, 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -234,9 +248,9 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
   if (heads) {
     HeadArgs h;
     h.n_boards = n_ptr; h.max_boards = max_boards; h.act = n->act[last]; h.w1 = n->head_w1; h.scale1 = n->head_scale1;
-    h.shift1 = n->head_shift1; h.hidden = n->hidden; h.pol_wt = n->pol_wt; h.pol_b = n->pol_b; h.v1_wt = n->v1_wt;
+    h.shift1 = n->head_shift1; h.hidden = n->hidden; h.pol_b = n->pol_b;
     h.v1_b = n->v1_b; h.v2_w = n->v2_w; h.v2_b = n->v2_b; h.probs = probs; h.values = values; h.logits = logits;
-    if ((rc = azg_heads_launch(C, h, n->n_sm, s, fused_heads))) return rc;
+    if ((rc = azg_heads_launch(C, h, n->tm_hid, n->tm_wp, n->tm_wv, n->error_dev, n->n_sm, s, fused_heads))) return rc;
   }
   return AZG_OK;
 }

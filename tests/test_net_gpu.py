@@ -167,13 +167,13 @@ def test_search_with_real_network_on_device():
 
 
 def test_outputs_do_not_depend_on_batch_shape():
-    """The small-batch head kernel (<= 296 boards) and the 16-board-tile kernel add the same K slices in the
-    same order: a position evaluates to identical bits whatever batch it travels in (the search's sharding
-    and pipelining invariance rests on this)."""
+    """A row of the heads GEMM depends on that board's features only and the trunk handles boards independently:
+    a position evaluates to identical bits whatever batch it travels in (the search's sharding and pipelining
+    invariance rests on this)."""
     sd, eng = build(2, 128, seed=3, max_batch=1024)
     X = torch.from_numpy(positions(24, seed=11)).cuda()
-    small_p, small_v = eng.forward(X)                        # 24 boards: head2_small_kernel
-    big = X.repeat(30, 1, 1, 1)                              # 720 boards: head2_kernel
+    small_p, small_v = eng.forward(X)                        # 24 boards: one partly filled 128-board tile
+    big = X.repeat(30, 1, 1, 1)                              # 720 boards: six tiles on six SMs
     big_p, big_v = eng.forward(big)
     assert torch.equal(small_p, big_p[:24]) and torch.equal(small_p, big_p[-24:])
     assert torch.equal(small_v, big_v[:24]) and torch.equal(small_v, big_v[-24:])

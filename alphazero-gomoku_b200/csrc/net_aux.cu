@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
         const uint32_t st = (q2 >= 0 && q2 < 256) ? s_state[q2] : 0;
         code |= st << (2 * tap);
       }
-      s_code[qi] = s_state[qi] ? code : 0xffffffffu;      // pad rows/columns are written as zeros
+      s_code[qi] = s_state[qi] ? code : 0xffffffffu;      // pad rows/columns
     }
     __syncthreads();
     __nv_bfloat16* out = a.out + ((size_t)AZG_NET_FRONT + (size_t)b * 256) * CT;
@@ -160,11 +160,11 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
     for (int i = 0; i < 32; ++i) {
       const int qi = warp * 32 + i;
       const uint32_t code = s_code[qi];
+      // pad rows / columns are not written: the buffers are zeroed at creation and every writer (this kernel, the
+      // trunk epilogue) keeps the pad positions zero, so they still are (12 % fewer bytes to HBM)
+      if (code == 0xffffffffu) continue;
       float acc[CPL];
-      if (code == 0xffffffffu) {
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
-      } else {
+      {
 #pragma unroll
         for (int j = 0; j < CPL; ++j) acc[j] = base[j];
 #pragma unroll

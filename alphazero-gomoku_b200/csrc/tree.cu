@@ -350,22 +350,22 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
 // leaf batch assembly: exclusive scan of the per-game queue lengths (single block)
 // ------------------------------------------------------------------------------------------------
 extern "C" __global__ void __launch_bounds__(1024) azg_scan_kernel(azg_dev e) {
-  __shared__ int part[1024];
+  __shared__ int part[1024], s_n[1024], s_off[1024], s_rn[1024];
   __shared__ int carry, s_active, s_errors, s_roots;
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
   if (t == 0) { carry = 0; s_active = 0; s_errors = 0; s_roots = 0; }
   __syncthreads();
   for (int base = 0; base < e.G; base += 1024) {
     const int g = base + t;
-    int n = 0, st = AZG_ST_DONE;
+    int n = 0, st = AZG_ST_DONE, rn = -1;
     if (g < e.G) {
       st = e.ctl[g].state;
       if (st == AZG_ST_NEED_EVAL || st == AZG_ST_NEED_FINAL) n = e.ctl[g].n_pending;
-      if (st == AZG_ST_RUN || st == AZG_ST_NEED_EVAL) atomicAdd(&s_active, 1);   // needs another fill after the commit
-      if (st == AZG_ST_ERROR) atomicAdd(&s_errors, 1);
-      const int rn = e.ctl[g].root_node;
-      for (int i = 0; i < n; ++i) if (e.ctl[g].pending[i] == rn) atomicAdd(&s_roots, 1);
+      rn = e.ctl[g].root_node;
     }
+    const int act = __popc(__ballot_sync(AZG_FULL, st == AZG_ST_RUN || st == AZG_ST_NEED_EVAL));   // needs another fill after the commit
+    const int bad = __popc(__ballot_sync(AZG_FULL, st == AZG_ST_ERROR));
+    if (l == 0 && (act | bad)) { atomicAdd(&s_active, act); atomicAdd(&s_errors, bad); }
     part[t] = n;
     __syncthreads();
     for (int s = 1; s < 1024; s <<= 1) {
@@ -375,13 +375,23 @@ extern "C" __global__ void __launch_bounds__(1024) azg_scan_kernel(azg_dev e) {
       __syncthreads();
     }
     const int off = carry + part[t] - n;
-    if (g < e.G) {
-      e.ctl[g].leaf_off = off;
-      for (int i = 0; i < n; ++i) {
-        e.leaf_game[off + i] = g;
-        e.leaf_node[off + i] = e.ctl[g].pending[i];
+    if (g < e.G) e.ctl[g].leaf_off = off;
+    s_n[t] = n; s_off[t] = off; s_rn[t] = rn;
+    __syncthreads();
+    // the queues are copied by warps: lane i moves entry i of one game (coalesced on both sides)
+    int roots = 0;
+    for (int k = 0; k < 32; ++k) {
+      const int j = w * 32 + k, gg = base + j;
+      const int nn = s_n[j];
+      for (int i = l; i < nn; i += 32) {
+        const int node = e.ctl[gg].pending[i];
+        e.leaf_game[s_off[j] + i] = gg;
+        e.leaf_node[s_off[j] + i] = node;
+        roots += node == s_rn[j];
       }
     }
+    roots = __reduce_add_sync(AZG_FULL, roots);
+    if (l == 0 && roots) atomicAdd(&s_roots, roots);
     __syncthreads();
     if (t == 1023) carry += part[t];
     __syncthreads();

@@ -89,7 +89,7 @@ int azg_planes_to_keys_launch(const float* planes, int n, uint32_t* keys, uint32
 // (the kernel is bound by shared-memory bandwidth, then by the HBM writes).
 constexpr uint32_t kRowEmpty = 0x15u;
 template <int CT>
-__global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
+__global__ void __launch_bounds__(512) stem_kernel(StemArgs a) {
   // CT channels in total; a block computes a slab of C = min(CT, 128) of them (blockIdx.y selects it)
   constexpr int C = CT > 128 ? 128 : CT;
   constexpr int CPL = C / 32;
@@ -97,9 +97,13 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
   a.w += cbase; a.shift += cbase; a.out += cbase;
   extern __shared__ __align__(16) float s_rows[];   // [3][64][C]
   __shared__ __align__(16) float s_empty[C];
-  __shared__ uint8_t s_state[256];                   // 0 off-board / pad, 1 empty, 2 mover stone, 3 opponent stone
-  __shared__ uint32_t s_code[256];                   // the nine neighbour states of each padded pixel, 2 bits per tap
-  for (int i = threadIdx.x; i < 3 * 64 * C; i += 256) {
+  // 512 threads: two boards at a time (threads 0-255 and 256-511) share one copy of the tables.  The kernel is bound by
+  // instruction issue (ncu: 0.48 IPC per scheduler at 4 warps), and the 96 KB of tables allow only two blocks per SM,
+  // so the second board per block is what doubles the resident warps.
+  __shared__ uint8_t s_state[2][256];                // 0 off-board / pad, 1 empty, 2 mover stone, 3 opponent stone
+  __shared__ uint32_t s_code[2][256];                // the nine neighbour states of each padded pixel, 2 bits per tap
+  const int sub = threadIdx.x >> 8, tid = threadIdx.x & 255;
+  for (int i = threadIdx.x; i < 3 * 64 * C; i += 512) {
     const int c = i % C, combo = (i / C) & 63, d = i / (64 * C);
     float v = 0.f, e = 0.f;
 #pragma unroll
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
     }
     s_rows[i] = v - e;
   }
-  for (int i = threadIdx.x; i < C; i += 256) {
+  for (int i = threadIdx.x; i < C; i += 512) {
     float e = a.shift[i];
     for (int tap = 0; tap < 9; ++tap) e += a.w[(tap * 3 + 2) * CT + i];
     s_empty[i] = e;
@@ -124,15 +128,17 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
   for (int j = 0; j < CPL; ++j) base[j] = s_empty[(threadIdx.x & 31) * CPL + j];
   int n = *a.n_boards;
   if (n > a.max_boards) n = a.max_boards;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int b = blockIdx.x; b < n; b += gridDim.x) {
-    size_t node = (size_t)b;
-    if (a.leaf_game) node = (size_t)a.leaf_game[b] * (size_t)a.slab_stride + (size_t)a.leaf_node[b];
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int pb = blockIdx.x; pb * 2 < n; pb += gridDim.x) {
+    const int b = pb * 2 + sub;
+    const bool live = b < n;
+    size_t node = (size_t)(live ? b : n - 1);
+    if (a.leaf_game) node = (size_t)a.leaf_game[live ? b : n - 1] * (size_t)a.slab_stride + (size_t)a.leaf_node[live ? b : n - 1];
     const uint32_t* k = a.keys + node * 16;
     const int player = (int)((a.meta[node] >> 1) & 3u);
     __syncthreads();
     {
-      const int qi = threadIdx.x, y = qi >> 4, x = qi & 15;
+      const int qi = tid, y = qi >> 4, x = qi & 15;
       uint8_t st = 0;
       if (y >= 1 && x < 15) {
         const int cell = (y - 1) * 15 + x;
@@ -140,26 +146,26 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
         const uint32_t mine = player == 2 ? b2 : b1, theirs = player == 2 ? b1 : b2;
         st = mine ? 2 : (theirs ? 3 : 1);
       }
-      s_state[qi] = st;
+      s_state[sub][qi] = st;
     }
     __syncthreads();
     {
-      const int qi = threadIdx.x;
+      const int qi = tid;
       uint32_t code = 0;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const int q2 = qi + (tap / 3 - 1) * 16 + (tap % 3 - 1);
-        const uint32_t st = (q2 >= 0 && q2 < 256) ? s_state[q2] : 0;
+        const uint32_t st = (q2 >= 0 && q2 < 256) ? s_state[sub][q2] : 0;
         code |= st << (2 * tap);
       }
-      s_code[qi] = s_state[qi] ? code : 0xffffffffu;      // pad rows/columns
+      s_code[sub][qi] = (live && s_state[sub][qi]) ? code : 0xffffffffu;      // pad rows/columns (and the odd board out)
     }
     __syncthreads();
     __nv_bfloat16* out = a.out + ((size_t)AZG_NET_FRONT + (size_t)b * 256) * CT;
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
       const int qi = warp * 32 + i;
-      const uint32_t code = s_code[qi];
+      const uint32_t code = s_code[sub][qi];
       // pad rows / columns are not written: the buffers are zeroed at creation and every writer (this kernel, the
       // trunk epilogue) keeps the pad positions zero, so they still are (12 % fewer bytes to HBM)
       if (code == 0xffffffffu) continue;
@@ -205,7 +211,7 @@ static int stem_launch_t(const StemArgs& a, int n_sm, cudaStream_t stream) {
   int grid = n_sm * (C == 64 ? 4 : 2) / (C / CB);
   if (grid > a.max_boards) grid = a.max_boards;
   if (grid < 1) grid = 1;
-  stem_kernel<C><<<dim3(grid, C / CB), 256, smem, stream>>>(a);
+  stem_kernel<C><<<dim3(grid, C / CB), 512, smem, stream>>>(a);
   return azg_check_launch("stem_kernel");
 }
 

@@ -180,3 +180,19 @@ def test_outputs_do_not_depend_on_batch_shape():
     one_p, one_v = eng.forward(X[5:6])
     assert torch.equal(one_p[0], small_p[5]) and torch.equal(one_v[0], small_v[5])
     eng.close()
+
+
+@pytest.mark.parametrize("ch", [64, 256])
+def test_network_without_residual_blocks(ch):
+    """n_res_blocks = 0: stem -> unfused 1x1 head convolutions (head1_kernel) -> heads GEMM; the only path
+    on which 64/128-channel networks use the unfused head kernel."""
+    sd, eng = build(0, ch, seed=4, max_batch=64)
+    X = positions(48, 21)
+    with torch.no_grad():
+        lo, v_ref = onet.forward(sd, torch.from_numpy(X))
+        p_ref = torch.softmax(lo, dim=1).numpy()
+    probs, values = eng.forward(torch.from_numpy(X).cuda())
+    kl = onet.policy_kl(p_ref, probs.cpu().numpy())
+    dv = np.abs(values.cpu().numpy() - v_ref.numpy())
+    assert kl.max() < 2e-2 and dv.max() < 0.1, (kl.max(), dv.max())
+    eng.close()

@@ -57,7 +57,7 @@ struct Cfg {
   static constexpr int NACC = C == 256 ? 2 : 4;
   static constexpr int TMEM_COLS = NACC * C;              // 256 or 512 columns (a power of two)
   static constexpr int STAGES = MODE == 0 ? (C == 128 ? 4 : 6) : 3;   // activation tiles in flight
-  static constexpr int EPI = (MODE == 1 || MODE == 4) ? 8 * 2048 : 0;                // per-warp epilogue staging tiles (32 rows x 64 B)
+  static constexpr int EPI = (MODE == 1 || MODE == 4 || MODE == 5) ? 8 * 2048 : 0;                // per-warp epilogue staging tiles (32 rows x 64 B)
   static constexpr int SMEM = 1024 + BBYTES + STAGES * Stage<MODE>::PITCH + EPI + 512;
 };
 
@@ -282,8 +282,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     // both bank-conflict free and the layout of a SWIZZLE_64B TMA box): residual rows are read with
     // coalesced 16-byte loads (8 rows x 64 B per instruction) and transposed through the tile, results
     // leave by one TMA store per tile.  MODE 0 keeps the direct row-per-thread accesses.
-    constexpr bool STAGED = MODE == 1 || MODE == 4;
-    constexpr bool TMA_OUT = MODE == 1;
+    // MODE 5: results staged + TMA store as in MODE 1, but the residual comes straight from global memory in the
+    // accumulator's row-per-thread layout (256-bit loads, one full sector per lane): no shared-memory round trip
+    // for it - on residual layers the shared memory is the busiest unit.
+    constexpr bool STAGED = MODE == 1 || MODE == 4 || MODE == 5;
+    constexpr bool STAGED_RES = MODE == 1 || MODE == 4;
+    constexpr bool TMA_OUT = MODE == 1 || MODE == 5;
     constexpr int NCHUNK = NCH / 32;
     const uint32_t tile = ptx::smem_u32(sEpi) + (uint32_t)(warp - 2) * 2048u;
     const uint32_t own = tile + (uint32_t)lane * 64u;                      // this thread's row in the tile
@@ -296,10 +300,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       __nv_bfloat16* orow = p.out ? p.out + grow * C : nullptr;
       const bool has_res = p.residual != nullptr && working;
       // the residual is fetched while the MMAs of this board are still running
-      uint4 rc[STAGED ? NCHUNK * 4 : 1];
-      uint32_t res[STAGED ? 16 : NCH / 2];
+      uint4 rc[STAGED_RES ? NCHUNK * 4 : 1];
+      uint32_t res[STAGED_RES ? 16 : NCH / 2];
       if (has_res) {
-        if constexpr (STAGED) {
+        if constexpr (STAGED_RES) {
 #pragma unroll
           for (int c = 0; c < NCHUNK; ++c)
 #pragma unroll
@@ -330,11 +334,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
               __syncwarp();
             }
             if (detail) { t_wr += clock64() - tp; tp = clock64(); }
-            if (has_res) {
+            if (STAGED_RES && has_res) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int r = 8 * i + crow;
-                ptx::sts128(tile + (uint32_t)r * 64u + (uint32_t)((cunit ^ ((r >> 1) & 3)) * 16), rc[c * 4 + i]);
+                ptx::sts128(tile + (uint32_t)r * 64u + (uint32_t)((cunit ^ ((r >> 1) & 3)) * 16), rc[STAGED_RES ? c * 4 + i : 0]);
               }
               __syncwarp();
 #pragma unroll
@@ -358,7 +362,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
               float y0 = __uint_as_float(v[2 * h]) + shift.v[decltype(SHOFF)::value + cc + 2 * h];
               float y1 = __uint_as_float(v[2 * h + 1]) + shift.v[decltype(SHOFF)::value + cc + 2 * h + 1];
               if constexpr (decltype(RES)::value) {
-                const uint32_t rw = STAGED ? res[h] : res[(cc / 2 + h) % (STAGED ? 16 : NCH / 2)];
+                const uint32_t rw = STAGED_RES ? res[h] : res[(cc / 2 + h) % (STAGED_RES ? 16 : NCH / 2)];
                 y0 += __uint_as_float(rw << 16);
                 y1 += __uint_as_float(rw & 0xffff0000u);
               }
@@ -498,6 +502,7 @@ int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtenso
     if (mode == 1) return launch_conv_heads<128, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 3) return launch_conv_heads<128, 3>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 4) return launch_conv_heads<128, 4>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (mode == 5) return launch_conv_heads<128, 5>(tm_act, tm_w, tm_out, args, n_sm, stream);
     return azg_fail(AZG_E_ARG, "conv3x3: unknown staging mode");
   }
   if (C == 64) {

@@ -146,7 +146,8 @@ extern "C" int azg_net_create(int device, int n_blocks, int channels, int max_ba
     // 64 channels: single copy + direct stores (3) - the short N = 64 MMAs leave no time for the staging
     // round trip (5.91 M vs 5.41 M sims/s on the 3x64 net)
     n->conv_mode = m ? atoi(m) : (channels == 64 ? 3 : 1);
-    if (n->conv_mode != 0 && n->conv_mode != 1 && n->conv_mode != 3 && n->conv_mode != 4) n->conv_mode = channels == 64 ? 3 : 1;
+    if (n->conv_mode != 0 && n->conv_mode != 1 && n->conv_mode != 3 && n->conv_mode != 4 && !(n->conv_mode == 5 && channels == 128))
+      n->conv_mode = channels == 64 ? 3 : 1;
     if (channels == 256 && n->conv_mode == 0) n->conv_mode = 1;      // the streaming-weights kernel needs the single-copy layout
   }
   for (int i = 0; i < 3; ++i)

@@ -329,7 +329,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * C + ch), v);
           if constexpr (STAGED) {
             long long tp = detail ? clock64() : 0;
-            if (TMA_OUT && p.out) {            // the previous TMA store must have finished reading the tile
+            if (TMA_OUT && STAGED_RES && p.out) {   // the previous TMA store must have finished reading the tile
               if (lane == 0) ptx::bulk_wait_read0();
               __syncwarp();
             }
@@ -386,6 +386,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
           }
           if (p.out) {
             if constexpr (STAGED) {
+              if constexpr (TMA_OUT && !STAGED_RES) {   // MODE 5: the tile is first touched here, after the arithmetic,
+                if (lane == 0) ptx::bulk_wait_read0();  // so the previous store's read-out has had that long to finish
+                __syncwarp();
+              }
 #pragma unroll
               for (int u = 0; u < 4; ++u)
                 ptx::sts128(own + (uint32_t)(((uint32_t)u ^ own_sw) * 16u),

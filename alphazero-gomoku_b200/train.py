@@ -185,27 +185,50 @@ def play_game_and_collect(mcts: MCTS, game, temp_fn, max_moves=225, use_symmetri
 
 
 # ------------------------------------------------------------------ evaluation arena (train.py:418-486)
+def draw_first_stones(n_games: int, board_size: int = 15) -> np.ndarray:
+    """The arena's opening stones, one per game: uniform over the central 9x9, drawn from ``random`` in the
+    reference's order (row, then column; train.py:431-434)."""
+    center, radius = board_size // 2, 4
+    cells = np.zeros(n_games, np.int32)
+    for i in range(n_games):
+        r, c = random.randint(center - radius, center + radius), random.randint(center - radius, center + radius)
+        cells[i] = r * board_size + c
+    return cells
+
+
 def evaluate_models(model_new: PyTorchModel, model_best: PyTorchModel, game_name: str, n_games: int = 20,
-                    n_simulations: int = 100, cpuct: float = 1.0) -> Tuple[int, float, int]:
+                    n_simulations: int = 100, cpuct: float = 1.0, *, first_stones: Optional[np.ndarray] = None,
+                    first_game: int = 0) -> Tuple[int, float, int]:
     """Same protocol as the reference - random first stone in the central 9x9, the new model starts the
     even games, argmax play without noise, one search tree per (model, game) kept for the whole game -
-    with all ``n_games`` games advancing in lock step on two batched engines (one per model)."""
+    with all ``n_games`` games advancing in lock step on two batched engines (one per model).
+    ``first_stones`` / ``first_game`` let a caller play a slice of a larger match (the data-parallel arena):
+    the opening cells of this slice and the match index of its first game (which decides who starts)."""
     from .engine import SearchEngine
     dev = torch.device(model_new.device if str(model_new.device) != "cuda" else f"cuda:{torch.cuda.current_device()}")
     G = n_games
-    center, radius = model_new.board_size // 2, 4
+    if first_stones is None:
+        first_stones = draw_first_stones(G, model_new.board_size)
+    if G == 0:
+        return 0, 0.0, 0
+    limit = min(model_new._ensure_engine().max_batch, model_best._ensure_engine().max_batch) // 32 // 2 * 2
+    if G > limit:                # more games than one leaf batch of the models' evaluators holds: play them in even-sized groups
+        wins = draws = 0
+        for first in range(0, G, limit):
+            m = min(limit, G - first)
+            w, _, d = evaluate_models(model_new, model_best, game_name, m, n_simulations, cpuct,
+                                      first_stones=first_stones[first:first + m], first_game=first_game + first)
+            wins, draws = wins + w, draws + d
+        return wins, wins / float(G), draws
     boards = np.zeros((G, 225), np.int8)
-    lasts = np.zeros(G, np.int32)
-    for i in range(G):
-        r, c = random.randint(center - radius, center + radius), random.randint(center - radius, center + radius)
-        boards[i, r * 15 + c] = 1
-        lasts[i] = r * 15 + c
+    lasts = np.asarray(first_stones, np.int32).copy()
+    boards[np.arange(G), lasts] = 1
     engines = [SearchEngine(0, G, cpuct=cpuct, queue_len=32, node_capacity=max(4096, 3 * n_simulations), noise=False, device=dev)
                for _ in range(2)]                                     # 0: new model, 1: best model
     nets = [model_new._ensure_engine(), model_best._ensure_engine()]
     rules = engines[0].rules
     pos = rules.pack(boards, np.full(G, 2, np.int32), lasts, np.zeros((G, 2), np.int32), np.ones(G, np.int32))
-    new_starts = (torch.arange(G, device=dev) % 2 == 0)
+    new_starts = ((torch.arange(G, device=dev) + first_game) % 2 == 0)
     alive = torch.ones(G, dtype=torch.bool, device=dev)
     status = torch.zeros(G, dtype=torch.int32, device=dev)
     probs = torch.empty((G * 32, 225), dtype=torch.float32, device=dev)
@@ -242,6 +265,36 @@ def evaluate_models(model_new: PyTorchModel, model_best: PyTorchModel, game_name
     draws = int((winner == 0).sum())
     new_wins = int((((winner == 1) & starts) | ((winner == 2) & ~starts)).sum())
     return new_wins, new_wins / float(n_games), draws
+
+
+def evaluate_models_dp(model_new: PyTorchModel, model_best: PyTorchModel, game_name: str, n_games: int = 20,
+                       n_simulations: int = 100, cpuct: float = 1.0) -> Tuple[int, float, int]:
+    """The arena sharded over the ranks of an initialised process group (the reference's process-pool
+    evaluation, train.py:492-569): rank 0 draws the opening stones, every rank plays a contiguous slice of the
+    match on its own GPU with its own replica of both models, wins and draws are summed with one all-reduce.
+    The result does not depend on the number of ranks.  Without a process group: ``evaluate_models``."""
+    world, rank = _world()
+    if world == 1:
+        return evaluate_models(model_new, model_best, game_name, n_games, n_simulations, cpuct)
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}") if dist.get_backend() == "nccl" else torch.device("cpu")
+    stones = torch.zeros(n_games, dtype=torch.int32, device=dev)
+    if rank == 0:
+        stones.copy_(torch.from_numpy(draw_first_stones(n_games, model_new.board_size)))
+    dist.broadcast(stones, 0)
+    lo, hi = shard_bounds(n_games, world, rank)
+    wins, _, draws = evaluate_models(model_new, model_best, game_name, hi - lo, n_simulations, cpuct,
+                                     first_stones=stones[lo:hi].cpu().numpy(), first_game=lo)
+    tally = torch.tensor([wins, draws], dtype=torch.int64, device=dev)
+    dist.all_reduce(tally)
+    wins, draws = int(tally[0].item()), int(tally[1].item())
+    return wins, wins / float(n_games), draws
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced [lo, hi) slice of n items for ``rank``."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
 
 
 def evaluate_models_mp(model_new: PyTorchModel, model_best: PyTorchModel, board_size: int, action_size: int, n_games: int,
@@ -412,13 +465,16 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
                 print(f"[train] epoch {ep + 1}/{epochs_per_iter} mean loss {tot / n_batches:.4f}")
         # ---- evaluation and accept / reject (train.py:768-827), rank 0 decides
         accept = torch.zeros(1, dtype=torch.int32, device=dev)
+        # every rank plays its slice of the match (collective inside: all ranks must call it)
+        try:
+            new_wins, win_rate, draws = evaluate_models_dp(model_candidate, model_best, game_name, n_games=eval_games,
+                                                           n_simulations=eval_mcts_simulations, cpuct=cpuct)
+        except Exception as e:          # single process: the reference prints and goes on with win_rate 0 (train.py:783-786)
+            if world > 1:
+                raise                   # a rank that skipped the collectives would hang the others
+            print(f"[eval] failed: {e}")
+            new_wins, win_rate, draws = 0, 0.0, 0
         if rank == 0:
-            try:
-                new_wins, win_rate, draws = evaluate_models(model_candidate, model_best, game_name, n_games=eval_games,
-                                                            n_simulations=eval_mcts_simulations, cpuct=cpuct)
-            except Exception as e:      # the reference prints and continues with win_rate 0
-                print(f"[eval] failed: {e}")
-                new_wins, win_rate, draws = 0, 0.0, 0
             print(f"[eval] new model wins {new_wins}/{eval_games} (draws {draws}) win rate {win_rate:.3f}")
             accept[0] = int(win_rate >= win_rate_threshold)
         if world > 1:

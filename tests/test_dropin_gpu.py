@@ -98,6 +98,12 @@ def test_batched_arena_equals_game_by_game():
     serial = tr.evaluate_models_serial(a, b, "gomoku", n_games=6, n_simulations=40, cpuct=1.0)
     assert batched == serial, (batched, serial)
     assert 0 <= batched[0] + batched[2] <= 6
+    # the data-parallel arena plays contiguous slices of the same match on different ranks: slices must add up
+    random.seed(5)
+    stones = tr.draw_first_stones(6)
+    parts = [tr.evaluate_models(a, b, "gomoku", hi - lo, 40, 1.0, first_stones=stones[lo:hi], first_game=lo)
+             for lo, hi in (tr.shard_bounds(6, 4, r) for r in range(4))]
+    assert sum(p[0] for p in parts) == batched[0] and sum(p[2] for p in parts) == batched[2]
 
 
 @pytest.mark.parametrize("noise", [False, True])

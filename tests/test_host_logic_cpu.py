@@ -130,3 +130,14 @@ def test_public_surface_matches_reference_fixture():
             assert hasattr(getattr(train, cls_name), member), f"train.{cls_name}.{member} missing"
             if isinstance(ref_params, list):
                 check_params(f"train.{cls_name}.{member}", getattr(getattr(train, cls_name), member), ref_params)
+
+
+def test_shard_bounds_partition():
+    from alphazero_gomoku_b200.train import shard_bounds
+    for n in (0, 1, 5, 12, 13, 40):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_bounds(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1

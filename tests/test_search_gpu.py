@@ -191,3 +191,63 @@ def test_tree_is_dropped_instead_of_overflowing():
         eng.advance(torch.tensor([a], dtype=torch.int32).cuda(), gc=True, reserve=reserve)
     assert eng.stats()["dropped_trees"] >= 1 and eng.stats()["games_in_error"] == 0
     eng.close()
+
+
+@pytest.mark.parametrize("seed", list(range(10)))     # 16 seeds verified once (109 s); ten kept for the suite
+def test_random_configurations_vs_oracle(seed):
+    """Randomised differential test: rule, simulation count, queue length, cpuct, prior model, noise on/off (float64
+    root path), openings and two consecutive moves with tree reuse + GC are drawn at random; 8 concurrent games
+    per configuration against one oracle search per game."""
+    import alphazero_gomoku_b200 as m
+    rng = np.random.default_rng(1000 + seed)
+    rule = int(rng.integers(0, 2))
+    n_sims = int(rng.choice([1, 7, 31, 33, 64, 100, 130]))
+    queue = int(rng.choice([1, 2, 5, 8, 16, 32, 48]))
+    cpuct = float(rng.choice([0.5, 1.0, 1.2, 2.5, 4.0]))
+    model_name = str(rng.choice(sorted(fakes.BY_NAME)))
+    noise = bool(rng.integers(0, 2))
+    alpha, eps, noise_plies = float(rng.choice([0.05, 0.3])), float(rng.choice([0.03, 0.25])), int(rng.choice([0, 4, 40]))
+    G = 8
+    # a queue of 1 flushes at every new node and the simulation goes on below it: one simulation then adds a whole
+    # line to the end of the game (~50 nodes), so the slabs are sized for that
+    eng = m.SearchEngine(rule, G, cpuct=cpuct, queue_len=queue, node_capacity=16384, noise=noise, alpha=alpha, eps=eps,
+                         noise_plies=noise_plies)
+    starts = []
+    for g in range(G):
+        p = orules.Position(rule)
+        for _ in range(int(rng.integers(0, 24))):
+            e = np.flatnonzero(p.cells == 0)
+            q = p.copy()
+            orules.play(q, int(e[int(rng.integers(0, len(e)))]))
+            if orules.game_over(q):
+                break
+            p = q
+        starts.append(p)
+    pos = eng.rules.pack(np.stack([p.cells for p in starts]), [p.player for p in starts], [p.last for p in starts],
+                         [p.caps for p in starts], [p.plies for p in starts])
+    eng.set_roots(pos)
+    model = fakes.BY_NAME[model_name]()
+    ev = lambda planes: torch.from_numpy(model.predict(planes.cpu().numpy())[0]).cuda()
+    draws = {}
+    searches = [Search(rule, n_sims, fakes.BY_NAME[model_name](), cpuct=cpuct, queue_len=queue, alpha=alpha, eps=eps,
+                       noise_plies=noise_plies, noise=noise, noise_fn=(lambda n, g=g: draws[g])) for g in range(G)]
+    tag = (seed, rule, n_sims, queue, cpuct, model_name, noise, noise_plies)
+    for move in range(2):
+        d = rng.dirichlet([alpha] * 225, size=G)                        # this run's noise row of every game
+        for g in range(G):
+            draws[g] = d[g]
+        plies = torch.tensor([p.plies for p in starts], dtype=torch.int32)
+        pi, visits = eng.run(n_sims, ev, plies=plies, noise=torch.from_numpy(d).cuda() if noise else None)
+        pi, visits = pi.cpu().numpy(), visits.cpu().numpy()
+        acts = np.zeros(G, np.int32)
+        for g in range(G):
+            want = searches[g].run(starts[g], starts[g].plies)
+            assert np.array_equal(visits[g], searches[g].Nv[starts[g].key()].astype(np.int32)), (tag, g, move)
+            assert np.array_equal(pi[g], want), (tag, g, move)
+            acts[g] = int(np.argmax(want))
+            orules.play(starts[g], int(acts[g]))
+        eng.advance(torch.from_numpy(acts).cuda(), gc=True)
+        if any(orules.game_over(p) for p in starts):
+            break
+    assert eng.stats()["games_in_error"] == 0
+    eng.close()

@@ -172,7 +172,9 @@ int azg_selfplay_finish(azg_engine* e, const int32_t* status, int max_moves, int
 /* ------------------------------------------------------------------ leaf evaluator (policy/value ResNet)
  * Replaces AlphaZeroNet.forward + PyTorchModel.predict (network.py:85-117, 168-183): stem conv,
  * n_blocks residual blocks of two 3x3 convs (tcgen05 implicit GEMM, bf16 in / fp32 accumulate,
- * eval-mode BatchNorm folded into the epilogue), fused policy / value heads. */
+ * eval-mode BatchNorm folded into the epilogue), the 1x1 head convolutions fused into the last layer, the
+ * dense head layers as tcgen05 TF32 GEMMs with softmax / tanh in their epilogue.  Tolerance against the fp32
+ * reference forward is stated and tested in tests/test_net_gpu.py. */
 typedef struct azg_net azg_net;
 #define AZG_NET_MAX_LAYERS 80
 

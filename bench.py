@@ -53,7 +53,7 @@ def parse():
                          "the per-launch trunk timing is then unavailable (events are not recorded inside the graph)")
     ap.add_argument("--pipeline", type=int, default=1, choices=[1, 2],
                     help="game groups per GPU: 2 overlaps one group's tree walk with the other group's leaf evaluation "
-                         "(+1.6 %% sims/s measured; the per-launch CUDA-event timing of the trunk kernel, and with it the "
+                         "(+1.6 %% sims/s when first measured, -0.6 %% with the final kernels; the per-launch CUDA-event timing of the trunk kernel, and with it the "
                          "roofline block, is only meaningful with 1 because the two groups' event brackets overlap)")
     return ap.parse_args()
 

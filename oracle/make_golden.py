@@ -444,12 +444,202 @@ def build_api():
     print("api surface:", {k: len(v) for k, v in api.items()})
 
 
+# --------------------------------------------------------------------------- whole self-play game (a17)
+def _pack_rows(examples):
+    """(planes, pi, z) tuples -> (planes as packed bits uint8[n, 85], pi f32[n,225], z f32[n])."""
+    st = np.stack([e[0] for e in examples]).astype(np.float32)
+    assert ((st == 0) | (st == 1)).all()
+    bits = np.packbits(st.reshape(len(examples), -1).astype(np.uint8), axis=1)
+    return bits, np.stack([e[1] for e in examples]).astype(np.float32), np.array([e[2] for e in examples], dtype=np.float32)
+
+
+def build_game():
+    """train.py:360-412 ``play_game_and_collect`` run by the reference with injected priors: whole games,
+    every example row (planes, pi, z) in order.  Cases: T = 0 without noise (Gomoku, Pente by duck typing,
+    a max_moves cut-off) and the reference's temperature schedule with root noise, numpy seeded."""
+    import train as ref_train
+    from oracle import selfplay
+    out = {}
+    cases = [("g_t0", rules.GOMOKU, "hashed", 64, 225, None, True), ("p_t0", rules.PENTE, "spiky", 48, 225, None, True),
+             ("g_cut", rules.GOMOKU, "hashed", 40, 7, None, False), ("g_temp_noise", rules.GOMOKU, "hashed", 96, 225, 8, True)]
+    for name, rule, model, n_sims, max_moves, thr, syms in cases:
+        noise = thr is not None
+        temp_fn = (lambda mn: 0.0) if thr is None else (lambda mn, thr=thr: max(0.0, 1.0 - mn / thr))
+        kw = dict(cpuct=1.0, dirichlet_alpha=0.3, epsilon=0.25, apply_dirichlet_n_first_moves=6, add_dirichlet_noise=noise)
+        ref = MCTS(REF_GAME[rule], n_sims, fakes.BY_NAME[model](), **kw)
+        g = REF_GAME[rule](15)
+        np.random.seed(4242)
+        ex_ref, win_ref = ref_train.play_game_and_collect(ref, g, temp_fn, max_moves=max_moves, use_symmetries=syms)
+        orc = Search(rule, n_sims, fakes.BY_NAME[model](), cpuct=1.0, queue_len=32, alpha=0.3, eps=0.25, noise_plies=6, noise=noise)
+        np.random.seed(4242)
+        ex_orc, win_orc = selfplay.play_one(orc, rules.Position(rule), temp_fn, max_plies=max_moves, expand=syms)
+        assert win_ref == win_orc and len(ex_ref) == len(ex_orc)
+        for (a, b, c), (d, e, f) in zip(ex_ref, ex_orc):
+            assert a.dtype == np.float32 and b.dtype == np.float32
+            assert np.array_equal(a, d) and np.array_equal(b, e) and c == f
+        bits, pis, zs = _pack_rows(ex_ref)
+        out[f"{name}/planes_bits"], out[f"{name}/pi"], out[f"{name}/z"] = bits, pis, zs
+        out[f"{name}/moves"] = np.array([r * 15 + c for r, c in g.move_history], dtype=np.int16)
+        out[f"{name}/cfg"] = np.array([rule, n_sims, max_moves, -1 if thr is None else thr, int(syms), int(noise), win_ref], dtype=np.int64)
+        out[f"{name}/model"] = np.array([model])
+        print(f"  game {name}: {len(g.move_history)} plies, winner {win_ref}, {len(ex_ref)} rows")
+    out["names"] = np.array([c[0] for c in cases])
+    out["seed"] = np.array([4242])
+    np.savez_compressed(os.path.join(OUT, "selfplay_games.npz"), **out)
+
+
+# --------------------------------------------------------------------------- evaluation arena (f2)
+class _ArenaFake:
+    """A fake evaluator with the one attribute evaluate_models reads from a model (train.py:430)."""
+
+    def __init__(self, name):
+        self.inner = fakes.BY_NAME[name]()
+        self.board_size = 15
+
+    def predict(self, X):
+        return self.inner.predict(X)
+
+
+def build_arena():
+    """train.py:418-486 ``evaluate_models`` run by the reference between two injected-prior models:
+    result tuple plus the transcript (every move of every game), captured from outside by giving the
+    reference's module a Gomoku subclass that logs ``do_move``."""
+    import random
+    import train as ref_train
+    games = []
+
+    class Logged(Gomoku):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self._top = True
+            games.append([])
+            self._log = games[-1]
+
+        def clone(self):
+            c = super().clone()
+            c._top = False
+            return c
+
+        def do_move(self, mv):
+            ok = super().do_move(mv)
+            if getattr(self, "_top", False) and ok:
+                self._log.append(mv[0] * 15 + mv[1])
+            return ok
+
+    out = {}
+    saved = ref_train.GameClass
+    ref_train.GameClass = Logged
+    try:
+        for name, a, b, n_games, n_sims, cpuct in (("hashed_vs_spiky", "hashed", "spiky", 6, 48, 1.0),
+                                                    ("spiky_vs_hashed", "spiky", "hashed", 5, 64, 1.5)):
+            games.clear()
+            random.seed(77)
+            res = ref_train.evaluate_models(_ArenaFake(a), _ArenaFake(b), "gomoku", n_games=n_games, n_simulations=n_sims, cpuct=cpuct)
+            # evaluate_models builds its MCTS with game_class=GameClass: instances made inside the search count too
+            tops = [g for g in games if len(g) > 0][:n_games]
+            assert len(tops) == n_games
+            L = max(len(g) for g in tops)
+            moves = np.full((n_games, L), -1, dtype=np.int16)
+            for i, g in enumerate(tops):
+                moves[i, :len(g)] = g
+            out[f"{name}/moves"] = moves
+            out[f"{name}/result"] = np.array([res[0], res[2]], dtype=np.int64)
+            out[f"{name}/win_rate"] = np.array([res[1]])
+            out[f"{name}/cfg"] = np.array([n_games, n_sims], dtype=np.int64)
+            out[f"{name}/cpuct"] = np.array([cpuct])
+            out[f"{name}/models"] = np.array([a, b])
+            print(f"  arena {name}: new wins {res[0]}, draws {res[2]}, game lengths {[len(g) for g in tops]}")
+    finally:
+        ref_train.GameClass = saved
+    out["names"] = np.array(["hashed_vs_spiky", "spiky_vs_hashed"])
+    out["seed"] = np.array([77])
+    np.savez_compressed(os.path.join(OUT, "arena_transcripts.npz"), **out)
+
+
+# --------------------------------------------------------------------------- train_batch (f1) + formats (f3)
+def _train_data(n, seed):
+    """n training rows shaped like self-play output: positions from random legal playouts, a smooth
+    target distribution over the empties, z in {-1, 0, 1}."""
+    rng = np.random.default_rng(seed)
+    X, P, Z = [], [], []
+    for _ in range(n):
+        pos = rules.Position(rules.GOMOKU)
+        for _ in range(int(rng.integers(0, 60))):
+            e = np.flatnonzero(pos.cells == 0)
+            rules.play(pos, int(e[int(rng.integers(0, len(e)))]))
+        X.append(rules.encode(pos))
+        w = rng.random(225) ** 4 * (pos.cells == 0)
+        P.append((w / w.sum()).astype(np.float32))
+        Z.append(float(rng.integers(-1, 2)))
+    return np.stack(X).astype(np.float32), np.stack(P), np.array(Z, dtype=np.float32).reshape(-1, 1)
+
+
+def build_train():
+    """network.py:199-235 ``train_batch`` run by the reference (fp32, CPU): three Adam steps on one seeded
+    batch for a 2x64 and a 6x128 net (losses; the 2x64 model is then written with the reference's own
+    ``save`` so weights, BatchNorm statistics and Adam moments after the steps are the fixture), and a
+    100-step loss curve over a fixed 256-row data set.  Also the format fixtures: a seed-0 3x64 checkpoint
+    (``PyTorchModel.save``, network.py:240-248) and a replay-buffer pickle (train.py:302-320)."""
+    import torch
+    import network as ref_net
+    import train as ref_train
+    torch.set_num_threads(4)
+    out = {}
+    X, P, Z = _train_data(32, 101)
+    out["batch/planes_bits"] = np.packbits(X.reshape(32, -1).astype(np.uint8), axis=1)
+    out["batch/pi"], out["batch/z"] = P, Z
+    for tag, blocks, ch in (("2x64", 2, 64), ("6x128", 6, 128)):
+        torch.manual_seed(0)
+        m = ref_net.PyTorchModel(board_size=15, n_res_blocks=blocks, channels=ch, device="cpu")
+        before = {k: v.clone() for k, v in m.net.state_dict().items()}
+        losses = [m.train_batch(X, P, Z, epochs=1) for _ in range(3)]
+        out[f"{tag}/losses"] = np.array([[l["policy_loss"], l["value_loss"], l["total_loss"]] for l in losses])
+        after = m.net.state_dict()
+        names = sorted(k for k, v in after.items() if v.dtype.is_floating_point)
+        out[f"{tag}/names"] = np.array(names)
+        out[f"{tag}/delta_l2"] = np.array([float((after[k].double() - before[k].double()).norm()) for k in names])
+        out[f"{tag}/after_sum"] = np.array([float(after[k].double().sum()) for k in names])
+        probs, values = m.predict(X[:8])          # eval-mode forward with the updated running statistics
+        out[f"{tag}/probs_after"], out[f"{tag}/values_after"] = probs, values
+        if tag == "2x64":
+            m.save(os.path.join(OUT, "ref_train_2x64_after3.pt"))
+        print(f"  train {tag}: losses {[round(l['total_loss'], 4) for l in losses]}")
+    # 100-step curve, 2x64, fixed data set of 256 rows, batches of 32 by a seeded permutation stream
+    DX, DP, DZ = _train_data(256, 202)
+    out["curve/planes_bits"] = np.packbits(DX.reshape(256, -1).astype(np.uint8), axis=1)
+    out["curve/pi"], out["curve/z"] = DP, DZ
+    rng = np.random.default_rng(303)
+    idx = np.stack([rng.choice(256, 32, replace=False) for _ in range(100)])
+    out["curve/idx"] = idx.astype(np.int16)
+    torch.manual_seed(0)
+    m = ref_net.PyTorchModel(board_size=15, n_res_blocks=2, channels=64, device="cpu")
+    curve = []
+    for i in range(100):
+        l = m.train_batch(DX[idx[i]], DP[idx[i]], DZ[idx[i]], epochs=1)
+        curve.append([l["policy_loss"], l["value_loss"], l["total_loss"]])
+    out["curve/losses"] = np.array(curve)
+    print(f"  curve: total loss {curve[0][2]:.4f} -> {curve[-1][2]:.4f}")
+    np.savez_compressed(os.path.join(OUT, "train_steps.npz"), **out)
+    # format fixtures written by the reference's own functions
+    torch.manual_seed(0)
+    ref_net.PyTorchModel(board_size=15).save(os.path.join(OUT, "ref_checkpoint_3x64_seed0.pt"))
+    buf = ref_train.ReplayBuffer(capacity=50)
+    ref = MCTS(Gomoku, 24, fakes.Hashed(), add_dirichlet_noise=False)
+    ex, _ = ref_train.play_game_and_collect(ref, Gomoku(15), lambda mn: 0.0, max_moves=5, use_symmetries=True)
+    buf.add(ex)
+    assert len(buf) == 40
+    assert ref_train.save_replay_buffer(buf, os.path.join(OUT, "ref_replay_buffer.pkl"))
+    bits, pis, zs = _pack_rows(ex)
+    np.savez_compressed(os.path.join(OUT, "ref_replay_rows.npz"), planes_bits=bits, pi=pis, z=zs)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["rules", "search", "noise", "misc", "net", "api"]
+    which = sys.argv[1:] or ["rules", "search", "noise", "misc", "net", "api", "game", "arena", "train"]
     for w in which:
         print(f"== {w}")
-        {"rules": build_rules, "search": build_search, "noise": build_noise, "misc": build_misc, "net": build_net, "api": build_api}[w]()
+        {"rules": build_rules, "search": build_search, "noise": build_noise, "misc": build_misc, "net": build_net, "api": build_api,
+         "game": build_game, "arena": build_arena, "train": build_train}[w]()
 
 
 if __name__ == "__main__":

@@ -141,3 +141,34 @@ def test_shard_bounds_partition():
             assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
             sizes = [hi - lo for lo, hi in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_reference_written_files_load():
+    """Files written by the REFERENCE's own save functions (oracle/make_golden.py build_train): the replay
+    pickle (train.py:302-320) through load_replay_buffer, the checkpoint dictionary (network.py:240-248)
+    into this package's parameter container, with the architecture read off the state_dict."""
+    import os
+    from conftest import GOLDEN
+    from alphazero_gomoku_b200 import train as tr
+    import alphazero_gomoku_b200.network as mynet
+    from oracle import net as onet
+    rows = load_golden("ref_replay_rows.npz")
+    buf = tr.load_replay_buffer(os.path.join(GOLDEN, "ref_replay_buffer.pkl"), 50)
+    assert buf is not None and buf.capacity == 50 and len(buf) == 40
+    planes = np.unpackbits(rows["planes_bits"], axis=1)[:, :675].astype(np.float32).reshape(-1, 3, 15, 15)
+    for i, (s, p, zz) in enumerate(buf.buffer):
+        assert s.dtype == np.float32 and np.array_equal(s, planes[i]) and np.array_equal(p, rows["pi"][i]) and zz == rows["z"][i]
+    dev = tr.DeviceReplayBuffer.from_host(buf, "cpu")
+    assert torch.equal(dev.rows[:40, :675], torch.from_numpy(planes.reshape(40, -1)))
+    assert torch.equal(dev.rows[:40, 675:900], torch.from_numpy(rows["pi"])) and torch.equal(dev.rows[:40, 900], torch.from_numpy(rows["z"]))
+    smaller = tr.load_replay_buffer(os.path.join(GOLDEN, "ref_replay_buffer.pkl"), 16)       # deque(maxlen) keeps the newest
+    assert len(smaller) == 16 and np.array_equal(smaller.buffer[0][1], rows["pi"][24])
+    state = torch.load(os.path.join(GOLDEN, "ref_checkpoint_3x64_seed0.pt"), map_location="cpu")
+    assert set(state) == {"net", "opt", "board_size", "action_size"} and state["board_size"] == 15 and state["action_size"] == 225
+    assert mynet.infer_architecture(state["net"]) == (3, 64)
+    net = mynet.AlphaZeroNet(n_res_blocks=3, channels=64)
+    net.load_state_dict(state["net"])                       # strict: same keys and shapes
+    z = load_golden("net_outputs.npz")
+    logits, _ = onet.forward(net.state_dict(), torch.from_numpy(z["X"]))
+    assert np.allclose(logits.numpy(), z["3x64/logits"], rtol=1e-4, atol=1e-4)
+    assert mynet.infer_architecture(torch.load(os.path.join(GOLDEN, "ref_train_2x64_after3.pt"), map_location="cpu")["net"]) == (2, 64)

@@ -106,3 +106,59 @@ def test_net_forward():
     assert np.allclose(logits.numpy(), z["3x64/logits"], rtol=1e-4, atol=1e-4)
     p, v = onet.CpuModel(sd).predict(z["X"])
     assert np.allclose(p, z["3x64/probs"], atol=1e-5) and np.allclose(v, z["3x64/values"], atol=1e-5)
+
+
+def unpack_planes(bits):
+    return np.unpackbits(bits, axis=1)[:, :675].astype(np.float32).reshape(-1, 3, 15, 15)
+
+
+@pytest.mark.parametrize("name", ["g_t0", "p_t0", "g_cut", "g_temp_noise"])
+def test_whole_selfplay_game(name):
+    """oracle.selfplay.play_one == the reference's play_game_and_collect (train.py:360-412), row for row."""
+    z = load_golden("selfplay_games.npz")
+    rule, n_sims, max_moves, thr, syms, noise, winner = (int(v) for v in z[f"{name}/cfg"])
+    temp_fn = (lambda mn: 0.0) if thr < 0 else (lambda mn: max(0.0, 1.0 - mn / thr))
+    s = Search(rule, n_sims, fakes.BY_NAME[str(z[f"{name}/model"][0])](), cpuct=1.0, queue_len=32, alpha=0.3, eps=0.25,
+               noise_plies=6, noise=bool(noise))
+    np.random.seed(int(z["seed"][0]))
+    rows, won = selfplay.play_one(s, rules.Position(rule), temp_fn, max_plies=max_moves, expand=bool(syms))
+    assert won == winner and len(rows) == len(z[f"{name}/z"])
+    assert np.array_equal(np.stack([r[0] for r in rows]), unpack_planes(z[f"{name}/planes_bits"]))
+    assert np.array_equal(np.stack([r[1] for r in rows]), z[f"{name}/pi"])
+    assert np.array_equal(np.array([r[2] for r in rows], dtype=np.float32), z[f"{name}/z"])
+
+
+def test_train_step_oracle_against_reference_steps():
+    """oracle.train.train_step == three reference train_batch steps (network.py:199-235): losses, every
+    updated tensor, BatchNorm running statistics and the Adam moments the reference saved afterwards."""
+    import os
+    import torch
+    from conftest import GOLDEN
+    from oracle import train as otrain
+    import alphazero_gomoku_b200.network as mynet
+    z = load_golden("train_steps.npz")
+    X, P, Z = unpack_planes(z["batch/planes_bits"]), z["batch/pi"], z["batch/z"]
+    torch.set_num_threads(4)
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in mynet.AlphaZeroNet(n_res_blocks=2, channels=64).state_dict().items()}
+    opt = otrain.Adam(sd)
+    got = [otrain.train_step(sd, opt, X, P, Z) for _ in range(3)]
+    want = z["2x64/losses"]
+    for g, w in zip(got, want):
+        assert np.allclose([g["policy_loss"], g["value_loss"], g["total_loss"]], w, rtol=2e-4, atol=2e-5), (g, w)
+    ref = torch.load(os.path.join(GOLDEN, "ref_train_2x64_after3.pt"), map_location="cpu")
+    assert set(ref) == {"net", "opt", "board_size", "action_size"}
+    for k, v in ref["net"].items():
+        if v.dtype.is_floating_point:
+            # Adam normalises the step: a gradient element near zero can land on either side, one lr apart
+            assert torch.allclose(sd[k], v, atol=2.5e-4), (k, float((sd[k] - v).abs().max()))
+            assert float((sd[k] - v).abs().mean()) < 2e-5, k
+        else:
+            assert int(sd[k]) == int(v) == 3, k
+    names = otrain.param_names(sd)
+    for i, k in enumerate(names):
+        st = ref["opt"]["state"][i]
+        assert int(st["step"]) == 3
+        # fp32 summation order of the convolutions differs with the thread count: compare at the tensor's own scale
+        assert torch.allclose(opt.m[k], st["exp_avg"], rtol=1e-3, atol=1e-3 * float(st["exp_avg"].abs().max())), k
+        assert torch.allclose(opt.v[k], st["exp_avg_sq"], rtol=1e-3, atol=1e-3 * float(st["exp_avg_sq"].abs().max())), k

@@ -76,6 +76,7 @@ PROTOTYPES = {
     "azg_search_advance": (_I, [_P, _P, _I, _I, _P]),
     "azg_search_stats": (_I, [_P, _P]),
     "azg_selfplay_enable": (_I, [_P, _I]),
+    "azg_selfplay_set_active": (_I, [_P, _P]),
     "azg_selfplay_noise": (_I, [_P, C.c_uint64, _P]),
     "azg_selfplay_choose": (_I, [_P, _P, C.c_float, C.c_uint64, _P]),
     "azg_selfplay_finish": (_I, [_P, _P, _I, _I, _P, C.c_int64, _P, _P, _P]),

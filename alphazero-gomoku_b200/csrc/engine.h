@@ -10,6 +10,7 @@ struct azg_selfplay_buf {
   int32_t* n_plies = nullptr;     // [G] plies played in the current game
   int32_t* n_done = nullptr;      // [G] games finished so far (part of the RNG counter: streams never repeat)
   int32_t max_plies = 0;
+  const int32_t* active = nullptr; // [G] optional caller-owned mask: slots with 0 are retired (azg_selfplay_set_active)
 };
 
 struct azg_engine {

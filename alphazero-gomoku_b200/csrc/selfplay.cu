@@ -101,6 +101,10 @@ choose_kernel(azg_dev e, azg_selfplay_buf sp, const float* __restrict__ pi, floa
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= e.G) return;
   const int l = lane_id();
+  if (sp.active && sp.active[g] == 0) {          // retired slot: no move, no example, no ply count
+    if (l == 0) actions[g] = -1;
+    return;
+  }
   const azg_ctl* ctl = e.ctl + g;
   const WPos root = wpos_load(&ctl->root);
   const int ply = sp.n_plies[g];
@@ -183,6 +187,10 @@ finish_games_kernel(azg_dev e, azg_selfplay_buf sp, const int32_t* __restrict__ 
   const int g = blockIdx.x;
   if (g >= e.G) return;
   __shared__ long long s_base;
+  if (sp.active && sp.active[g] == 0) {
+    if (threadIdx.x == 0) { done_mask[g] = 0; if (winners) winners[g] = -1; }
+    return;
+  }
   const int st = status[g];
   const int plies = sp.n_plies[g];
   const bool over = (st & 4) != 0 || plies >= max_moves;
@@ -243,6 +251,12 @@ extern "C" int azg_selfplay_enable(azg_engine* e, int max_plies) {
   e->sp.max_plies = max_plies;
   AZG_CUDA(cudaMemset(e->sp.n_plies, 0, (size_t)e->dev.G * 4));
   AZG_CUDA(cudaMemset(e->sp.n_done, 0, (size_t)e->dev.G * 4));
+  return AZG_OK;
+}
+
+extern "C" int azg_selfplay_set_active(azg_engine* e, const int32_t* active) {
+  if (!e) return azg_fail(AZG_E_ARG, "null argument");
+  e->sp.active = active;
   return AZG_OK;
 }
 

@@ -116,6 +116,8 @@ class PyTorchModel:
             raise ValueError("azgomoku_b200 kernels are specialised for the 15x15 board")
         self.board_size = board_size
         self.action_size = action_size if action_size is not None else board_size * board_size
+        if self.action_size != board_size * board_size:
+            raise ValueError("azgomoku_b200 kernels are specialised for action_size == board_size**2 == 225")
         self.device = device or "cuda"
         if not str(self.device).startswith("cuda") or not torch.cuda.is_available():
             raise _lib.AzgError("PyTorchModel needs a CUDA device: azgomoku_b200 has no CPU fallback")
@@ -131,14 +133,30 @@ class PyTorchModel:
         from .nn_engine import NetEngine
         if self._engine is None:
             self._engine = NetEngine(len(self.net.res_blocks), self.net.channels, torch.device(self.device))
-        version = tuple(p._version for p in self.net.parameters()) + tuple(b._version for b in self.net.buffers())
+        # _version catches in-place tensor ops; data_ptr catches `p.data = ...`; writes through `.data` views that
+        # bypass both must call invalidate() (broadcast_model and load do)
+        version = tuple((t._version, t.data_ptr()) for t in list(self.net.parameters()) + list(self.net.buffers()))
         if version != self._packed_version:
             self._engine.load_state_dict(self.net.state_dict())
             self._packed_version = version
         return self._engine
 
-    def predict_device(self, planes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """planes float32[B,3,15,15] on the device -> (probs f32[B,225], values f32[B,1]) on the device."""
+    def invalidate(self) -> None:
+        """Forget the packed bf16 weights: the next predict / search repacks from ``self.net``.  Needed after
+        writes the version counters cannot see (``tensor.data`` views, raw device copies)."""
+        self._packed_version = None
+
+    def predict_device(self, planes: torch.Tensor, validate: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """planes float32[B,3,15,15] on the device -> (probs f32[B,225], values f32[B,1]) on the device.
+        The CUDA stem consumes stone bitboards, so the input must be what ``get_encoded_state`` produces
+        (gomoku.py:130-150): planes 0/1 binary and disjoint, plane 2 all ones.  Anything else raises instead
+        of silently evaluating a different input (one fused device reduction; ``validate=False`` skips it)."""
+        if validate and planes.numel():
+            a, b = planes[:, 0], planes[:, 1]
+            bad = (((a != 0) & (a != 1)) | ((b != 0) & (b != 1)) | ((a != 0) & (b != 0))).any() | (planes[:, 2] != 1).any()
+            if bool(bad):
+                raise ValueError("predict: input is not an encoded board state (planes 0/1 must be binary and disjoint, "
+                                 "plane 2 all ones); the CUDA evaluator has no generic float stem")
         return self._ensure_engine().forward(planes)
 
     def predict(self, encoded_states: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
@@ -192,6 +210,7 @@ class PyTorchModel:
     def load(self, path: str, map_location: Optional[str] = None) -> None:
         state = torch.load(path, map_location=map_location or self.device)
         self.net.load_state_dict(state["net"])
+        self.invalidate()
         opt = state.get("opt")
         if opt is not None:
             try:                                   # optimiser state of another architecture is skipped, as in the reference

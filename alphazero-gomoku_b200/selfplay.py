@@ -18,7 +18,14 @@ from .engine import POS_WORDS, SearchEngine
 from .nn_engine import NetEngine
 
 ROW = 901          # floats per example: planes 3*225, pi 225, z
-TRUNK_FLOPS = {64: 2 * 225 * 9 * 64 * 64, 128: 2 * 225 * 9 * 128 * 128}   # per position per 3x3 layer
+
+
+def trunk_flops(channels: int) -> int:
+    """Algorithmic FLOPs (2 x MAC) of one 3x3 trunk layer on one position (225 real pixels)."""
+    return 2 * 225 * 9 * channels * channels
+
+
+TRUNK_FLOPS = {c: trunk_flops(c) for c in (64, 128, 256)}
 
 
 class SelfPlay:
@@ -26,7 +33,10 @@ class SelfPlay:
                  queue_len: int = 32, node_capacity: int = 8192, noise: bool = True, alpha: float = 0.05,
                  eps: float = 0.15, noise_plies: int = 10, temp_threshold: float = 10.0, max_moves: int = 225,
                  use_symmetries: bool = True, example_capacity: int = 1 << 20, seed: int = 12345, device="cuda:0",
-                 game_base: int = 0):
+                 game_base: int = 0, max_games: int | None = None):
+        """``max_games``: play exactly that many games to completion (train.py:671-694 plays
+        ``games_per_iteration`` full games): finished slots restart only while fewer than ``max_games`` games
+        have been started, afterwards they retire (``active`` mask) - no game is cut off or counted twice."""
         self.device = torch.device(device)
         self.G, self.n_sims, self.temp_threshold, self.max_moves = n_games, n_sims, float(temp_threshold), max_moves
         self.use_symmetries = use_symmetries
@@ -56,6 +66,13 @@ class SelfPlay:
         self.empty_roots = empty
         self.engine.set_roots(empty, clear_tree=True)
         self.draw = 0
+        self.max_games = max_games
+        if max_games is not None:
+            self.active = (torch.arange(n_games, device=dev) < max_games).to(torch.int32)
+            self.started = torch.tensor([min(n_games, max_games)], dtype=torch.int64, device=dev)
+            check(lib.azg_selfplay_set_active(self.engine._h, ptr(self.active)))
+        else:
+            self.active = None
         # counters
         self.total_sims = 0
         self.total_evals = 0
@@ -78,9 +95,26 @@ class SelfPlay:
         return self.engine.result()
 
     # the run in its asynchronous pieces (PipelinedSelfPlay interleaves them for two game groups)
+    def _restart(self):
+        """Restart finished slots from the empty board with a cleared tree (train.py:674-694); with ``max_games``
+        only while games remain to be started - the other finished slots retire.  Device-side, no host sync."""
+        eng = self.engine
+        if self.max_games is None:
+            eng.set_roots(self.empty_roots, mask=self.done, clear_tree=True)
+            return
+        done = self.done != 0
+        restart = done & ((self.started + torch.cumsum(self.done, 0)) <= self.max_games)
+        self.started += restart.sum()
+        self.active.copy_(((self.active != 0) & (~done | restart)).to(torch.int32))
+        eng.set_roots(self.empty_roots, mask=restart.to(torch.int32), clear_tree=True)
+
+    def games_running(self) -> int:
+        """Slots still playing (host sync); always G without ``max_games``."""
+        return self.G if self.active is None else int(self.active.sum().item())
+
     def search_begin(self):
         eng = self.engine
-        eng.begin(self.n_sims)
+        eng.begin(self.n_sims, mask=self.active)
         self._launches = 1
         if self.noise is not None:
             eng._sync_stream()
@@ -123,14 +157,18 @@ class SelfPlay:
         (every kernel reads its work count from device memory), so no host synchronisation is left in
         the ply.  Results are identical to the host-driven loop."""
         q = self.engine.queue_len
-        leaves = self.n_sims + self.n_sims // q + 1
+        if q < 2:
+            raise ValueError("graph mode needs queue_len >= 2 (with a queue of 1 every simulation is its own round)")
+        # every flush parks one simulation that queues a second leaf, so n simulations queue up to n*q/(q-1) leaves
+        leaves = -(-self.n_sims * q // (q - 1)) + 1
         self._graph_rounds = (leaves + q - 1) // q + extra_rounds
         self._graph = None
+        self._graph_plies = 0
 
     def _ply_async(self):
         """Everything of one ply, without host synchronisation (capturable)."""
         eng = self.engine
-        eng.begin(self.n_sims)
+        eng.begin(self.n_sims, mask=self.active)
         if self.noise is not None:
             eng._sync_stream()
             check(lib.azg_selfplay_noise(eng._h, self.draw, ptr(self.noise)))
@@ -140,11 +178,26 @@ class SelfPlay:
             eng.commit(self.probs, self.noise)
         check(lib.azg_search_result(eng._h, ptr(self._pi), ptr(self._visits)))
         check(lib.azg_selfplay_choose(eng._h, ptr(self._pi), C.c_float(self.temp_threshold), self.draw, ptr(self.actions)))
-        reserve = self.n_sims + self.n_sims // eng.queue_len + 8
-        check(lib.azg_search_advance(eng._h, ptr(self.actions), 1, reserve, ptr(self._status)))
+        check(lib.azg_search_advance(eng._h, ptr(self.actions), 1, self._reserve(), ptr(self._status)))
         check(lib.azg_selfplay_finish(eng._h, ptr(self._status), self.max_moves, int(self.use_symmetries), ptr(self.examples),
                                       self.capacity, ptr(self.cursor), ptr(self.done), ptr(self.winners)))
-        check(lib.azg_set_roots(eng._h, ptr(self.empty_roots), ptr(self.done), 1))
+        self._restart()
+
+    def _reserve(self) -> int:
+        """Free nodes a slab needs for another run: one per simulation plus one per flush (see enable_graph)."""
+        q = max(self.engine.queue_len, 2)
+        return -(-self.n_sims * q // (q - 1)) + 8
+
+    GRAPH_CHECK_EVERY = 16
+
+    def _check_graph_run(self):
+        """The replayed graph never looks at the counters: every few plies make sure no run was truncated by the
+        fixed round count and no game hit an engine error (full slab, depth overflow, no float64 prior slot)."""
+        _, n_more, _ = self.engine.read_counters()
+        st = self.engine.stats()
+        if n_more != 0 or st["games_in_error"] != 0:
+            raise RuntimeError(f"graph-mode self-play: {n_more} games still had simulations to run after "
+                               f"{self._graph_rounds} rounds, {st['games_in_error']} games in error (bits {st['error_bits']:#x})")
 
     def _step_graph(self):
         """Captured once, replayed every ply (the RNG streams are keyed on device-side counters)."""
@@ -159,6 +212,9 @@ class SelfPlay:
                 self._ply_async()
             self._graph = g
         self._graph.replay()
+        self._graph_plies += 1
+        if self._graph_plies % self.GRAPH_CHECK_EVERY == 1:
+            self._check_graph_run()
         self.last_pi = self._pi
         self.total_sims += self.G * self.n_sims
         self.total_rounds += self._graph_rounds
@@ -169,10 +225,10 @@ class SelfPlay:
         eng = self.engine
         self.last_pi = pi
         check(lib.azg_selfplay_choose(eng._h, ptr(pi), C.c_float(self.temp_threshold), self.draw, ptr(self.actions)))
-        status = eng.advance(self.actions, gc=True, reserve=self.n_sims + self.n_sims // self.engine.queue_len + 8)
+        status = eng.advance(self.actions, gc=True, reserve=self._reserve())
         check(lib.azg_selfplay_finish(eng._h, ptr(status), self.max_moves, int(self.use_symmetries), ptr(self.examples),
                                       self.capacity, ptr(self.cursor), ptr(self.done), ptr(self.winners)))
-        eng.set_roots(self.empty_roots, mask=self.done, clear_tree=True)
+        self._restart()
         self.total_launches += 4
         return status
 

@@ -198,34 +198,40 @@ def draw_first_stones(n_games: int, board_size: int = 15) -> np.ndarray:
 
 def evaluate_models(model_new: PyTorchModel, model_best: PyTorchModel, game_name: str, n_games: int = 20,
                     n_simulations: int = 100, cpuct: float = 1.0, *, first_stones: Optional[np.ndarray] = None,
-                    first_game: int = 0) -> Tuple[int, float, int]:
+                    first_game: int = 0, transcript: Optional[list] = None) -> Tuple[int, float, int]:
     """Same protocol as the reference - random first stone in the central 9x9, the new model starts the
     even games, argmax play without noise, one search tree per (model, game) kept for the whole game -
     with all ``n_games`` games advancing in lock step on two batched engines (one per model).
     ``first_stones`` / ``first_game`` let a caller play a slice of a larger match (the data-parallel arena):
-    the opening cells of this slice and the match index of its first game (which decides who starts)."""
+    the opening cells of this slice and the match index of its first game (which decides who starts).
+    A model without this package's CUDA evaluator (anything with the reference's ``predict`` protocol, e.g. an
+    injected-prior fake) is evaluated through one host round trip per leaf batch.  ``transcript``, if a list,
+    receives the move list of every game (opening stone first)."""
     from .engine import SearchEngine
-    dev = torch.device(model_new.device if str(model_new.device) != "cuda" else f"cuda:{torch.cuda.current_device()}")
+    dev_name = str(getattr(model_new, "device", "cuda"))
+    dev = torch.device(dev_name if dev_name.startswith("cuda:") else f"cuda:{torch.cuda.current_device()}")
     G = n_games
     if first_stones is None:
         first_stones = draw_first_stones(G, model_new.board_size)
     if G == 0:
         return 0, 0.0, 0
-    limit = min(model_new._ensure_engine().max_batch, model_best._ensure_engine().max_batch) // 32 // 2 * 2
+    nets = [m._ensure_engine() if hasattr(m, "_ensure_engine") else None for m in (model_new, model_best)]      # 0: new model, 1: best model
+    limit = min([n.max_batch for n in nets if n is not None] or [1 << 30]) // 32 // 2 * 2
     if G > limit:                # more games than one leaf batch of the models' evaluators holds: play them in even-sized groups
         wins = draws = 0
         for first in range(0, G, limit):
             m = min(limit, G - first)
             w, _, d = evaluate_models(model_new, model_best, game_name, m, n_simulations, cpuct,
-                                      first_stones=first_stones[first:first + m], first_game=first_game + first)
+                                      first_stones=first_stones[first:first + m], first_game=first_game + first, transcript=transcript)
             wins, draws = wins + w, draws + d
         return wins, wins / float(G), draws
     boards = np.zeros((G, 225), np.int8)
     lasts = np.asarray(first_stones, np.int32).copy()
     boards[np.arange(G), lasts] = 1
     engines = [SearchEngine(0, G, cpuct=cpuct, queue_len=32, node_capacity=max(4096, 3 * n_simulations), noise=False, device=dev)
-               for _ in range(2)]                                     # 0: new model, 1: best model
-    nets = [model_new._ensure_engine(), model_best._ensure_engine()]
+               for _ in range(2)]
+    models = [model_new, model_best]
+    played = [np.asarray(first_stones, np.int32).copy()]
     rules = engines[0].rules
     pos = rules.pack(boards, np.full(G, 2, np.int32), lasts, np.zeros((G, 2), np.int32), np.ones(G, np.int32))
     new_starts = ((torch.arange(G, device=dev) + first_game) % 2 == 0)
@@ -239,7 +245,7 @@ def evaluate_models(model_new: PyTorchModel, model_best: PyTorchModel, game_name
         players = pos[:, 16]
         new_to_move = ((players == 1) & new_starts) | ((players == 2) & ~new_starts)
         action = torch.full((G,), -1, dtype=torch.int32, device=dev)
-        for side, (eng, net) in enumerate(zip(engines, nets)):
+        for side, (eng, net, model) in enumerate(zip(engines, nets, models)):
             mask = alive & (new_to_move if side == 0 else ~new_to_move)
             if not bool(mask.any()):
                 continue
@@ -248,13 +254,19 @@ def evaluate_models(model_new: PyTorchModel, model_best: PyTorchModel, game_name
             eng.begin(n_simulations, mask=mask)
             while True:
                 n_leaves, n_more, _ = eng.fill()
-                if n_leaves > 0:
+                if n_leaves > 0 and net is not None:
                     net.forward_leaves(eng, probs)
+                    eng.commit(probs, None)
+                elif n_leaves > 0:           # the reference's predict protocol on the host (new_mcts_alpha.py:160-161)
+                    p, _ = model.predict(eng.leaf_planes(n_leaves).cpu().numpy())
+                    probs[:n_leaves] = torch.from_numpy(np.ascontiguousarray(np.asarray(p, np.float32).reshape(n_leaves, 225))).to(dev)
                     eng.commit(probs, None)
                 if n_more == 0:
                     break
             pi, _ = eng.result()
             action = torch.where(mask, pi.argmax(dim=1).to(torch.int32), action)
+        if transcript is not None:
+            played.append(action.cpu().numpy())
         st = rules.play(pos, action)
         status = torch.where(alive, st, status)
         alive = alive & ((st & 4) == 0)
@@ -264,6 +276,9 @@ def evaluate_models(model_new: PyTorchModel, model_best: PyTorchModel, game_name
     starts = new_starts.cpu().numpy()
     draws = int((winner == 0).sum())
     new_wins = int((((winner == 1) & starts) | ((winner == 2) & ~starts)).sum())
+    if transcript is not None:
+        moves = np.stack(played, axis=1)
+        transcript.extend([int(a) for a in row if a >= 0] for row in moves)
     return new_wins, new_wins / float(n_games), draws
 
 
@@ -396,8 +411,28 @@ def broadcast_model(model: PyTorchModel, src: int = 0):
     world, _ = _world()
     if world == 1:
         return
-    for t in list(model.net.parameters()) + list(model.net.buffers()):
-        dist.broadcast(t.data, src)
+    with torch.no_grad():
+        for t in list(model.net.parameters()) + list(model.net.buffers()):
+            dist.broadcast(t, src)
+    model.invalidate()
+
+
+def sync_batchnorm_buffers(model: PyTorchModel):
+    """Data-parallel training normalises every rank's micro-batch with its own statistics, so the BatchNorm
+    running statistics drift apart while the parameters stay identical.  Average them over the ranks (each
+    rank saw an equally sized slice of every batch) so that self-play, the arena and the saved checkpoint use
+    one and the same network on every rank."""
+    world, _ = _world()
+    if world == 1:
+        return
+    with torch.no_grad():
+        for name, b in model.net.named_buffers():
+            if b.dtype.is_floating_point:
+                dist.all_reduce(b, op=dist.ReduceOp.SUM)
+                b /= world
+            else:                                   # num_batches_tracked: identical on every rank already
+                dist.broadcast(b, 0)
+    model.invalidate()
 
 
 # ------------------------------------------------------------------ the training loop (train.py:575-842)
@@ -438,15 +473,18 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
                       alpha=dirichlet_alpha, eps=dirichlet_epsilon, noise_plies=dirichlet_n_moves,
                       temp_threshold=float(temp_threshold), max_moves=board_size * board_size,
                       example_capacity=max(my_games, G) * 225 * 8, seed=selfplay_base_seed + it, game_base=rank * G,
-                      node_capacity=max(4096, 4 * n_simulations), device=dev)
+                      node_capacity=max(4096, 4 * n_simulations), device=dev, max_games=my_games)
+        # exactly my_games games are started and every one of them is played to the end (train.py:671-694):
+        # slots restart only while games remain to be started, then retire
         finished = 0
         winners = {0: 0, 1: 0, 2: 0}
-        while finished < my_games:
+        while sp.games_running() > 0:
             sp.step()
             w = sp.winners[sp.done.bool()].cpu().tolist()
             for x in w:
                 winners[int(x)] = winners.get(int(x), 0) + 1
             finished += len(w)
+        assert finished == my_games
         rows = gather_rows(sp.drain_examples())
         sp.close()
         buffer.add_rows(rows)
@@ -463,6 +501,7 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
                 tot += train_batch_dp(model_candidate, states[sl], pis[sl], zs[sl])["total_loss"]
             if rank == 0 and n_batches:
                 print(f"[train] epoch {ep + 1}/{epochs_per_iter} mean loss {tot / n_batches:.4f}")
+        sync_batchnorm_buffers(model_candidate)
         # ---- evaluation and accept / reject (train.py:768-827), rank 0 decides
         accept = torch.zeros(1, dtype=torch.int32, device=dev)
         # every rank plays its slice of the match (collective inside: all ranks must call it)

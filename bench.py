@@ -9,11 +9,13 @@ COMMIT.  Synthetic data: games start from seeded random legal positions of 0..39
 the batch is a steady-state mix of game phases; weights are random-init.
 
     python bench.py --gpus N --steps K --warmup W            # this repository (CUDA engine)
-    python bench.py --impl reference ...                      # the reference's CPU algorithm (oracle port)
+    python bench.py --impl reference ...                      # the reference's own CPU path (oracle/_ref), all host cores
+    python bench.py --soak 150                                # tree-memory soak: 150 plies with respawn, fails on a dropped tree
 
 Prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = the same
 metric through host buffers (boards up, pi/actions/boards down every step), roofline = the
-conv3x3 tcgen05 kernel against the measured bf16 peak, cpu_baseline = the oracle port on one core.
+conv3x3 tcgen05 kernel against the measured bf16 peak, cpu_baseline = the reference's CPU path
+(W worker processes, a bounded sample of the same workload) timed on this box's host cores.
 """
 from __future__ import annotations
 
@@ -51,6 +53,9 @@ def parse():
     ap.add_argument("--graph", action="store_true",
                     help="replay each ply as one CUDA graph (fixed round count, no host synchronisation inside the ply); "
                          "the per-launch trunk timing is then unavailable (events are not recorded inside the graph)")
+    ap.add_argument("--soak", type=int, default=0, metavar="PLIES",
+                    help="instead of the benchmark: play PLIES plies of the configured workload from the empty board with respawn, "
+                         "then print {max_nodes_per_game, dropped_trees, games_finished, ...} and exit 1 if any tree was dropped")
     ap.add_argument("--pipeline", type=int, default=1, choices=[1, 2],
                     help="game groups per GPU: 2 overlaps one group's tree walk with the other group's leaf evaluation "
                          "(+1.6 %% sims/s when first measured, -0.6 %% with the final kernels; the per-launch CUDA-event timing of the trunk kernel, and with it the "
@@ -106,97 +111,186 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------------- CPU legs (oracle)
-def _oracle_model(blocks, channels):
-    import torch
-    from oracle import net as onet
-    import alphazero_gomoku_b200.network as mynet
-    torch.manual_seed(0)
-    return onet.CpuModel(mynet.AlphaZeroNet(n_res_blocks=blocks, channels=channels).state_dict())
-
-
-_WORKER_MODEL = None
-
-
-def _cpu_worker_init(blocks, channels):
-    """Per-process model, created once (the reference's _selfplay_worker_init, train.py:30-59)."""
-    global _WORKER_MODEL
+# ----------------------------------------------------------------------------------------------- CPU legs
+# The reference's own CPU path, in the reference's own parallel scheme (train.py:695-742: spawned worker processes,
+# one torch thread each, a private model per process).  Each worker owns ONE self-play game and advances it by one ply
+# per step - reference ``MCTS.run`` of --sims simulations with tree reuse, temperature sampling, ``do_move``, symmetry
+# expansion - through the reference's unmodified ``play_game_and_collect(max_moves=1)``; finished games restart from
+# the empty board with a cleared tree.  That is exactly one "step" of this repository's own arm (one ply of every
+# game), on W games instead of 2048 per GPU: a bounded sample of the same workload.
+# The code executed is /root/reference byte-compiled into oracle/_ref (oracle/build_ref.py, kind "reference"); if that
+# directory is missing the oracle port runs instead (kind "port").
+def _ref_worker(conn, idx, blocks, channels, rule, sims, seed):
+    import random
     import torch
     torch.set_num_threads(1)
-    _WORKER_MODEL = _oracle_model(blocks, channels)
-
-
-def _cpu_worker(job):
-    """One task of the reference's parallel mode (train.py:62-129): one torch thread, one MCTS.run
-    of `sims` simulations from the empty board with root noise, fresh tree."""
-    blocks, channels, rule, sims, seed = job
-    import torch
-    torch.set_num_threads(1)
-    from oracle import rules
-    from oracle.search import Search
+    from oracle import build_ref
+    kind = "reference" if build_ref.activate() else "port"
     np.random.seed(seed)
-    model = _WORKER_MODEL or _oracle_model(blocks, channels)
-    s = Search(rule, sims, model, cpuct=1.0, queue_len=32, alpha=0.05, eps=0.15, noise_plies=10, noise=True)
-    t0 = time.perf_counter()
-    s.run(rules.Position(rule), 0)
-    return sims, s.n_evals, time.perf_counter() - t0
+    random.seed(seed)
+    rng = np.random.default_rng(seed)
+    thr = 10.0
+
+    class Counting:
+        def __init__(self, inner):
+            self.inner, self.rows = inner, 0
+
+        def predict(self, X):
+            self.rows += len(X)
+            return self.inner.predict(X)
+
+    if kind == "reference":
+        from games.gomoku import Gomoku
+        from games.pente import Pente
+        from mcts.new_mcts_alpha import MCTS
+        from network import PyTorchModel
+        import train as ref_train
+        torch.manual_seed(0)
+        model = Counting(PyTorchModel(board_size=15, n_res_blocks=blocks, channels=channels, device="cpu"))
+        cls = Pente if rule else Gomoku
+
+        def new_game(plies):
+            g = cls(15)
+            for _ in range(plies):                      # seeded random legal opening, as bench.py's scatter_start
+                e = np.flatnonzero(g.board.reshape(-1) == 0)
+                g2 = g.clone()
+                a = int(e[int(rng.integers(0, len(e)))])
+                g2.do_move(divmod(a, 15))
+                if g2.is_game_over():
+                    break
+                g = g2
+            m = MCTS(game_class=cls, n_simulations=sims, nn_model=model, cpuct=1.0, dirichlet_alpha=0.05, epsilon=0.15,
+                     apply_dirichlet_n_first_moves=10, add_dirichlet_noise=True)
+            return g, m
+
+        def one_ply(g, m):
+            temp_fn = lambda _mn: max(0.0, 1.0 - len(g.move_history) / thr)
+            ref_train.play_game_and_collect(m, g, temp_fn, max_moves=1, use_symmetries=True)
+            return g.is_game_over()
+    else:
+        from oracle import net as onet, rules as orules, selfplay as oselfplay
+        from oracle.search import Search
+        import alphazero_gomoku_b200.network as mynet
+        torch.manual_seed(0)
+        model = Counting(onet.CpuModel(mynet.AlphaZeroNet(n_res_blocks=blocks, channels=channels).state_dict()))
+
+        def new_game(plies):
+            g = orules.Position(rule)
+            for _ in range(plies):
+                e = np.flatnonzero(g.cells == 0)
+                g2 = g.copy()
+                orules.play(g2, int(e[int(rng.integers(0, len(e)))]))
+                if orules.game_over(g2):
+                    break
+                g = g2
+            return g, Search(rule, sims, model, cpuct=1.0, queue_len=32, alpha=0.05, eps=0.15, noise_plies=10, noise=True)
+
+        def one_ply(g, m):
+            oselfplay.play_one(m, g, lambda _p: max(0.0, 1.0 - g.plies / thr), max_plies=1, expand=True)
+            return orules.game_over(g)
+
+    game, mcts = new_game(idx % 40)
+    conn.send(("ready", kind))
+    while True:
+        cmd = conn.recv()
+        if cmd == "quit":
+            break
+        rows0 = model.rows
+        t0 = time.perf_counter()
+        over = one_ply(game, mcts)
+        dt = time.perf_counter() - t0
+        if over:
+            game, mcts = new_game(0)
+        conn.send((sims, model.rows - rows0, dt))
+
+
+class ReferencePool:
+    def __init__(self, workers, args):
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        rule = 1 if args.rule == "pente" else 0
+        self.procs, self.conns = [], []
+        for i in range(workers):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_ref_worker, args=(b, i, args.blocks, args.channels, rule, args.sims, 12345 + i), daemon=True)
+            p.start()
+            self.procs.append(p)
+            self.conns.append(a)
+        self.kind = [c.recv() for c in self.conns][0][1]
+        self.workers = workers
+
+    def step(self):
+        """One ply of every worker's game.  -> (simulations, leaf evaluations)."""
+        for c in self.conns:
+            c.send("step")
+        out = [c.recv() for c in self.conns]
+        return sum(o[0] for o in out), sum(o[1] for o in out)
+
+    def close(self):
+        for c in self.conns:
+            c.send("quit")
+        for p in self.procs:
+            p.join(timeout=10)
+
+
+def host_workers():
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)
+    return max(1, min(n - 1, 64))
+
+
+def reference_workload(args, workers, kind):
+    w = workload(args)
+    w["workload"] = (f"{args.rule} 15x15 self-play on the reference's CPU path ({kind}): {workers} worker processes x 1 torch thread, one game "
+                     f"each, one ply per step = reference MCTS.run of {args.sims} sims/move with tree reuse via play_game_and_collect(max_moves=1), "
+                     f"{args.blocks}x{args.channels} ResNet fp32, leaf queue 32; a bounded sample ({workers} games) of the "
+                     f"{args.games}-games/GPU workload of the CUDA arm")
+    w["games_per_gpu"] = workers
+    w["parallelism"] = f"{workers} CPU worker processes (train.py:695-742 scheme)"
+    w["cache"] = "n/a (CPU)"
+    return w
 
 
 def cpu_baseline(args, seconds):
-    """Oracle port (numpy tree + fp32 torch-CPU network, one thread) for ~`seconds` of self-play:
-    successive MCTS.run calls of one game with tree reuse, 400 sims per move."""
-    import torch
-    torch.set_num_threads(1)
-    from oracle import rules
-    from oracle.search import Search
-    rule = 1 if args.rule == "pente" else 0
-    np.random.seed(12345)
-    model = _oracle_model(args.blocks, args.channels)
-    s = Search(rule, 400, model, cpuct=1.0, queue_len=32, alpha=0.05, eps=0.15, noise_plies=10, noise=True)
-    pos = rules.Position(rule)
-    sims = moves = 0
+    """The same harness for ~`seconds`: as many one-ply steps of all workers as fit (at least one)."""
+    workers = host_workers()
+    pool = ReferencePool(workers, args)
+    sims = evals = steps = 0
     t0 = time.perf_counter()
-    while time.perf_counter() - t0 < seconds and not rules.game_over(pos):
-        pi = s.run(pos, pos.plies)
-        rules.play(pos, int(np.argmax(pi)))
-        sims += 400
-        moves += 1
+    while steps == 0 or time.perf_counter() - t0 < seconds:
+        s, e = pool.step()
+        sims, evals, steps = sims + s, evals + e, steps + 1
     dt = time.perf_counter() - t0
-    return {"value": sims / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"oracle port of mcts/new_mcts_alpha.py + network.py, one game, {moves} moves x 400 sims, "
-                      f"{s.n_evals} leaf evals, 1 torch thread, {dt:.1f} s"}
+    pool.close()
+    src = "the unmodified reference (byte-compiled into oracle/_ref)" if pool.kind == "reference" else "oracle port of mcts/new_mcts_alpha.py + network.py"
+    return {"value": sims / dt, "unit": UNIT, "cores": workers, "kind": pool.kind,
+            "sample": f"{src}: {workers} worker processes x 1 torch thread, one self-play game each from a seeded position of 0..39 plies, "
+                      f"{steps} plies per game x {args.sims} sims/move (play_game_and_collect(max_moves=1), tree reuse, root noise), "
+                      f"{evals} leaf evals, {dt:.1f} s"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python and
-    is not present on the GPU box) in the reference's own parallel mode: one process per host core
-    minus one, one torch thread each (train.py:695-742)."""
+    """--impl reference: see the comment above _ref_worker.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
-    workers = max(1, (os.cpu_count() or 2) - 1)
-    workers = min(workers, 64)
-    rule = 1 if args.rule == "pente" else 0
-    sims = 200
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(workers, initializer=_cpu_worker_init, initargs=(args.blocks, args.channels)) as pool:
-        for w in range(args.warmup):
-            pool.map(_cpu_worker, [(args.blocks, args.channels, rule, 32, 1000 + i) for i in range(workers)])
-        t0 = time.perf_counter()
-        total = evals = 0
-        for k in range(args.steps):
-            out = pool.map(_cpu_worker, [(args.blocks, args.channels, rule, sims, 12345 + k * workers + i) for i in range(workers)])
-            total += sum(o[0] for o in out)
-            evals += sum(o[1] for o in out)
-        dt = time.perf_counter() - t0
+    workers = host_workers()
+    pool = ReferencePool(workers, args)
+    for _ in range(args.warmup):
+        pool.step()
+    t0 = time.perf_counter()
+    total = evals = 0
+    for _ in range(args.steps):
+        s, e = pool.step()
+        total, evals = total + s, evals + e
+    dt = time.perf_counter() - t0
+    pool.close()
     value = total / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(args),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
-                             "sample": f"{workers} processes x {args.steps} MCTS.run of {sims} sims from the empty board "
-                                       f"(oracle port, 1 torch thread each), {evals} leaf evals"},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": reference_workload(args, workers, pool.kind),
+            "leaf_evals_per_s": evals / dt, "evals_per_sim": evals / max(total, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": pool.kind,
+                             "sample": f"{workers} processes x {args.steps} plies x {args.sims} sims/move, {evals} leaf evals, {dt:.1f} s"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -223,12 +317,35 @@ def scatter_start(sp, rng_seed):
     return pos
 
 
+def run_soak(args, sp, units, rank, world):
+    """Tree-memory soak: full games from the empty board with respawn on termination, the garbage
+    collector of ``azg_search_advance`` working at game length.  A dropped tree is a silent departure from the
+    reference's results, so any drop fails the run."""
+    import torch
+    t0 = time.perf_counter()
+    finished = 0
+    for ply in range(args.soak):
+        sp.step()
+        finished += int(sum(int(u.done.sum().item()) for u in units))
+        for u in units:
+            u.cursor.zero_()
+    torch.cuda.synchronize()
+    per = [u.engine.stats() for u in units]
+    line = {"soak_plies": args.soak, "config": workload(args), "rank": rank, "games_finished": finished,
+            "max_nodes_per_game": max(x["max_nodes"] for x in per), "node_capacity": args.node_capacity,
+            "dropped_trees": sum(x["dropped_trees"] for x in per), "games_in_error": sum(x["games_in_error"] for x in per),
+            "sims": sum(x["sims"] for x in per), "seconds": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+    if line["dropped_trees"] or line["games_in_error"]:
+        sys.exit(1)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import alphazero_gomoku_b200 as m
     from alphazero_gomoku_b200.network import PyTorchModel
-    from alphazero_gomoku_b200.selfplay import PipelinedSelfPlay, SelfPlay, TRUNK_FLOPS
+    from alphazero_gomoku_b200.selfplay import PipelinedSelfPlay, SelfPlay, trunk_flops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -249,6 +366,8 @@ def run_ours(args):
     else:
         sp = SelfPlay(model, n_games=args.games, game_base=rank * args.games, device=str(dev), **kw)
         units = [sp]
+    if args.soak:
+        return run_soak(args, sp, units, rank, world)
     for i, u in enumerate(units):
         scatter_start(u, 777 + 2 * rank + i)
         if args.graph:
@@ -379,7 +498,7 @@ def run_ours(args):
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
-        flops = float(evals) * TRUNK_FLOPS[args.channels] * 2 * args.blocks
+        flops = float(evals) * trunk_flops(args.channels) * 2 * args.blocks
         achieved = flops / (trunk_ms * 1e-3) / 1e12 if trunk_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": tot_sims / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -399,7 +518,7 @@ def run_ours(args):
                          "peak_source": peak_src,
                          "launches": int(conv_launches), "avg_launch_ms": trunk_ms / max(conv_launches, 1),
                          "trunk_share_of_step": trunk_ms / ms if ms else None,
-                         "algorithmic_flops_per_position_per_launch": TRUNK_FLOPS[args.channels],
+                         "algorithmic_flops_per_position_per_launch": trunk_flops(args.channels),
                          "pipeline_cycles_per_board": {k: round(v / max(pipe["boards"], 1), 1) for k, v in pipe.items()
                                                        if k != "boards" and not isinstance(v, dict)},
                          "pipeline_cycles_per_board_by_layer_type": {

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AZG_ABI_VERSION 1
+#define AZG_ABI_VERSION 2
 #define AZG_BOARD 15
 #define AZG_ACTIONS 225
 
@@ -153,6 +153,11 @@ int azg_search_stats(azg_engine* e, uint64_t* out_host);
  * play_game_and_collect for G games at once (train.py:360-412) with on-device Philox. */
 /* Allocate example capture for games of up to max_plies moves (train.py max_moves). */
 int azg_selfplay_enable(azg_engine* e, int max_plies);
+/* Optional slot mask int32[G] (device memory owned by the caller, read by every later azg_selfplay_choose /
+ * azg_selfplay_finish; NULL = all slots play).  A slot with active[g] == 0 is retired: it chooses no move
+ * (actions[g] = -1), records no example and never reports done.  This is how a fixed number of games is
+ * played to completion (train.py:671-694 plays exactly games_per_iteration games). */
+int azg_selfplay_set_active(azg_engine* e, const int32_t* active);
 /* noise float64[G][225] ~ Dirichlet(alpha) over all 225 actions (new_mcts_alpha.py:172);
  * The Philox stream is keyed by (global game id, action, `draw`, games finished in this slot, ply of
  * the current game); `draw` is an extra caller-chosen index and may stay constant. */

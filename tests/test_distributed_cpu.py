@@ -24,6 +24,10 @@ class _CpuModel:
         self.optimizer = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
         self.value_loss_fn = torch.nn.MSELoss()
         self.policy_loss_fn = torch.nn.KLDivLoss(reduction="batchmean")
+        self.invalidated = 0
+
+    def invalidate(self):
+        self.invalidated += 1
 
 
 def _batch(seed, n):
@@ -81,6 +85,29 @@ def _worker(rank, world, port, out):
     parts = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(parts, flat)
     same = bool(torch.equal(parts[0], parts[1]))
+    # BatchNorm running statistics: every rank normalised its own slice, so they differ until they are synchronised;
+    # afterwards the WHOLE state_dict (buffers included) is bit-identical on all ranks and the engine cache is dropped
+    def buffers():
+        return torch.cat([b.detach().reshape(-1).double() for b in model.net.buffers()])
+    parts = [torch.empty_like(buffers()) for _ in range(world)]
+    dist.all_gather(parts, buffers())
+    assert not torch.equal(parts[0], parts[1])
+    tr.sync_batchnorm_buffers(model)
+    assert model.invalidated == 1
+    parts = [torch.empty_like(buffers()) for _ in range(world)]
+    dist.all_gather(parts, buffers())
+    same = same and bool(torch.equal(parts[0], parts[1]))
+    assert int(model.net.bn.num_batches_tracked) == 1
+    # broadcast_model goes through the tensors (not .data) and drops the packed-weight cache
+    with torch.no_grad():
+        for p in model.net.parameters():
+            p.add_(float(rank))
+    tr.broadcast_model(model, 0)
+    assert model.invalidated == 2
+    flat = torch.cat([p.detach().reshape(-1) for p in model.net.parameters()])
+    parts = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(parts, flat)
+    same = same and bool(torch.equal(parts[0], parts[1]))
     out.put((rank, worst, same))
     dist.destroy_process_group()
 

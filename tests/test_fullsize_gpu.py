@@ -97,3 +97,44 @@ def test_selfplay_is_deterministic():
         outs.append((torch.stack(acts), torch.stack(pis)))
         sp.close()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("rule", [0, 1])
+def test_full_size_step_sampled_games_replayed_through_oracle(rule):
+    """A REAL configs[1] / configs[2] step - 2 048 concurrent games x 800 simulations, 6x128 network, root noise,
+    games scattered over plies 0..39 as in bench.py - with a sample of its games replayed one by one through
+    the oracle search (oracle.search.Search, the restatement of mcts/new_mcts_alpha.py).  The oracle is fed
+    the same network outputs (CUDA evaluator through its numpy API; a position's output does not depend on the
+    batch it travels in) and the same Dirichlet draws (read back from the device), so the visit counts of
+    every sampled game must be IDENTICAL, not just plausible."""
+    import bench
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import SelfPlay
+    from oracle import rules as orules
+    from oracle.search import Search
+    torch.manual_seed(0)
+    model = PyTorchModel(n_res_blocks=6, channels=128, device="cuda:0")
+    G, S = 2048, 800
+    sp = SelfPlay(model, rule=rule, n_games=G, n_sims=S, node_capacity=8192, noise=True, alpha=0.05, eps=0.15, noise_plies=10,
+                  example_capacity=1 << 16, seed=12345)
+    pos = bench.scatter_start(sp, 777)
+    pi, visits = sp.search()
+    pi, visits, noise = pi.cpu().numpy(), visits.cpu().numpy(), sp.noise.cpu().numpy()
+    boards, players, lasts, caps, plies = (t.cpu().numpy() for t in sp.engine.rules.unpack(pos))
+    assert sp.engine.stats()["games_in_error"] == 0
+
+    class DeviceNet:
+        def predict(self, X):
+            return model.predict(X)
+
+    sample = [0, 43, 126, 369, 1010, 1297, 1953, 2047]          # root plies 0, 3, 6, 9, 10, 17, 33, 7: noised and plain roots
+    for g in sample:
+        p = orules.Position(rule)
+        p.cells = boards[g].astype(np.int8).copy()
+        p.player, p.last, p.caps, p.plies = int(players[g]), int(lasts[g]), [int(caps[g][0]), int(caps[g][1])], int(plies[g])
+        s = Search(rule, S, DeviceNet(), cpuct=1.0, queue_len=32, alpha=0.05, eps=0.15, noise_plies=10, noise=True,
+                   noise_fn=lambda n, g=g: noise[g].copy())
+        want = s.run(p, p.plies)
+        assert np.array_equal(visits[g], s.Nv[p.key()].astype(np.int32)), (g, p.plies)
+        assert np.array_equal(pi[g], want), (g, p.plies)
+    sp.close()

@@ -67,6 +67,9 @@ def test_trunk_layer_by_layer(blocks, ch):
     eng.close()
 
 
+TOL = {(3, 64): (2e-4, 1.2e-3, 5e-3, 0.025, 0.97), (6, 128): (1e-3, 1.5e-2, 1.5e-2, 0.2, 0.97)}
+
+
 @pytest.mark.parametrize("blocks,ch", [(3, 64), (6, 128)])
 def test_policy_value_tolerance(blocks, ch):
     import alphazero_gomoku_b200.network as mynet
@@ -87,9 +90,12 @@ def test_policy_value_tolerance(blocks, ch):
     dv = np.abs(values - v_ref.numpy())
     agree = float((probs.argmax(1) == p_ref.argmax(1)).mean())
     print(f"{blocks}x{ch}: KL mean {kl.mean():.2e} max {kl.max():.2e}  |dv| mean {dv.mean():.2e} max {dv.max():.2e}  argmax {agree:.3f}")
-    assert kl.mean() < 5e-3 and kl.max() < 8e-2
-    assert dv.mean() < 3e-2 and dv.max() < 0.3
-    assert agree >= 0.95
+    # stated bf16 tolerance = about twice what this kernel measures (round 1: 6x128 KL mean 4.3e-4 / max 6.7e-3,
+    # |dv| mean 6.8e-3 / max 0.10; 3x64 KL mean 9.4e-5 / max 5.3e-4, |dv| max 0.011)
+    kl_mean, kl_max, dv_mean, dv_max, min_agree = TOL[(blocks, ch)]
+    assert kl.mean() < kl_mean and kl.max() < kl_max
+    assert dv.mean() < dv_mean and dv.max() < dv_max
+    assert agree >= min_agree
     eng.close()
 
 
@@ -128,8 +134,11 @@ def test_golden_reference_outputs():
     probs, values = model.predict(z["X"])
     assert probs.shape == (24, 225) and values.shape == (24, 1) and probs.dtype == np.float32
     kl = onet.policy_kl(z["6x128/probs"], probs)
-    assert kl.mean() < 5e-3 and kl.max() < 8e-2
-    assert np.abs(values - z["6x128/values"]).max() < 0.3
+    kl_mean, kl_max, dv_mean, dv_max, _ = TOL[(6, 128)]
+    dv = np.abs(values - z["6x128/values"])
+    print(f"golden 6x128: KL mean {kl.mean():.2e} max {kl.max():.2e}  |dv| mean {dv.mean():.2e} max {dv.max():.2e}")
+    assert kl.mean() < kl_mean and kl.max() < kl_max
+    assert dv.mean() < dv_mean and dv.max() < dv_max
 
 
 def test_search_with_real_network_on_device():

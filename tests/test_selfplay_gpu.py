@@ -233,3 +233,91 @@ def test_graph_captured_ply_matches_host_driven_loop():
     assert graph.engine.stats()["evals"] == plain.engine.stats()["evals"]
     plain.close()
     graph.close()
+
+
+def test_max_games_plays_exactly_that_many_complete_games():
+    """SelfPlay(max_games=n): exactly n games are started, every one is played to its end and counted once
+    (train.py:671-694 plays games_per_iteration full games) - finished slots restart only while games remain
+    to be started, then retire; no game is cut off, none is counted twice."""
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import SelfPlay
+    torch.manual_seed(2)
+    model = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    for G, n, use_graph in ((4, 7, False), (8, 5, False), (4, 6, True)):
+        sp = SelfPlay(model, n_games=G, n_sims=32, noise=True, max_moves=225, node_capacity=2048, example_capacity=1 << 16,
+                      seed=3, max_games=n)
+        if use_graph:
+            sp.enable_graph()
+        finished, steps, rows_by_len = 0, 0, 0
+        lengths = torch.zeros(G, dtype=torch.int64, device="cuda")
+        while sp.games_running() > 0:
+            active_before = sp.active.clone()
+            sp.step()
+            steps += 1
+            lengths += active_before
+            done = sp.done.bool()
+            assert bool((active_before[done] == 1).all())              # only running slots finish
+            rows_by_len += int(lengths[done].sum().item()) * 8
+            lengths[done] = 0
+            finished += int(done.sum().item())
+            assert steps < 2000
+        assert finished == n and int(sp.started.item()) == n
+        assert sp.n_examples() == rows_by_len                          # every finished game contributed all its plies
+        before = sp.n_examples()
+        sp.step()                                                      # all retired: nothing moves, nothing is emitted
+        assert sp.n_examples() == before and int(sp.done.sum().item()) == 0
+        sp.close()
+
+
+def test_predict_rejects_inputs_that_are_not_encoded_boards():
+    from alphazero_gomoku_b200.network import PyTorchModel
+    torch.manual_seed(1)
+    model = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    X = np.zeros((2, 3, 15, 15), np.float32)
+    X[:, 2] = 1
+    X[0, 0, 7, 7] = 1
+    model.predict(X)
+    for bad in ("frac", "overlap", "turn"):
+        Y = X.copy()
+        if bad == "frac":
+            Y[1, 1, 3, 3] = 0.5
+        elif bad == "overlap":
+            Y[0, 1, 7, 7] = 1
+        else:
+            Y[1, 2, 0, 0] = 0
+        with pytest.raises(ValueError):
+            model.predict(Y)
+    with pytest.raises(ValueError):
+        PyTorchModel(action_size=226, device="cuda:0")
+    # a write through .data is invisible to the version counters: invalidate() makes it count
+    p0, _ = model.predict(X)
+    model.net.policy_fc.bias.data[5] += 3.0
+    model.invalidate()
+    p1, _ = model.predict(X)
+    assert not np.array_equal(p0, p1)
+
+
+def test_graph_mode_round_bound_small_queue():
+    """The captured ply must hold enough rounds for n*q/(q-1) leaves (every flush parks one simulation that
+    queues a second leaf): graph == host-driven loop also for a short queue, and queue_len 1 is refused."""
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import SelfPlay
+    torch.manual_seed(6)
+    model = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    outs = []
+    for use_graph in (False, True):
+        sp = SelfPlay(model, n_games=16, n_sims=50, queue_len=3, node_capacity=2048, example_capacity=1 << 14, seed=9)
+        if use_graph:
+            sp.enable_graph()
+        pis = []
+        for _ in range(3):
+            sp.step()
+            pis.append(sp.last_pi.clone())
+        outs.append(torch.stack(pis))
+        assert sp.engine.stats()["games_in_error"] == 0
+        sp.close()
+    assert torch.equal(outs[0], outs[1])
+    sp = SelfPlay(model, n_games=2, n_sims=8, queue_len=1, node_capacity=256, example_capacity=1 << 10)
+    with pytest.raises(ValueError):
+        sp.enable_graph()
+    sp.close()

@@ -76,3 +76,15 @@ int azg_heads_gemm_launch(const CUtensorMap& tm_hid, const CUtensorMap& tm_wp, c
 struct PackArgs {
   int C, n_blocks;
 };
+
+// net_wgrad.cu: weight gradient of one 3x3 layer, dW[tap][co][ci] (fp32, accumulated with reductions: zero it first).
+// tm_dz: box {64 channels, 64 rows} over the output-gradient buffer; tm_a: box {64 channels, azg_wgrad3x3_a_rows()}
+// over the layer's input activations; both in the padded activation layout, SWIZZLE_128B.
+struct WgradArgs {
+  int n_boards;
+  float* dw;                      // [9][C][C]
+  int* error;                     // watchdog flag
+  int desc_variant;               // experiment switch for the MN-major descriptor fields (0 = documented layout)
+};
+int azg_wgrad3x3_a_rows();
+int azg_wgrad3x3_launch(int C, const CUtensorMap& tm_dz, const CUtensorMap& tm_a, const WgradArgs& a, int n_sm, cudaStream_t stream);

@@ -11,14 +11,18 @@
 //
 // Kernel shape: persistent, one 2-CTA cluster per SM pair (cta_group::2, UMMA 256 x C x 16).
 //   * the layer's weights (9 taps x C x C bf16) stay RESIDENT in shared memory, split by output
-//     channel across the pair (C = 128: 144 KB per CTA) - no weight traffic per tile;
-//   * activations arrive by TMA as three column-shifted copies (dc = -1, 0, +1) of 160 rows per
-//     64-channel slice; the three row taps (dr) of a copy are 2 KB-aligned offsets of the same
-//     shared-memory tile, so each activation byte is fetched 3x from L2 instead of 9x;
-//   * accumulators live in TMEM (2 x C columns, double buffered) so the epilogue of board i
-//     overlaps the MMAs of board i+1;
+//     channel across the pair (C = 128: 144 KB per CTA) - no weight traffic per tile; C = 256 streams
+//     one 64-channel slice of all nine taps at a time through a 9-slot ring instead;
+//   * activations arrive by TMA as ONE copy of 162 rows (tile + halo) per 64-channel slice; all nine
+//     taps are row offsets of that tile in the UMMA shared-memory descriptor, so each activation byte
+//     is fetched once from L2 (MODE 1/3/4/5; MODE 0, three column-shifted copies, is the recorded
+//     first version);
+//   * accumulators live in TMEM as a ring of NACC buffers (4 x 128 columns at C = 128, 8 x 64 at
+//     C = 64, 2 x 256 at C = 256): the epilogue of board i overlaps the MMAs of boards i+1 ...;
 //   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator,
-//     warps 2-9 epilogue (TMEM -> registers -> shift (+residual) -> ReLU -> bf16 -> HBM).
+//     warps 2-9 epilogue (TMEM -> registers -> shift (+residual) -> ReLU (optional) -> bf16 -> HBM).
+// The same kernel is the forward AND the input-gradient convolution of the training step (train_engine.cu):
+// relu = 0, shift = 0, weights either raw (z = conv(a)) or transposed with flipped taps (da = conv^T(dz)).
 #include <cuda_bf16.h>
 #include <type_traits>
 #include "net.h"
@@ -40,7 +44,11 @@ struct Stage {
   static constexpr int BYTES = ROWS * 128;                         // TMA transaction size
   static constexpr int PITCH = (BYTES + 1023) & ~1023;             // 1024-aligned stage pitch
 };
-constexpr int kThreads = 320;                  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+// warp 0 TMA, warp 1 MMA, then EG groups of 8 epilogue warps.  With 64 channels the MMAs of a board take 1.15 k cycles
+// but one group of 8 warps needs ~2.3 k cycles for its epilogue (round 1: 1 178 cycles per board spent waiting for a free
+// accumulator), so two groups work on alternate boards there.
+template <int C> constexpr int epi_groups() { return C == 64 ? 2 : 1; }
+template <int C> constexpr int conv_threads() { return 64 + 256 * epi_groups<C>(); }
 
 template <int C, int MODE>
 struct Cfg {
@@ -54,10 +62,10 @@ struct Cfg {
   // Accumulator ring in TMEM.  Two buffers only hide an epilogue that is SHORTER than the MMAs of a board;
   // on residual layers its latency is longer (measured 5.9 k vs 4.25 k cycles), so the whole 512 columns
   // are used: four buffers at 128 channels (MMA of board i+4 waits for the epilogue of board i).
-  static constexpr int NACC = C == 256 ? 2 : 4;
+  static constexpr int NACC = C == 256 ? 2 : (C == 64 ? 8 : 4);
   static constexpr int TMEM_COLS = NACC * C;              // 256 or 512 columns (a power of two)
   static constexpr int STAGES = MODE == 0 ? (C == 128 ? 4 : 6) : 3;   // activation tiles in flight
-  static constexpr int EPI = (MODE == 1 || MODE == 4 || MODE == 5) ? 8 * 2048 : 0;                // per-warp epilogue staging tiles (32 rows x 64 B)
+  static constexpr int EPI = (MODE == 1 || MODE == 4 || MODE == 5) ? 8 * epi_groups<C>() * 2048 : 0;                // per-warp epilogue staging tiles (32 rows x 64 B)
   static constexpr int SMEM = 1024 + BBYTES + STAGES * Stage<MODE>::PITCH + EPI + 512;
 };
 
@@ -80,7 +88,7 @@ struct HeadConst {
 enum { ERR_BFULL = 1, ERR_EMPTY = 2, ERR_FULL = 3, ERR_TEMPTY = 4, ERR_TFULL = 5 };
 
 template <int C, bool HEADS, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(conv_threads<C>(), 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
                     const __grid_constant__ CUtensorMap tm_out, ConvArgs p,
                     const __grid_constant__ ConvShift<C> shift, const __grid_constant__ HeadConst<HEADS ? C : 1> head) {
@@ -265,7 +273,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     // that the three head dot products stay inside a thread; the other warp only signals.
     ptx::grid_dep_wait();                      // residual reads and output writes follow the previous layer
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 3;                 // epilogue group: takes the boards with it % EG == grp
+    const int half = ((warp - 2) & 7) >> 2;
+    constexpr int EG = epi_groups<C>();
     constexpr int NCH = HEADS ? C : C / 2;           // channels handled by a working warp
     const int ch0 = HEADS ? 0 : half * (C / 2);
     const bool working = !HEADS || half == 0;
@@ -276,6 +286,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     bool ok = true;
     long long t_tfull = 0, t_wr = 0, t_rt = 0, t_ld = 0, t_cs = 0, t_st = 0;
     const bool detail = p.prof != nullptr && p.prof_detail != 0;      // per-phase clocks only on request (AZG_CONV_PHASES=1)
+    const float lo = p.relu ? 0.f : -INFINITY;       // relu == 0: linear output (training: pre-BatchNorm z, input gradients)
     const long long t_begin = clock64();
     // MODE >= 1: global traffic of the epilogue is coalesced through a per-warp 2 KB staging tile
     // (32 rows x 32 channels, 64-byte rows, 16-byte units XOR-swizzled with (row >> 1) & 3, which is
@@ -294,6 +305,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     const uint32_t own_sw = (uint32_t)((lane >> 1) & 3);
     const int crow = lane >> 2, cunit = lane & 3;                          // coalesced mapping: row 8i + crow, unit cunit
     for (int b = cid; b < n_boards && ok; b += ncl, ++it) {
+      if (EG > 1 && (it % EG) != grp) continue;
       const int acc = it % K::NACC;
       const size_t grow0 = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)rank * 128 + (size_t)quad * 32;   // first row of this warp
       const size_t grow = grow0 + (size_t)lane;
@@ -366,7 +378,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
                 y0 += __uint_as_float(rw << 16);
                 y1 += __uint_as_float(rw & 0xffff0000u);
               }
-              const __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(y0, 0.f), fmaxf(y1, 0.f));
+              const __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(y0, lo), fmaxf(y1, lo));
               outv[h] = pad ? 0u : *reinterpret_cast<const uint32_t*>(&pk);
             }
           };
@@ -475,7 +487,7 @@ int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtens
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(conv_threads<C>());
   cfg.dynamicSmemBytes = K::SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -42,6 +42,12 @@ class azg_net_weights(C.Structure):
                 ("value_fc2_b", C.c_void_p)]
 
 
+class azg_train_config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("n_blocks", C.c_int32), ("channels", C.c_int32), ("max_batch", C.c_int32),
+                ("lr", C.c_double), ("weight_decay", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("clip", C.c_double), ("bn_momentum", C.c_double), ("bn_eps", C.c_double)]
+
+
 assert C.sizeof(azg_pos) == 96
 
 _P = C.c_void_p
@@ -91,6 +97,18 @@ PROTOTYPES = {
     "azg_net_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "azg_net_profile_counters": (_I, [_P, _P]),
     "azg_net_check": (_I, [_P, _P]),
+    "azg_train_create": (_I, [C.POINTER(azg_train_config), C.POINTER(_P)]),
+    "azg_train_destroy": (_I, [_P]),
+    "azg_train_param_count": (C.c_int64, [_P]),
+    "azg_train_memory_bytes": (C.c_int64, [_P]),
+    "azg_train_bind": (_I, [_P, _P, _P, _P, _P, C.POINTER(azg_net_weights), C.c_int64, _P]),
+    "azg_train_pack": (_I, [_P, _P]),
+    "azg_train_forward_backward": (_I, [_P, _P, _P, _P, _I, _P, _P]),
+    "azg_train_apply": (_I, [_P, _I, _P]),
+    "azg_train_check": (_I, [_P, _P, _P]),
+    "azg_train_read_activation": (_I, [_P, _I, _I, _P, _P]),
+    "azg_train_export_grads": (_I, [_P, _P, _P]),
+    "azg_train_debug_conv_grads": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
 }
 
 

@@ -1,0 +1,885 @@
+// Training-step kernels around the tensor-core convolutions: training-mode BatchNorm (forward and
+// backward), stem, policy / value heads with the loss, gradient-norm clip + Adam + bf16 repack.
+//
+// Replaces what torch autograd does for PyTorchModel.train_batch (network.py:199-235):
+//   forward   network.py:94-117 with module.training = True (BatchNorm2d uses batch statistics and
+//             updates its running statistics with momentum 0.1 / unbiased variance)
+//   loss      KLDivLoss(batchmean)(log_softmax(logits), pi) + MSELoss(value, z)   (network.py:143-144, 217-222)
+//   backward  of all of the above
+//   update    clip_grad_norm_(3.0) (network.py:224) and Adam(lr, weight_decay) (network.py:141, 225)
+//
+// These kernels are HBM / L2 bound elementwise and reduction passes over the padded bf16 activation
+// layout of net_conv.cu ([board][256 rows][C], pad rows zero); all arithmetic is fp32 (statistics are
+// finished in fp64).  Per-channel reductions are deterministic: every block writes its partial sums and
+// the last block to finish (ticket counter) adds them in block order.
+#include <cuda_bf16.h>
+#include <math.h>
+#include "train.h"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int kEwThreads = 256;
+
+__device__ __forceinline__ bool is_pad_row(int qi) { return qi < 16 || (qi & 15) == 15; }
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&p);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Ticket: true in exactly one block - the last one to arrive - after all blocks' global writes are visible.
+__device__ __forceinline__ bool last_block_arrives(unsigned* counter) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *counter = 0;          // ready for the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trunk BatchNorm: batch statistics
+// ------------------------------------------------------------------------------------------------
+// Thread = (row lane rl, 8-channel group cg); a block covers RL = 256 / (C/8) rows per iteration.
+template <int C, bool BWD>
+__device__ __forceinline__ void channel_reduce(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ g,
+                                               const __nv_bfloat16* __restrict__ a, const float* __restrict__ stats,
+                                               int n_boards, float* __restrict__ partial) {
+  constexpr int CG = C / 8, RL = kEwThreads / CG;
+  __shared__ float red[RL][2][C];
+  const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
+  float mean[8], rstd[8];
+  if (BWD) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mean[i] = stats[cg * 8 + i]; rstd[i] = stats[C + cg * 8 + i]; }
+  }
+  const long long n_rows = (long long)n_boards * 256;
+  for (long long r = (long long)blockIdx.x * RL + rl; r < n_rows; r += (long long)gridDim.x * RL) {
+    const size_t off = ((size_t)AZG_NET_FRONT + (size_t)r) * C + (size_t)cg * 8;
+    float zf[8];
+    unpack8(ptx::ldg128(z + off), zf);
+    if (!BWD) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s0[i] += zf[i]; s1[i] = fmaf(zf[i], zf[i], s1[i]); }
+    } else {
+      float gf[8], af[8];
+      unpack8(ptx::ldg128(g + off), gf);
+      unpack8(ptx::ldg128(a + off), af);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dy = af[i] > 0.f ? gf[i] : 0.f;
+        s0[i] += dy;
+        s1[i] = fmaf(dy, (zf[i] - mean[i]) * rstd[i], s1[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[rl][0][cg * 8 + i] = s0[i]; red[rl][1][cg * 8 + i] = s1[i]; }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 2 * C; t += kEwThreads) {
+    const int k = t / C, c = t % C;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < RL; ++j) acc += red[j][k][c];
+    partial[((size_t)blockIdx.x * 2 + k) * C + c] = acc;
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kEwThreads)
+bn_stats_kernel(BnStatsArgs p) {
+  channel_reduce<C, false>(p.z, nullptr, nullptr, nullptr, p.n_boards, p.partial);
+  if (!last_block_arrives(p.counter)) return;
+  const double n = (double)p.n_boards * 225.0;
+  for (int c = threadIdx.x; c < C; c += kEwThreads) {
+    double s = 0.0, q = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) {
+      s += (double)p.partial[((size_t)b * 2 + 0) * C + c];
+      q += (double)p.partial[((size_t)b * 2 + 1) * C + c];
+    }
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    p.stats[c] = (float)mean;
+    p.stats[C + c] = (float)(1.0 / sqrt(var + (double)p.eps));
+    const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+    p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
+    p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)unbiased;
+  }
+}
+
+// a = relu(gamma * (z - mean) * rstd + beta (+ residual)), pad rows zero
+template <int C>
+__global__ void __launch_bounds__(kEwThreads)
+bn_apply_kernel(BnApplyArgs p) {
+  constexpr int CG = C / 8;
+  const long long total = (long long)p.n_boards * 256 * CG;
+  const long long stride = (long long)gridDim.x * kEwThreads;          // a multiple of CG: the channel group of a thread is fixed
+  long long idx = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+  const int cg = (int)(idx % CG);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cg * 8 + i;
+    sc[i] = p.gamma[c] * p.stats[C + c];
+    sh[i] = p.beta[c] - p.stats[c] * sc[i];
+  }
+  for (; idx < total; idx += stride) {
+    const long long r = idx / CG;
+    const size_t off = ((size_t)AZG_NET_FRONT + (size_t)r) * C + (size_t)cg * 8;
+    float y[8];
+    if (is_pad_row((int)(r & 255))) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = 0.f;
+    } else {
+      float zf[8];
+      unpack8(ptx::ldg128(p.z + off), zf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = fmaf(zf[i], sc[i], sh[i]);
+      if (p.residual) {
+        float rf[8];
+        unpack8(ptx::ldg128(p.residual + off), rf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] += rf[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
+    }
+    ptx::stg128(p.out + off, pack8(y));
+  }
+}
+
+// backward: sums of dy and dy * x_hat per channel, dgamma / dbeta
+template <int C>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_reduce_kernel(BnBwdArgs p) {
+  channel_reduce<C, true>(p.z, p.g, p.a, p.stats, p.n_boards, p.partial);
+  if (!last_block_arrives(p.counter)) return;
+  for (int t = threadIdx.x; t < 2 * C; t += kEwThreads) {
+    const int k = t / C, c = t % C;
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += (double)p.partial[((size_t)b * 2 + k) * C + c];
+    p.sums[k * C + c] = (float)s;
+    if (k == 0) p.dbeta[c] = (float)s; else p.dgamma[c] = (float)s;
+  }
+}
+
+// dz = gamma * rstd * (dy - mean(dy) - x_hat * mean(dy * x_hat)), pad rows zero; gskip = dy
+template <int C>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply_kernel(BnBwdArgs p) {
+  constexpr int CG = C / 8;
+  const long long total = (long long)p.n_boards * 256 * CG;
+  const long long stride = (long long)gridDim.x * kEwThreads;
+  long long idx = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+  const int cg = (int)(idx % CG);
+  const float inv_n = 1.0f / ((float)p.n_boards * 225.0f);
+  float mean[8], rstd[8], k0[8], m1[8], m2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cg * 8 + i;
+    mean[i] = p.stats[c];
+    rstd[i] = p.stats[C + c];
+    k0[i] = p.gamma[c] * rstd[i];
+    m1[i] = p.sums[c] * inv_n;
+    m2[i] = p.sums[C + c] * inv_n;
+  }
+  for (; idx < total; idx += stride) {
+    const long long r = idx / CG;
+    const size_t off = ((size_t)AZG_NET_FRONT + (size_t)r) * C + (size_t)cg * 8;
+    float dz[8], dy[8];
+    if (is_pad_row((int)(r & 255))) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz[i] = dy[i] = 0.f;
+    } else {
+      float zf[8], gf[8], af[8];
+      unpack8(ptx::ldg128(p.z + off), zf);
+      unpack8(ptx::ldg128(p.g + off), gf);
+      unpack8(ptx::ldg128(p.a + off), af);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dy[i] = af[i] > 0.f ? gf[i] : 0.f;
+        const float xh = (zf[i] - mean[i]) * rstd[i];
+        dz[i] = k0[i] * (dy[i] - m1[i] - xh * m2[i]);
+      }
+    }
+    ptx::stg128(p.dz + off, pack8(dz));
+    if (p.gskip) ptx::stg128(p.gskip + off, pack8(dy));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: conv 3x3, 3 planes -> C (network.py:94)
+// ------------------------------------------------------------------------------------------------
+// One board per block iteration.  Planes live zero-padded (17 x 17) in shared memory, weights as [27][C].
+template <int C>
+__global__ void __launch_bounds__(256)
+stem_train_fwd_kernel(StemTrainArgs p) {
+  __shared__ float xs[3][17][17];
+  __shared__ float ws[27][C];
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) ws[i % 27][i / 27] = p.w[i];           // [c][27] -> [27][c]
+  constexpr int CG = C / 8;
+  for (int b = blockIdx.x; b < p.n_boards; b += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 17 * 17; i += blockDim.x) (&xs[0][0][0])[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 675; i += blockDim.x) {
+      const int pl = i / 225, pix = i % 225;
+      xs[pl][pix / 15 + 1][pix % 15 + 1] = p.planes[(size_t)b * 675 + i];
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < 225 * CG; item += blockDim.x) {
+      const int pix = item / CG, cg = item % CG;
+      const int r = pix / 15, c = pix % 15;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float x = xs[pl][r + t / 3][c + t % 3];
+          const float* w = &ws[pl * 9 + t][cg * 8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(x, w[i], acc[i]);
+        }
+      const size_t row = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)((r + 1) * 16 + c);
+      ptx::stg128(p.z + row * C + (size_t)cg * 8, pack8(acc));
+    }
+  }
+}
+
+// dW[plane*9+tap][c] = sum over boards, pixels of dz[pixel][c] * x[plane][pixel + tap]; thread = channel.
+template <int C>
+__global__ void __launch_bounds__(C)
+stem_train_wgrad_kernel(StemTrainArgs p) {
+  __shared__ float xs[3][17][17];
+  const int c = threadIdx.x;
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  for (int b = blockIdx.x; b < p.n_boards; b += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 17 * 17; i += blockDim.x) (&xs[0][0][0])[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 675; i += blockDim.x) {
+      const int pl = i / 225, pix = i % 225;
+      xs[pl][pix / 15 + 1][pix % 15 + 1] = p.planes[(size_t)b * 675 + i];
+    }
+    __syncthreads();
+    for (int pix = 0; pix < 225; ++pix) {
+      const int r = pix / 15, cc = pix % 15;
+      const size_t row = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)((r + 1) * 16 + cc);
+      const float d = __bfloat162float(p.dz[row * C + c]);
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[pl * 9 + t] = fmaf(d, xs[pl][r + t / 3][cc + t % 3], acc[pl * 9 + t]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 27; ++i) p.partial[((size_t)blockIdx.x * 27 + i) * C + c] = acc[i];
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_partial, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int p = 0; p < n_partial; ++p) acc += partial[(size_t)p * n + i];
+  out[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// heads, forward
+// ------------------------------------------------------------------------------------------------
+// 1x1 convolutions C -> 2 (policy) + 1 (value): warp per pixel row, lanes over channels.
+template <int C>
+__global__ void __launch_bounds__(256)
+head_conv_fwd_kernel(HeadTrainArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  constexpr int PER = C / 32;              // channels per lane
+  float w[3][PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    w[0][i] = p.w1p[lane * PER + i];
+    w[1][i] = p.w1p[C + lane * PER + i];
+    w[2][i] = p.w1v[lane * PER + i];
+  }
+  const int total = p.n_boards * 225;
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += warps) {
+    const int b = item / 225, pix = item % 225;
+    const size_t row = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)((pix / 15 + 1) * 16 + pix % 15);
+    const __nv_bfloat16* src = p.act + row * C + lane * PER;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const float x = __bfloat162float(src[i]);
+      d0 = fmaf(x, w[0][i], d0); d1 = fmaf(x, w[1][i], d1); d2 = fmaf(x, w[2][i], d2);
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      d0 += __shfl_xor_sync(0xffffffffu, d0, s);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, s);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, s);
+    }
+    if (lane == 0) {
+      float* o = p.zh + (size_t)b * 675 + pix;
+      o[0] = d0; o[225] = d1; o[450] = d2;
+    }
+  }
+}
+
+// deterministic block sum of two doubles (1024 threads)
+__device__ __forceinline__ void block_sum2(double& a, double& b) {
+  __shared__ double sa[32], sb[32];
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, s); b += __shfl_xor_sync(0xffffffffu, b, s); }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) { sa[warp] = a; sb[warp] = b; }
+  __syncthreads();
+  a = lane < nw ? sa[lane] : 0.0;
+  b = lane < nw ? sb[lane] : 0.0;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, s); b += __shfl_xor_sync(0xffffffffu, b, s); }
+}
+
+// BatchNorm2d(2) / BatchNorm2d(1) in training mode + ReLU: one block per head channel h (0, 1 policy; 2 value)
+__global__ void __launch_bounds__(1024)
+head_bn_fwd_kernel(HeadTrainArgs p) {
+  const int h = blockIdx.x;
+  const int n = p.n_boards * 225;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float z = p.zh[(size_t)(i / 225) * 675 + h * 225 + i % 225];
+    s += z; q += (double)z * z;
+  }
+  block_sum2(s, q);
+  const double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+  const int which = h < 2 ? 0 : 1, ch = h < 2 ? h : 0;
+  const float gamma = p.bn_gamma[which][ch], beta = p.bn_beta[which][ch];
+  if (threadIdx.x == 0) {
+    p.hstats[h * 2] = (float)mean;
+    p.hstats[h * 2 + 1] = rstd;
+    const double unbiased = n > 1 ? var * n / (n - 1.0) : var;
+    p.bn_rmean[which][ch] = (1.f - p.momentum) * p.bn_rmean[which][ch] + p.momentum * (float)mean;
+    p.bn_rvar[which][ch] = (1.f - p.momentum) * p.bn_rvar[which][ch] + p.momentum * (float)unbiased;
+  }
+  const float sc = gamma * rstd, sh = beta - (float)mean * sc;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const size_t o = (size_t)(i / 225) * 675 + h * 225 + i % 225;
+    p.hidden[o] = fmaxf(fmaf(p.zh[o], sc, sh), 0.f);
+  }
+}
+
+// dense layers + loss, NB boards per block: logits = hidden_p Wp^T + bp; h1 = relu(hidden_v Wv1^T + bv1);
+// value = tanh(h1 w2 + b2); KL row sum, squared error, dlogits, dvpre.
+constexpr int kFcBoards = 4;
+__global__ void __launch_bounds__(256)
+head_fc_fwd_kernel(HeadTrainArgs p) {
+  __shared__ float hs[kFcBoards][675];
+  __shared__ float h1s[kFcBoards][64];
+  __shared__ float red[kFcBoards][8];
+  __shared__ float red2[kFcBoards][8];
+  const int b0 = blockIdx.x * kFcBoards;
+  const int nb = min(kFcBoards, p.n_boards - b0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kFcBoards * 675; i += blockDim.x) {
+    const int k = i / 675;
+    hs[k][i % 675] = k < nb ? p.hidden[(size_t)(b0 + k) * 675 + i % 675] : 0.f;
+  }
+  __syncthreads();
+  float logit[kFcBoards];
+  const int j = tid;
+  if (j < 225) {
+#pragma unroll
+    for (int k = 0; k < kFcBoards; ++k) logit[k] = p.bp[j];
+    for (int i = 0; i < 450; ++i) {
+      const float w = p.wp_t[(size_t)i * 225 + j];
+#pragma unroll
+      for (int k = 0; k < kFcBoards; ++k) logit[k] = fmaf(hs[k][i], w, logit[k]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kFcBoards; ++k) logit[k] = -INFINITY;
+  }
+  if (tid < 64) {
+    float acc[kFcBoards];
+#pragma unroll
+    for (int k = 0; k < kFcBoards; ++k) acc[k] = p.bv1[tid];
+    for (int i = 0; i < 225; ++i) {
+      const float w = p.wv1_t[(size_t)i * 64 + tid];
+#pragma unroll
+      for (int k = 0; k < kFcBoards; ++k) acc[k] = fmaf(hs[k][450 + i], w, acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kFcBoards; ++k) {
+      h1s[k][tid] = fmaxf(acc[k], 0.f);
+      if (k < nb) p.h1[(size_t)(b0 + k) * 64 + tid] = h1s[k][tid];
+    }
+  }
+  // row maxima
+#pragma unroll
+  for (int k = 0; k < kFcBoards; ++k) {
+    float m = logit[k];
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if (lane == 0) red[k][warp] = m;
+  }
+  __syncthreads();
+  float mx[kFcBoards], ex[kFcBoards];
+#pragma unroll
+  for (int k = 0; k < kFcBoards; ++k) {
+    float m = red[k][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[k][w]);
+    mx[k] = m;
+    ex[k] = j < 225 ? expf(logit[k] - m) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kFcBoards; ++k) {
+    float s = ex[k];
+#pragma unroll
+    for (int t = 16; t >= 1; t >>= 1) s += __shfl_xor_sync(0xffffffffu, s, t);
+    if (lane == 0) red[k][warp] = s;
+  }
+  __syncthreads();
+  const float inv_b = 1.0f / (float)p.n_boards;
+  float klp[kFcBoards], pis[kFcBoards], prob[kFcBoards], tgt[kFcBoards];
+#pragma unroll
+  for (int k = 0; k < kFcBoards; ++k) {
+    float se = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) se += red[k][w];
+    klp[k] = pis[k] = prob[k] = tgt[k] = 0.f;
+    if (j < 225 && k < nb) {
+      const float logp = logit[k] - mx[k] - logf(se);
+      const float t = p.pi[(size_t)(b0 + k) * 225 + j];
+      tgt[k] = t;
+      prob[k] = ex[k] / se;
+      klp[k] = t > 0.f ? t * (logf(t) - logp) : 0.f;
+      pis[k] = t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kFcBoards; ++k) {
+    float a = klp[k], c = pis[k];
+#pragma unroll
+    for (int t = 16; t >= 1; t >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, t); c += __shfl_xor_sync(0xffffffffu, c, t); }
+    if (lane == 0) { red[k][warp] = a; red2[k][warp] = c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kFcBoards; ++k) {
+    if (k >= nb) continue;
+    float kl = 0.f, sp = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { kl += red[k][w]; sp += red2[k][w]; }
+    if (j < 225) p.dlogits[(size_t)(b0 + k) * 225 + j] = (prob[k] * sp - tgt[k]) * inv_b;
+    if (warp == k) {                        // value head of board k: warp k
+      float v = h1s[k][lane] * p.w2[lane] + h1s[k][lane + 32] * p.w2[lane + 32];
+#pragma unroll
+      for (int t = 16; t >= 1; t >>= 1) v += __shfl_xor_sync(0xffffffffu, v, t);
+      if (lane == 0) {
+        const float val = tanhf(v + p.b2[0]);
+        const float err = val - p.zt[b0 + k];
+        p.value[b0 + k] = val;
+        p.dvpre[b0 + k] = 2.f * err * inv_b * (1.f - val * val);
+        p.loss_parts[(size_t)(b0 + k) * 2] = kl;
+        p.loss_parts[(size_t)(b0 + k) * 2 + 1] = err * err;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// heads, backward
+// ------------------------------------------------------------------------------------------------
+// gradient at the head BatchNorm outputs (ReLU mask applied): one board per block
+__global__ void __launch_bounds__(512)
+head_fc_bwd_data_kernel(HeadTrainArgs p) {
+  __shared__ float dl[225];
+  __shared__ float dh1[64];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < 225) dl[tid] = p.dlogits[(size_t)b * 225 + tid];
+  if (tid >= 256 && tid < 320) {
+    const int t = tid - 256;
+    dh1[t] = p.h1[(size_t)b * 64 + t] > 0.f ? p.dvpre[b] * p.w2[t] : 0.f;
+  }
+  __syncthreads();
+  if (tid < 450) {
+    float acc = 0.f;
+    for (int jj = 0; jj < 225; ++jj) acc = fmaf(dl[jj], p.wp[(size_t)jj * 450 + tid], acc);
+    const size_t o = (size_t)b * 675 + tid;
+    p.dhid[o] = p.hidden[o] > 0.f ? acc : 0.f;
+  }
+  if (tid < 225) {
+    float acc = 0.f;
+    for (int t = 0; t < 64; ++t) acc = fmaf(dh1[t], p.wv1[(size_t)t * 225 + tid], acc);
+    const size_t o = (size_t)b * 675 + 450 + tid;
+    p.dhid[o] = p.hidden[o] > 0.f ? acc : 0.f;
+  }
+}
+
+// weight gradients of the dense layers: one thread per output element, loop over the batch (fixed order)
+__global__ void __launch_bounds__(256)
+head_fc_wgrad_kernel(HeadTrainArgs p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int B = p.n_boards;
+  constexpr int N_WP = 225 * 450, N_BP = 225, N_WV = 64 * 225, N_BV = 64, N_W2 = 64;
+  if (i < N_WP) {
+    const int j = i / 450, k = i % 450;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(p.dlogits[(size_t)b * 225 + j], p.hidden[(size_t)b * 675 + k], acc);
+    p.d_wp[i] = acc;
+    return;
+  }
+  int r = i - N_WP;
+  if (r < N_BP) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += p.dlogits[(size_t)b * 225 + r];
+    p.d_bp[r] = acc;
+    return;
+  }
+  r -= N_BP;
+  if (r < N_WV) {
+    const int t = r / 225, k = r % 225;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float d = p.h1[(size_t)b * 64 + t] > 0.f ? p.dvpre[b] * p.w2[t] : 0.f;
+      acc = fmaf(d, p.hidden[(size_t)b * 675 + 450 + k], acc);
+    }
+    p.d_wv1[r] = acc;
+    return;
+  }
+  r -= N_WV;
+  if (r < N_BV) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += p.h1[(size_t)b * 64 + r] > 0.f ? p.dvpre[b] * p.w2[r] : 0.f;
+    p.d_bv1[r] = acc;
+    return;
+  }
+  r -= N_BV;
+  if (r < N_W2) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(p.dvpre[b], p.h1[(size_t)b * 64 + r], acc);
+    p.d_w2[r] = acc;
+    return;
+  }
+  r -= N_W2;
+  if (r == 0) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += p.dvpre[b];
+    p.d_b2[0] = acc;
+  }
+}
+
+// head BatchNorm backward: one block per head channel
+__global__ void __launch_bounds__(1024)
+head_bn_bwd_kernel(HeadTrainArgs p) {
+  const int h = blockIdx.x;
+  const int n = p.n_boards * 225;
+  const float mean = p.hstats[h * 2], rstd = p.hstats[h * 2 + 1];
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const size_t o = (size_t)(i / 225) * 675 + h * 225 + i % 225;
+    const float dy = p.dhid[o];
+    s1 += dy;
+    s2 += (double)dy * ((p.zh[o] - mean) * rstd);
+  }
+  block_sum2(s1, s2);
+  const int which = h < 2 ? 0 : 1, ch = h < 2 ? h : 0;
+  const float gamma = p.bn_gamma[which][ch];
+  if (threadIdx.x == 0) { p.d_bn_gamma[which][ch] = (float)s2; p.d_bn_beta[which][ch] = (float)s1; }
+  const float m1 = (float)(s1 / n), m2 = (float)(s2 / n), k0 = gamma * rstd;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const size_t o = (size_t)(i / 225) * 675 + h * 225 + i % 225;
+    const float xh = (p.zh[o] - mean) * rstd;
+    p.dzh[o] = k0 * (p.dhid[o] - m1 - xh * m2);
+  }
+}
+
+// 1x1 convolutions backward: g[row][c] = sum_h dzh[h][row] * w1[h][c] (pad rows zero) and
+// dw1[h][c] = sum_rows dzh[h][row] * a[row][c] (block partials, last block adds them in order)
+template <int C>
+__global__ void __launch_bounds__(kEwThreads)
+head_conv_bwd_kernel(HeadTrainArgs p) {
+  constexpr int CG = C / 8, RL = kEwThreads / CG;
+  __shared__ float red[RL][3][C];
+  const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
+  float w[3][8], acc[3][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    w[0][i] = p.w1p[cg * 8 + i]; w[1][i] = p.w1p[C + cg * 8 + i]; w[2][i] = p.w1v[cg * 8 + i];
+    acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
+  }
+  const long long n_rows = (long long)p.n_boards * 256;
+  for (long long r = (long long)blockIdx.x * RL + rl; r < n_rows; r += (long long)gridDim.x * RL) {
+    const int qi = (int)(r & 255);
+    const size_t off = ((size_t)AZG_NET_FRONT + (size_t)r) * C + (size_t)cg * 8;
+    float g[8];
+    if (is_pad_row(qi)) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = 0.f;
+    } else {
+      const int pix = ((qi >> 4) - 1) * 15 + (qi & 15);
+      const float* d = p.dzh + (size_t)(r >> 8) * 675 + pix;
+      const float d0 = d[0], d1 = d[225], d2 = d[450];
+      float af[8];
+      unpack8(ptx::ldg128(p.act + off), af);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        g[i] = d0 * w[0][i] + d1 * w[1][i] + d2 * w[2][i];
+        acc[0][i] = fmaf(d0, af[i], acc[0][i]);
+        acc[1][i] = fmaf(d1, af[i], acc[1][i]);
+        acc[2][i] = fmaf(d2, af[i], acc[2][i]);
+      }
+    }
+    ptx::stg128(p.g + off, pack8(g));
+  }
+#pragma unroll
+  for (int h = 0; h < 3; ++h)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[rl][h][cg * 8 + i] = acc[h][i];
+  __syncthreads();
+  for (int t = threadIdx.x; t < 3 * C; t += kEwThreads) {
+    const int h = t / C, c = t % C;
+    float a = 0.f;
+#pragma unroll 4
+    for (int jx = 0; jx < RL; ++jx) a += red[jx][h][c];
+    p.partial[((size_t)blockIdx.x * 3 + h) * C + c] = a;
+  }
+  if (!last_block_arrives(p.counter)) return;
+  for (int t = threadIdx.x; t < 3 * C; t += kEwThreads) {
+    const int h = t / C, c = t % C;
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += (double)p.partial[((size_t)b * 3 + h) * C + c];
+    if (h < 2) p.d_w1p[h * C + c] = (float)s; else p.d_w1v[c] = (float)s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimiser
+// ------------------------------------------------------------------------------------------------
+// ||g / world||_2 over the flat gradient vector -> clip coefficient min(1, clip / (norm + 1e-6)) / world
+__global__ void __launch_bounds__(256)
+grad_norm_kernel(AdamArgs p) {
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const double g = (double)p.grads[i] * (double)p.inv_world;
+    s += g * g;
+  }
+  double dummy = 0.0;
+  block_sum2(s, dummy);
+  if (threadIdx.x == 0) p.norm_partial[blockIdx.x] = (float)s;
+  if (!last_block_arrives(p.counter)) return;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) tot += (double)p.norm_partial[b];
+    const float norm = (float)sqrt(tot);
+    float coef = p.clip / (norm + 1e-6f);
+    if (coef > 1.f) coef = 1.f;
+    p.scal[0] = coef * p.inv_world;
+    p.scal[1] = norm;
+    *p.step += 1;
+  }
+}
+
+// One block = 1024 consecutive elements of one segment.  update: Adam on the fp32 master copy; always: refresh the
+// bf16 tap-major convolution weights (forward and transposed / flipped for the input gradient) and the transposed
+// dense matrices from the (new) master values.
+__global__ void __launch_bounds__(256)
+adam_pack_kernel(AdamArgs p, int update) {
+  const int2 bs = p.block_seg[blockIdx.x];
+  const AdamSeg seg = p.segs[bs.x];
+  const int C = p.C;
+  float coef = 0.f, step_size = 0.f, inv_sqrt_bc2 = 0.f;
+  if (update) {
+    coef = p.scal[0];
+    const double t = (double)*p.step;
+    const double bc1 = 1.0 - pow((double)p.b1, t), bc2 = 1.0 - pow((double)p.b2, t);
+    step_size = (float)((double)p.lr / bc1);
+    inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = bs.y + u * 256 + threadIdx.x;         // element within the segment (parameter order)
+    if (e >= seg.count) continue;
+    int ge = e;                                          // element within the segment in GRADIENT order
+    int co = 0, ci = 0, tap = 0;
+    if (seg.kind == SEG_CONV3) {
+      co = e / (C * 9); ci = (e / 9) % C; tap = e % 9;
+      ge = (tap * C + co) * C + ci;                     // wgrad kernel layout [tap][co][ci]
+    } else if (seg.kind == SEG_STEM) {
+      ge = (e % 27) * C + e / 27;                       // stem wgrad layout [27][C]
+    }
+    const long long pi = seg.off + e;
+    float w = p.params[pi];
+    if (update) {
+      const float g = fmaf(p.grads[seg.off + ge], coef, p.wd * w);
+      const float m = p.b1 * p.m[pi] + (1.f - p.b1) * g;
+      const float v = p.b2 * p.v[pi] + (1.f - p.b2) * g * g;
+      p.m[pi] = m; p.v[pi] = v;
+      w -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + p.eps);
+      p.params[pi] = w;
+    }
+    if (seg.kind == SEG_CONV3) {
+      const __nv_bfloat16 wb16 = __float2bfloat16_rn(w);
+      p.wf[((size_t)(seg.layer * 9 + tap) * C + co) * C + ci] = wb16;
+      p.wb[((size_t)(seg.layer * 9 + (8 - tap)) * C + ci) * C + co] = wb16;
+    } else if (seg.kind == SEG_WP) {
+      p.wp_t[(size_t)(e % 450) * 225 + e / 450] = w;
+    } else if (seg.kind == SEG_WV1) {
+      p.wv1_t[(size_t)(e % 225) * 64 + e / 225] = w;
+    }
+  }
+}
+
+template <typename F>
+int dispatch_c(int C, F&& f) {
+  if (C == 64) return f(std::integral_constant<int, 64>{});
+  if (C == 128) return f(std::integral_constant<int, 128>{});
+  return azg_fail(AZG_E_ARG, "training kernels: channels must be 64 or 128");
+}
+
+int ew_grid(int n_boards, int C, int n_sm) {
+  const long long total = (long long)n_boards * 256 * (C / 8);
+  long long blocks = (total + kEwThreads - 1) / kEwThreads;
+  const long long cap = (long long)n_sm * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+int azg_bn_stats_launch(int C, const BnStatsArgs& a, cudaStream_t s) {
+  return dispatch_c(C, [&](auto c) {
+    constexpr int CC = decltype(c)::value;
+    int grid = a.n_boards * 256 / (kEwThreads / (CC / 8));
+    if (grid > AZG_TRAIN_PARTIALS) grid = AZG_TRAIN_PARTIALS;
+    if (grid < 1) grid = 1;
+    bn_stats_kernel<CC><<<grid, kEwThreads, 0, s>>>(a);
+    return azg_check_launch("bn_stats_kernel");
+  });
+}
+
+int azg_bn_apply_launch(int C, const BnApplyArgs& a, int n_sm, cudaStream_t s) {
+  return dispatch_c(C, [&](auto c) {
+    constexpr int CC = decltype(c)::value;
+    bn_apply_kernel<CC><<<ew_grid(a.n_boards, CC, n_sm), kEwThreads, 0, s>>>(a);
+    return azg_check_launch("bn_apply_kernel");
+  });
+}
+
+int azg_bn_bwd_reduce_launch(int C, const BnBwdArgs& a, cudaStream_t s) {
+  return dispatch_c(C, [&](auto c) {
+    constexpr int CC = decltype(c)::value;
+    int grid = a.n_boards * 256 / (kEwThreads / (CC / 8));
+    if (grid > AZG_TRAIN_PARTIALS) grid = AZG_TRAIN_PARTIALS;
+    if (grid < 1) grid = 1;
+    bn_bwd_reduce_kernel<CC><<<grid, kEwThreads, 0, s>>>(a);
+    return azg_check_launch("bn_bwd_reduce_kernel");
+  });
+}
+
+int azg_bn_bwd_apply_launch(int C, const BnBwdArgs& a, int n_sm, cudaStream_t s) {
+  return dispatch_c(C, [&](auto c) {
+    constexpr int CC = decltype(c)::value;
+    bn_bwd_apply_kernel<CC><<<ew_grid(a.n_boards, CC, n_sm), kEwThreads, 0, s>>>(a);
+    return azg_check_launch("bn_bwd_apply_kernel");
+  });
+}
+
+int azg_stem_train_fwd_launch(int C, const StemTrainArgs& a, cudaStream_t s) {
+  return dispatch_c(C, [&](auto c) {
+    constexpr int CC = decltype(c)::value;
+    stem_train_fwd_kernel<CC><<<a.n_boards < 1184 ? a.n_boards : 1184, 256, 0, s>>>(a);
+    return azg_check_launch("stem_train_fwd_kernel");
+  });
+}
+
+int azg_stem_train_wgrad_launch(int C, const StemTrainArgs& a, cudaStream_t s) {
+  int rc = dispatch_c(C, [&](auto c) {
+    constexpr int CC = decltype(c)::value;
+    stem_train_wgrad_kernel<CC><<<a.n_partial, CC, 0, s>>>(a);
+    return azg_check_launch("stem_train_wgrad_kernel");
+  });
+  if (rc) return rc;
+  return azg_reduce_partials_launch(a.partial, a.n_partial, 27 * C, a.dw, s);
+}
+
+int azg_reduce_partials_launch(const float* partial, int n_partial, int n, float* out, cudaStream_t s) {
+  reduce_partials_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, n_partial, n, out);
+  return azg_check_launch("reduce_partials_kernel");
+}
+
+int azg_head_train_fwd_launch(const HeadTrainArgs& a, int n_sm, cudaStream_t s) {
+  int rc = dispatch_c(a.C, [&](auto c) {
+    constexpr int CC = decltype(c)::value;
+    int grid = (a.n_boards * 225 + 7) / 8;
+    if (grid > n_sm * 8) grid = n_sm * 8;
+    head_conv_fwd_kernel<CC><<<grid, 256, 0, s>>>(a);
+    return azg_check_launch("head_conv_fwd_kernel");
+  });
+  if (rc) return rc;
+  head_bn_fwd_kernel<<<3, 1024, 0, s>>>(a);
+  if ((rc = azg_check_launch("head_bn_fwd_kernel"))) return rc;
+  head_fc_fwd_kernel<<<(a.n_boards + kFcBoards - 1) / kFcBoards, 256, 0, s>>>(a);
+  return azg_check_launch("head_fc_fwd_kernel");
+}
+
+int azg_head_train_bwd_launch(const HeadTrainArgs& a, int n_sm, cudaStream_t s) {
+  head_fc_bwd_data_kernel<<<a.n_boards, 512, 0, s>>>(a);
+  int rc = azg_check_launch("head_fc_bwd_data_kernel");
+  if (rc) return rc;
+  constexpr int n_out = 225 * 450 + 225 + 64 * 225 + 64 + 64 + 1;
+  head_fc_wgrad_kernel<<<(n_out + 255) / 256, 256, 0, s>>>(a);
+  if ((rc = azg_check_launch("head_fc_wgrad_kernel"))) return rc;
+  head_bn_bwd_kernel<<<3, 1024, 0, s>>>(a);
+  if ((rc = azg_check_launch("head_bn_bwd_kernel"))) return rc;
+  return dispatch_c(a.C, [&](auto c) {
+    constexpr int CC = decltype(c)::value;
+    int grid = a.n_boards * 256 / (kEwThreads / (CC / 8));
+    if (grid > AZG_TRAIN_PARTIALS) grid = AZG_TRAIN_PARTIALS;
+    if (grid < 1) grid = 1;
+    head_conv_bwd_kernel<CC><<<grid, kEwThreads, 0, s>>>(a);
+    return azg_check_launch("head_conv_bwd_kernel");
+  });
+}
+
+int azg_grad_norm_launch(const AdamArgs& a, cudaStream_t s) {
+  grad_norm_kernel<<<AZG_TRAIN_PARTIALS, 256, 0, s>>>(a);
+  return azg_check_launch("grad_norm_kernel");
+}
+
+int azg_adam_launch(const AdamArgs& a, bool update, cudaStream_t s) {
+  adam_pack_kernel<<<a.n_blocks, 256, 0, s>>>(a, update ? 1 : 0);
+  return azg_check_launch("adam_pack_kernel");
+}

@@ -9,8 +9,11 @@ snapshots load here and vice versa.
 ``predict`` (the search's leaf evaluator, network.py:168-183) is the hot path: it goes
 through ``azg_net_forward`` - folded BatchNorm, bf16 tensor-core trunk, fused heads - and
 raises if the CUDA library or a B200 is missing (no eager PyTorch fallback).
-``train_batch`` keeps the reference's loss and optimiser definitions and uses torch
-autograd on the same parameters (SURVEY 8f "next" row).
+``train_batch`` (network.py:199-235) runs in the CUDA library too: tensor-core
+forward / input-gradient / weight-gradient convolutions, training-mode BatchNorm, the reference's
+KLDiv + MSE loss, clip 3.0 and Adam on fp32 master weights (``trainer.TrainEngine``).  The torch
+autograd formulation of the same step is kept as ``train_batch_autograd`` (256-channel networks,
+which the training kernels do not cover, and the cross-check in the tests).
 """
 from __future__ import annotations
 
@@ -127,6 +130,8 @@ class PyTorchModel:
         self.policy_loss_fn = nn.KLDivLoss(reduction="batchmean")
         self._engine = None
         self._packed_version = None
+        self._trainer = None
+        self.train_graphs = os.environ.get("AZG_TRAIN_GRAPHS", "1") != "0"    # replay the training step from CUDA graphs
 
     # ------------------------------------------------------------------ CUDA inference engine
     def _ensure_engine(self):
@@ -178,9 +183,50 @@ class PyTorchModel:
         logits, values = self.net(states)
         return self.policy_loss_fn(F.log_softmax(logits, dim=1), target_pis), self.value_loss_fn(values, target_vs)
 
+    def _ensure_trainer(self, batch: int):
+        """The CUDA training engine for batches of up to ``batch`` positions (None for 256 channels)."""
+        if self.net.channels not in (64, 128):
+            return None
+        if self._trainer is None or self._trainer.max_batch < batch:
+            from .trainer import TrainEngine
+            if self._trainer is not None:
+                self._trainer.close()
+            self._trainer = TrainEngine(self.net, self.optimizer, max(int(batch), 32), self.device)
+        return self._trainer
+
+    def train_batch_async(self, states, target_pis, target_vs, world: int = 1, reduce_grads=None) -> torch.Tensor:
+        """One step of network.py:210-226 without a host synchronisation; returns the device tensor
+        [policy_loss, value_loss].  ``reduce_grads(flat_grads)`` (data-parallel training) is called between
+        the backward pass and the update and must leave the SUM over ``world`` ranks in the tensor."""
+        x, pi, z = self._to_device(states), self._to_device(target_pis), self._to_device(target_vs)
+        tr = self._ensure_trainer(x.shape[0])
+        if tr is None:
+            raise _lib.AzgError("the CUDA training step covers 64 and 128 channels; use train_batch_autograd")
+        self.net.train()
+        if self.train_graphs:
+            losses = tr.step_graph(x, pi, z, world, reduce_grads)
+        else:
+            losses = tr.forward_backward(x, pi, z)
+            if reduce_grads is not None:
+                reduce_grads(tr.flat_grads)
+            tr.apply(world)
+        self.invalidate()               # the kernels wrote the parameters: the inference engine must repack
+        return losses
+
     def train_batch(self, states, target_pis, target_vs, epochs: int = 1) -> dict:
-        """``epochs`` Adam steps on one batch: loss = KL + MSE, gradient norm clipped at 3.0.  Accepts numpy
-        arrays (as the reference) or device tensors (no host copy)."""
+        """``epochs`` Adam steps on one batch: loss = KL + MSE, gradient norm clipped at 3.0 (network.py:199-235).
+        Accepts numpy arrays (as the reference) or device tensors (no host copy)."""
+        if self.net.channels not in (64, 128):
+            return self.train_batch_autograd(states, target_pis, target_vs, epochs)
+        x, pi, z = self._to_device(states), self._to_device(target_pis), self._to_device(target_vs)
+        sums = torch.zeros(2, dtype=torch.float32, device=x.device)
+        for _ in range(epochs):
+            sums += self.train_batch_async(x, pi, z)
+        p, v = (sums / float(epochs)).tolist()          # the only host synchronisation of the call
+        return {"policy_loss": p, "value_loss": v, "total_loss": p + v}
+
+    def train_batch_autograd(self, states, target_pis, target_vs, epochs: int = 1) -> dict:
+        """The same step through torch autograd (library kernels)."""
         self.net.train()
         x, pi, z = self._to_device(states), self._to_device(target_pis), self._to_device(target_vs)
         sums = np.zeros(3)
@@ -192,6 +238,7 @@ class PyTorchModel:
             torch.nn.utils.clip_grad_norm_(self.net.parameters(), 3.0)
             self.optimizer.step()
             sums += (float(policy_loss.item()), float(value_loss.item()), float(total.item()))
+        self.invalidate()
         p, v, t = (sums / float(epochs)).tolist()
         return {"policy_loss": p, "value_loss": v, "total_loss": t}
 

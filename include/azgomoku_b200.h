@@ -227,6 +227,65 @@ int azg_net_profile_counters(azg_net* n, uint64_t* out32);
 /* Synchronise and report the tcgen05 pipeline watchdog (0 = healthy). */
 int azg_net_check(azg_net* n, void* stream);
 
+/* ------------------------------------------------------------------ training step
+ * Replaces PyTorchModel.train_batch (network.py:199-235): training-mode forward (BatchNorm2d batch statistics,
+ * running statistics updated with momentum 0.1), loss = KLDivLoss(batchmean)(log_softmax(logits), pi) +
+ * MSELoss(value, z), backward, clip_grad_norm_(3.0), Adam(lr, weight_decay).  3x3 convolutions forward /
+ * input gradient / weight gradient run on tcgen05 tensor cores (bf16 operands, fp32 accumulation); master
+ * weights, gradients and Adam moments are fp32.  Tolerance against the fp32 reference step is stated and
+ * tested in tests/test_train_gpu.py.
+ * The parameter vector is FLAT, in net.parameters() order (network.py:47-73): conv.weight, bn.weight, bn.bias,
+ * per residual block conv1.weight, bn1.weight, bn1.bias, conv2.weight, bn2.weight, bn2.bias, then
+ * policy_conv.weight, policy_bn.{weight,bias}, policy_fc.{weight,bias}, value_conv.weight,
+ * value_bn.{weight,bias}, value_fc1.{weight,bias}, value_fc2.{weight,bias}. */
+typedef struct azg_train azg_train;
+typedef struct azg_train_config {
+  int32_t device;
+  int32_t n_blocks;
+  int32_t channels;        /* 64 or 128 */
+  int32_t max_batch;       /* positions per step the activation buffers hold */
+  double lr;               /* Adam, network.py:141 defaults: 1e-3 */
+  double weight_decay;     /* 1e-4, added to the gradient (torch.optim.Adam) */
+  double beta1, beta2, eps;/* 0.9, 0.999, 1e-8 */
+  double clip;             /* clip_grad_norm_ max_norm, network.py:224: 3.0 */
+  double bn_momentum;      /* 0.1 */
+  double bn_eps;           /* 1e-5 */
+} azg_train_config;
+
+int azg_train_create(const azg_train_config* cfg, azg_train** out);
+int azg_train_destroy(azg_train* t);
+/* Number of floats of the flat parameter / gradient / moment vectors. */
+int64_t azg_train_param_count(const azg_train* t);
+int64_t azg_train_memory_bytes(const azg_train* t);
+/* Attach the caller-owned flat device vectors (float32[param_count] each) and the BatchNorm running statistics
+ * (only the running_mean / running_var entries of `stats` are read; they are UPDATED by every step).
+ * `step` is the number of Adam steps already taken (bias correction). */
+int azg_train_bind(azg_train* t, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                   const azg_net_weights* stats, int64_t step, void* stream);
+/* Refresh the bf16 / transposed weight copies after the parameters were changed from outside. */
+int azg_train_pack(azg_train* t, void* stream);
+/* network.py:210-223: planes float32[count][3][15][15], pis float32[count][225], zs float32[count] ->
+ * gradients of the summed loss in the bound gradient vector; loss_parts float32[count][2] = per position
+ * {KL row sum, squared value error} (policy_loss = sum / count, value_loss = sum / count). */
+int azg_train_forward_backward(azg_train* t, const float* planes, const float* pis, const float* zs, int count,
+                               float* loss_parts, void* stream);
+/* network.py:224-225: clip_grad_norm_ + Adam.step on the bound vectors.  world > 1: the gradient vector holds
+ * the SUM over `world` ranks (all-reduced by the caller between the two calls) and is averaged first. */
+int azg_train_apply(azg_train* t, int world, void* stream);
+/* Synchronise; fails if a tcgen05 pipeline watchdog fired.  out_host (may be NULL) receives
+ * {gradient norm before clipping, clip coefficient, Adam steps taken}. */
+int azg_train_check(azg_train* t, double* out_host, void* stream);
+/* Test hooks: activations of the last forward_backward as float32[count][C][15][15] (what: 0 = after
+ * BatchNorm+ReLU, 1 = convolution output; layer 0 = stem ... 2*n_blocks; 2 = gradient at the stem output,
+ * 3 = last dL/dz), and the gradient vector rearranged to the parameter layout (what p.grad would hold). */
+int azg_train_read_activation(azg_train* t, int what, int layer, float* out, void* stream);
+int azg_train_export_grads(azg_train* t, float* out, void* stream);
+/* The two tensor-core gradient kernels in isolation (test hook): dz, a float32[count][C][15][15] (rounded to bf16),
+ * current weights of trunk layer `layer` -> dw_out float32[C][C][3][3] (weight gradient), da_out
+ * float32[count][C][15][15] (input gradient, bf16-rounded).  Overwrites activation scratch only. */
+int azg_train_debug_conv_grads(azg_train* t, const float* dz, const float* a, int count, int layer, float* dw_out,
+                               float* da_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,19 +2,21 @@
 
 The reference (shirongcan/AlphaZero-Gomoku) is pure Python, so "building" it means byte-compiling
 the modules of the hot path from the sources where they lie under ``/root/reference`` into
-source-less ``.pyc`` files:
+source-less byte-code files (extension ``.refbin``: snapshot tools tend to drop ``*.pyc``):
 
-    python -m oracle.build_ref            # writes oracle/_ref/{network,train}.pyc, games/*.pyc, mcts/*.pyc
+    python -m oracle.build_ref            # writes oracle/_ref/{network,train}.refbin, games/*.refbin, mcts/*.refbin
 
 No reference source is copied into the repository: ``oracle/_ref/`` holds compiler output only,
 is listed in ``.gitignore`` (never in history) and not in ``.gpurunignore`` (it travels to the GPU
 box like the built ``.so``).  ``bench.py --impl reference`` and ``bench.py``'s ``cpu_baseline`` leg
-put ``oracle/_ref`` on ``sys.path`` and run the reference's own ``MCTS``, ``PyTorchModel`` and
+import those modules under their reference names (``activate()``) and run the reference's own ``MCTS``, ``PyTorchModel`` and
 ``play_game_and_collect`` (``cpu_baseline.kind`` = "reference"); when the directory is missing
 they fall back to the oracle port (kind "port").  Nothing in the product package reads it.
 """
 from __future__ import annotations
 
+import importlib.machinery
+import importlib.util
 import os
 import py_compile
 import sys
@@ -26,8 +28,15 @@ MODULES = ("games/__init__.py", "games/gomoku.py", "games/pente.py", "mcts/__ini
            "network.py", "train.py")
 
 
+EXT = ".refbin"
+
+
+def _out(m: str) -> str:
+    return os.path.join(OUT, m[:-3] + EXT)
+
+
 def available() -> bool:
-    return all(os.path.exists(os.path.join(OUT, m + "c")) for m in MODULES)
+    return all(os.path.exists(_out(m)) for m in MODULES)
 
 
 def build(reference: str = "/root/reference", quiet: bool = False) -> bool:
@@ -37,7 +46,7 @@ def build(reference: str = "/root/reference", quiet: bool = False) -> bool:
         return available()
     for m in MODULES:
         src = os.path.join(reference, m)
-        dst = os.path.join(OUT, m + "c")
+        dst = _out(m)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         # dfile keeps reference-relative file names in tracebacks; unchecked-hash pycs never look for a source file
         py_compile.compile(src, cfile=dst, dfile=m, doraise=True, invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
@@ -47,11 +56,24 @@ def build(reference: str = "/root/reference", quiet: bool = False) -> bool:
 
 
 def activate() -> bool:
-    """Put oracle/_ref first on sys.path (the reference imports its modules by top-level name)."""
+    """Make the byte-compiled reference importable under its own top-level names (``games.gomoku``,
+    ``mcts.new_mcts_alpha``, ``network``, ``train`` - the reference imports its modules that way)."""
     if not available():
         return False
-    if OUT not in sys.path:
-        sys.path.insert(0, OUT)
+    for m in MODULES:
+        name = m[:-3].replace("/", ".")
+        is_pkg = name.endswith(".__init__")
+        if is_pkg:
+            name = name[:-9]
+        if name in sys.modules:
+            continue
+        loader = importlib.machinery.SourcelessFileLoader(name, _out(m))
+        spec = importlib.util.spec_from_loader(name, loader, is_package=is_pkg)
+        mod = importlib.util.module_from_spec(spec)
+        if is_pkg:
+            mod.__path__ = [os.path.dirname(_out(m))]
+        sys.modules[name] = mod
+        loader.exec_module(mod)
     return True
 
 

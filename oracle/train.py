@@ -28,6 +28,20 @@ def param_names(sd):
     return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"))]
 
 
+class _Bf16RoundTrip(torch.autograd.Function):
+    """Round to bfloat16 and back in the forward AND in the backward pass: the storage format of the CUDA step's
+    activations (z, a) and activation gradients (dz, g).  Used by the "emulated" oracle, which separates what
+    bf16 storage does to a gradient from what a kernel bug would do."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
 def _bn_train(x, sd, name, stats):
     y = F.batch_norm(x, None, None, sd[name + ".weight"], sd[name + ".bias"], True, 0.0, BN_EPS)
     with torch.no_grad():
@@ -37,15 +51,24 @@ def _bn_train(x, sd, name, stats):
     return y
 
 
-def forward_train(sd, x, stats):
-    """Training-mode forward (network.py:94-117 with module.training = True)."""
-    h = F.relu(_bn_train(F.conv2d(x, sd["conv.weight"], padding=1), sd, "bn", stats))
+def forward_train(sd, x, stats, record=None, emulate_bf16=False):
+    """Training-mode forward (network.py:94-117 with module.training = True).  ``record`` (a list) receives the
+    activation after every 3x3 layer's BatchNorm + ReLU (stem first), for layer-by-layer checks.
+    ``emulate_bf16``: store what the CUDA step stores in bfloat16 (trunk conv weights, conv outputs, activations,
+    and - in the backward pass - their gradients); everything else stays fp32 as in the CUDA step."""
+    keep = (lambda t: record.append(t)) if record is not None else (lambda t: None)
+    q = _Bf16RoundTrip.apply if emulate_bf16 else (lambda t: t)
+    qw = (lambda w: w + (w.to(torch.bfloat16).to(torch.float32) - w).detach()) if emulate_bf16 else (lambda w: w)
+    h = q(F.relu(_bn_train(q(F.conv2d(x, sd["conv.weight"], padding=1)), sd, "bn", stats)))
+    keep(h)
     i = 0
     while f"res_blocks.{i}.conv1.weight" in sd:
         pre = f"res_blocks.{i}."
-        t = F.relu(_bn_train(F.conv2d(h, sd[pre + "conv1.weight"], padding=1), sd, pre + "bn1", stats))
-        t = _bn_train(F.conv2d(t, sd[pre + "conv2.weight"], padding=1), sd, pre + "bn2", stats)
-        h = F.relu(t + h)
+        t = q(F.relu(_bn_train(q(F.conv2d(h, qw(sd[pre + "conv1.weight"]), padding=1)), sd, pre + "bn1", stats)))
+        keep(t)
+        t = _bn_train(q(F.conv2d(t, qw(sd[pre + "conv2.weight"]), padding=1)), sd, pre + "bn2", stats)
+        h = q(F.relu(t + h))
+        keep(h)
         i += 1
     p = F.relu(_bn_train(F.conv2d(h, sd["policy_conv.weight"]), sd, "policy_bn", stats))
     logits = F.linear(p.reshape(p.shape[0], -1), sd["policy_fc.weight"], sd["policy_fc.bias"])
@@ -62,12 +85,12 @@ def losses(logits, value, pi, z):
     return kl, mse
 
 
-def gradients(sd, x, pi, z):
+def gradients(sd, x, pi, z, record=None, emulate_bf16=False):
     """-> (policy_loss, value_loss, {name: grad}, bn batch statistics) without touching ``sd``."""
     names = param_names(sd)
     work = {k: (v.detach().clone().to(torch.float32).requires_grad_(k in names) if v.dtype.is_floating_point else v) for k, v in sd.items()}
     stats = {}
-    logits, value = forward_train(work, x, stats)
+    logits, value = forward_train(work, x, stats, record, emulate_bf16)
     kl, mse = losses(logits, value, pi, z)
     (kl + mse).backward()
     return float(kl.detach()), float(mse.detach()), {k: work[k].grad.detach() for k in names}, stats

@@ -86,6 +86,8 @@ PROTOTYPES = {
     "azg_selfplay_noise": (_I, [_P, C.c_uint64, _P]),
     "azg_selfplay_choose": (_I, [_P, _P, C.c_float, C.c_uint64, _P]),
     "azg_selfplay_finish": (_I, [_P, _P, _I, _I, _P, C.c_int64, _P, _P, _P]),
+    "azg_selfplay_finish_packed": (_I, [_P, _P, _I, _P, C.c_int64, _P, _P, _P]),
+    "azg_examples_expand": (_I, [_P, C.c_int64, _I, _P, _P]),
     "azg_net_create": (_I, [_I, _I, _I, _I, C.POINTER(_P)]),
     "azg_net_destroy": (_I, [_P]),
     "azg_net_memory_bytes": (C.c_int64, [_P]),

@@ -26,7 +26,11 @@ struct ConvArgs {
   int* error;                     // device flag set by the pipeline watchdogs
   unsigned long long* prof;       // optional device counters [16] (cycles spent waiting per role), or null
   int prof_detail;                // also clock the phases of one epilogue warp (slightly intrusive)
+  float* stat_partial;            // training forward: [2 * C][AZG_CONV_STAT_SLOTS] per-channel sum / sum of squares of the
+                                  // outputs, one slot per epilogue warp (azg_conv3x3_stat_slots of them are written); null = off
 };
+#define AZG_CONV_STAT_SLOTS 1184   // 74 clusters x 2 CTAs x 4 quadrants x 2 epilogue groups
+int azg_conv3x3_stat_slots(int max_boards, int n_sm, int C);
 
 // mode: activation staging variant of the kernel (see net_conv.cu); tm_act must have been encoded
 // with box rows = azg_conv3x3_rows(mode).

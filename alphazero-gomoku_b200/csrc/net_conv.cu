@@ -87,7 +87,22 @@ struct HeadConst {
 
 enum { ERR_BFULL = 1, ERR_EMPTY = 2, ERR_FULL = 3, ERR_TEMPTY = 4, ERR_TFULL = 5 };
 
-template <int C, bool HEADS, int MODE>
+// Sum over the 32 lanes (rows) of each of 32 per-lane values (channels): afterwards lane L holds the total of v[L]
+// in v[0].  31 shuffles: in every round a lane hands half of its values to its partner and adds the partner's.
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? v[i] : v[i + s];
+      const float keep = upper ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
+template <int C, bool HEADS, int MODE, bool STATS = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(conv_threads<C>(), 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
                     const __grid_constant__ CUtensorMap tm_out, ConvArgs p,
@@ -285,6 +300,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     int it = 0;
     bool ok = true;
     long long t_tfull = 0, t_wr = 0, t_rt = 0, t_ld = 0, t_cs = 0, t_st = 0;
+    // STATS (training forward): per-channel sum and sum of squares of the bf16-rounded outputs, accumulated by this
+    // warp over all its boards (lane = channel within a 32-channel chunk) and left in stat_partial at the end
+    float st_sum[STATS ? (HEADS ? C : C / 2) / 32 : 1], st_sq[STATS ? (HEADS ? C : C / 2) / 32 : 1];
+    if constexpr (STATS) {
+#pragma unroll
+      for (int c = 0; c < (HEADS ? C : C / 2) / 32; ++c) st_sum[c] = st_sq[c] = 0.f;
+    }
     const bool detail = p.prof != nullptr && p.prof_detail != 0;      // per-phase clocks only on request (AZG_CONV_PHASES=1)
     const float lo = p.relu ? 0.f : -INFINITY;       // relu == 0: linear output (training: pre-BatchNorm z, input gradients)
     const long long t_begin = clock64();
@@ -386,6 +408,18 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
           using IH = std::integral_constant<int, HEADS ? 0 : C / 2>;
           if (!HEADS && half) { if (has_res) math(IH{}, std::true_type{}); else math(IH{}, std::false_type{}); }
           else { if (has_res) math(I0{}, std::true_type{}); else math(I0{}, std::false_type{}); }
+          if constexpr (STATS) {
+            float zs[32], zq[32];
+#pragma unroll
+            for (int h = 0; h < 16; ++h) {
+              zs[2 * h] = __uint_as_float(outv[h] << 16); zs[2 * h + 1] = __uint_as_float(outv[h] & 0xffff0000u);
+              zq[2 * h] = zs[2 * h] * zs[2 * h]; zq[2 * h + 1] = zs[2 * h + 1] * zs[2 * h + 1];
+            }
+            warp_transpose_sum(zs, lane);
+            warp_transpose_sum(zq, lane);
+            st_sum[c] += zs[0];
+            st_sq[c] += zq[0];
+          }
           if constexpr (HEADS) {
             // the heads see the bf16-rounded activations, exactly like the unfused path
 #pragma unroll
@@ -445,6 +479,17 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
     }
+    if constexpr (STATS) {
+      // slot = one epilogue warp's share of the rows: (cluster, CTA, quadrant[, group]); channel = ch0 + 32 c + lane
+      const int slot = ((cid * 2 + (int)rank) * 4 + quad) * EG + grp;
+      if (working) {
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          p.stat_partial[(size_t)(ch0 + 32 * c + lane) * AZG_CONV_STAT_SLOTS + slot] = st_sum[c];
+          p.stat_partial[(size_t)(C + ch0 + 32 * c + lane) * AZG_CONV_STAT_SLOTS + slot] = st_sq[c];
+        }
+      }
+    }
     if (TMA_OUT && lane == 0) ptx::bulk_wait0();            // all stores of this warp have landed before the CTA exits
     if (p.prof && rank == 0 && warp == 2 && lane == 0) {   // one representative epilogue warp
       atomicAdd(p.prof + 5, (unsigned long long)t_tfull);
@@ -463,11 +508,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   if (warp == 1) ptx::tmem_dealloc<2>(tmem_base, K::TMEM_COLS);
 }
 
-template <int C, bool HEADS, int MODE>
+template <int C, bool HEADS, int MODE, bool STATS = false>
 int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtensorMap& tm_out, const ConvArgs& args, int n_sm,
                 cudaStream_t stream) {
   using K = Cfg<C, MODE>;
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<C, HEADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<C, HEADS, MODE, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
   int grid = n_sm & ~1;
   const int want = 2 * args.max_boards;
@@ -495,7 +540,7 @@ int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtens
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<C, HEADS, MODE>, tm_act, tm_w, tm_out, args, shift, head);
+  e = cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<C, HEADS, MODE, STATS>, tm_act, tm_w, tm_out, args, shift, head);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
   return azg_check_launch("conv3x3_pair_kernel");
 }
@@ -511,8 +556,21 @@ int launch_conv_heads(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const 
 
 int azg_conv3x3_rows(int mode) { return mode == 0 ? Stage<0>::ROWS : Stage<1>::ROWS; }
 
+int azg_conv3x3_stat_slots(int max_boards, int n_sm, int C) {
+  int grid = n_sm & ~1;
+  const int want = 2 * max_boards;
+  if (grid > want) grid = want < 2 ? 2 : want;
+  return grid * 4 * (C == 64 ? epi_groups<64>() : 1);
+}
+
 int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtensorMap& tm_out,
                        const ConvArgs& args, int n_sm, cudaStream_t stream) {
+  if (args.stat_partial) {          // training forward: per-channel output statistics in the epilogue
+    if (args.head_host) return azg_fail(AZG_E_ARG, "conv3x3: statistics and fused heads are separate variants");
+    if (C == 128 && mode == 1) return launch_conv<128, false, 1, true>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (C == 64 && mode == 3) return launch_conv<64, false, 3, true>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    return azg_fail(AZG_E_ARG, "conv3x3: the statistics epilogue is built for (128 channels, mode 1) and (64 channels, mode 3)");
+  }
   if (C == 128) {
     if (mode == 0) return launch_conv_heads<128, 0>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (mode == 1) return launch_conv_heads<128, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);

@@ -233,7 +233,7 @@ static int run_network(azg_net* n, StemArgs stem, const int* n_ptr, int max_boar
     }
   }
   for (int l = 0; l < n_layers; ++l) {
-    ConvArgs a;
+    ConvArgs a{};
     a.n_boards = n_ptr; a.max_boards = max_boards; a.layer = l; a.relu = 1;
     a.shift_host = n->shift_host.data() + (size_t)l * C; a.error = n->error_dev; a.prof = n->profiling ? n->prof_dev + 16 * (l & 1) : nullptr; a.prof_detail = n->prof_detail;   // [0..15] layers without, [16..31] with residual
     a.head_host = nullptr; a.hidden = nullptr;

@@ -180,10 +180,26 @@ __device__ __forceinline__ int sym_source(int k, int i, int j) {
   }
 }
 
+// One expanded row (901 floats: planes[3][225], pi[225], z) of symmetry s from a stored ply.
+__device__ __forceinline__ void write_example_row(float* __restrict__ o, const uint32_t* __restrict__ k, int player,
+                                                  const float* __restrict__ ppi, float z, int s) {
+  for (int a = threadIdx.x; a < AZG_A; a += blockDim.x) {
+    const int src = sym_source(s, a / AZG_N, a % AZG_N);
+    const uint32_t b1 = (k[src >> 5] >> (src & 31)) & 1u, b2 = (k[8 + (src >> 5)] >> (src & 31)) & 1u;
+    o[a] = (float)(player == 1 ? b1 : b2);
+    o[AZG_A + a] = (float)(player == 1 ? b2 : b1);
+    o[2 * AZG_A + a] = 1.0f;
+    o[3 * AZG_A + a] = ppi[src];
+  }
+  if (threadIdx.x == 0) o[900] = z;
+}
+
+// packed != 0: out is uint32[capacity][AZG_PACKED_WORDS], one row per PLY (stones 16 words, side to move, z bits,
+// pi[225], pad) - 976 bytes instead of 8 x 3604: what travels between GPUs; azg_examples_expand makes the rows.
 __global__ void __launch_bounds__(256)
 finish_games_kernel(azg_dev e, azg_selfplay_buf sp, const int32_t* __restrict__ status, int max_moves, int n_sym,
                     float* __restrict__ out, long long capacity, unsigned long long* __restrict__ cursor,
-                    int32_t* __restrict__ done_mask, int32_t* __restrict__ winners) {
+                    int32_t* __restrict__ done_mask, int32_t* __restrict__ winners, int packed) {
   const int g = blockIdx.x;
   if (g >= e.G) return;
   __shared__ long long s_base;
@@ -201,7 +217,7 @@ finish_games_kernel(azg_dev e, azg_selfplay_buf sp, const int32_t* __restrict__ 
   if (!over) return;
   const int won = st & 3;
   const int stored = plies < sp.max_plies ? plies : sp.max_plies;
-  const long long rows = (long long)stored * n_sym;
+  const long long rows = packed ? (long long)stored : (long long)stored * n_sym;
   if (threadIdx.x == 0) s_base = out ? (long long)atomicAdd(cursor, (unsigned long long)rows) : 0;
   __syncthreads();
   const long long base = s_base;
@@ -212,23 +228,36 @@ finish_games_kernel(azg_dev e, azg_selfplay_buf sp, const int32_t* __restrict__ 
       const float z = won == 0 ? 0.f : (won == player ? 1.f : -1.f);
       const uint32_t* k = sp.ex_key + slot * 16;
       const float* ppi = sp.ex_pi + slot * AZG_A;
+      if (packed) {
+        const long long row = base + i;
+        if (row >= capacity) continue;
+        uint32_t* o = reinterpret_cast<uint32_t*>(out) + row * AZG_PACKED_WORDS;
+        for (int a = threadIdx.x; a < AZG_PACKED_WORDS; a += blockDim.x)
+          o[a] = a < 16 ? k[a] : a == 16 ? (uint32_t)player : a == 17 ? __float_as_uint(z) : a < 18 + AZG_A ? __float_as_uint(ppi[a - 18]) : 0u;
+        continue;
+      }
       for (int s = 0; s < n_sym; ++s) {
         const long long row = base + (long long)i * n_sym + s;
         if (row >= capacity) continue;
-        float* o = out + row * 901;
-        for (int a = threadIdx.x; a < AZG_A; a += blockDim.x) {
-          const int src = sym_source(s, a / AZG_N, a % AZG_N);
-          const uint32_t b1 = (k[src >> 5] >> (src & 31)) & 1u, b2 = (k[8 + (src >> 5)] >> (src & 31)) & 1u;
-          o[a] = (float)(player == 1 ? b1 : b2);
-          o[AZG_A + a] = (float)(player == 1 ? b2 : b1);
-          o[2 * AZG_A + a] = 1.0f;
-          o[3 * AZG_A + a] = ppi[src];
-        }
-        if (threadIdx.x == 0) o[900] = z;
+        write_example_row(out + row * 901, k, player, ppi, z, s);
       }
     }
   }
   if (threadIdx.x == 0) { sp.n_plies[g] = 0; sp.n_done[g] += 1; }
+}
+
+// packed plies -> example rows (train.py:392-410 on the receiving side of the exchange): block = one ply
+__global__ void __launch_bounds__(256)
+expand_examples_kernel(const uint32_t* __restrict__ packed, long long n, int n_sym, float* __restrict__ out) {
+  const long long i = blockIdx.x;
+  if (i >= n) return;
+  __shared__ uint32_t row[AZG_PACKED_WORDS];
+  for (int a = threadIdx.x; a < AZG_PACKED_WORDS; a += blockDim.x) row[a] = packed[i * AZG_PACKED_WORDS + a];
+  __syncthreads();
+  const int player = (int)row[16];
+  const float z = __uint_as_float(row[17]);
+  const float* ppi = reinterpret_cast<const float*>(row + 18);
+  for (int s = 0; s < n_sym; ++s) write_example_row(out + (i * n_sym + s) * 901, row, player, ppi, z, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -279,6 +308,23 @@ extern "C" int azg_selfplay_finish(azg_engine* e, const int32_t* status, int max
   if (!e || !status || !done_mask || !e->sp.ex_key || (out && !cursor)) return azg_fail(AZG_E_ARG, "azg_selfplay_finish: bad argument");
   AZG_USE_DEVICE(e->cfg.device);
   finish_games_kernel<<<e->dev.G, 256, 0, e->stream>>>(e->dev, e->sp, status, max_moves, use_symmetries ? 8 : 1, out,
-                                                        (long long)capacity, (unsigned long long*)cursor, done_mask, winners);
+                                                        (long long)capacity, (unsigned long long*)cursor, done_mask, winners, 0);
   return azg_check_launch("finish_games_kernel");
+}
+
+extern "C" int azg_selfplay_finish_packed(azg_engine* e, const int32_t* status, int max_moves, uint32_t* out, int64_t capacity,
+                                          uint64_t* cursor, int32_t* done_mask, int32_t* winners) {
+  if (!e || !status || !done_mask || !e->sp.ex_key || (out && !cursor)) return azg_fail(AZG_E_ARG, "azg_selfplay_finish_packed: bad argument");
+  AZG_USE_DEVICE(e->cfg.device);
+  finish_games_kernel<<<e->dev.G, 256, 0, e->stream>>>(e->dev, e->sp, status, max_moves, 1, reinterpret_cast<float*>(out),
+                                                        (long long)capacity, (unsigned long long*)cursor, done_mask, winners, 1);
+  return azg_check_launch("finish_games_kernel");
+}
+
+extern "C" int azg_examples_expand(const uint32_t* packed, int64_t n, int use_symmetries, float* out, void* stream) {
+  if (n < 0 || (n > 0 && (!packed || !out))) return azg_fail(AZG_E_ARG, "azg_examples_expand: bad argument");
+  if (n == 0) return AZG_OK;
+  if (n > 0x7fffffffLL) return azg_fail(AZG_E_ARG, "azg_examples_expand: too many rows for one call");
+  expand_examples_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(packed, (long long)n, use_symmetries ? 8 : 1, out);
+  return azg_check_launch("expand_examples_kernel");
 }

@@ -3,13 +3,13 @@
 #pragma once
 #include "net.h"
 
-#define AZG_TRAIN_PARTIALS 128        // blocks of the per-channel reduction kernels (partials reduced by the last block)
+#define AZG_TRAIN_PARTIALS 160        // max blocks of the per-channel reduction kernels (about one per SM); partial[output][block]
 
 // ---- trunk BatchNorm, training mode (batch statistics over boards x 225 pixels) -------------------------------------
 struct BnStatsArgs {
   const __nv_bfloat16* z;             // conv output, padded layout (pad rows are zero)
   int n_boards;
-  float* partial;                     // [AZG_TRAIN_PARTIALS][2][C] scratch
+  float* partial;                     // [2][C][AZG_TRAIN_PARTIALS] scratch
   unsigned* counter;                  // last-block ticket (zero before the launch, zero again after it)
   float* stats;                       // out [2][C]: batch mean, 1/sqrt(biased var + eps)
   float* running_mean;                // module buffers, updated as nn.BatchNorm2d does (momentum, unbiased variance)
@@ -17,6 +17,8 @@ struct BnStatsArgs {
   float momentum, eps;
 };
 int azg_bn_stats_launch(int C, const BnStatsArgs& a, cudaStream_t s);
+// statistics already summed per epilogue warp by the convolution (ConvArgs::stat_partial = a.partial, n_slots valid slots)
+int azg_bn_finalize_launch(int C, const BnStatsArgs& a, int n_slots, cudaStream_t s);
 
 struct BnApplyArgs {
   const __nv_bfloat16* z;
@@ -36,7 +38,7 @@ struct BnBwdArgs {
   const float* stats;                 // [2][C] batch mean, rstd
   const float* gamma;
   int n_boards;
-  float* partial;                     // [AZG_TRAIN_PARTIALS][2][C]
+  float* partial;                     // [2 * C][AZG_TRAIN_PARTIALS]
   unsigned* counter;
   float* sums;                        // [2][C]: sum dy, sum dy * x_hat   (reduce writes, apply reads)
   float* dgamma;                      // gradient outputs (reduce writes)
@@ -54,14 +56,11 @@ struct StemTrainArgs {
   int n_boards;
   __nv_bfloat16* z;                   // forward out: conv output, padded layout
   const __nv_bfloat16* dz;            // backward in
-  float* partial;                     // [blocks][27][C]
-  int n_partial;                      // blocks of the wgrad kernel
-  float* dw;                          // out [27][C] (plane*9 + tap major, channel minor)
+  float* partial;                     // [n_boards][27][C] scratch
+  float* dw;                          // out [27][C] (plane*9 + tap major, channel minor), accumulated with atomics: zero it first
 };
 int azg_stem_train_fwd_launch(int C, const StemTrainArgs& a, cudaStream_t s);
 int azg_stem_train_wgrad_launch(int C, const StemTrainArgs& a, cudaStream_t s);
-// out[i] = sum over p < n_partial of partial[p][i], fixed order (deterministic)
-int azg_reduce_partials_launch(const float* partial, int n_partial, int n, float* out, cudaStream_t s);
 
 // ---- heads + loss (network.py:102-117, 217-222) -----------------------------------------------------------------------
 struct HeadTrainArgs {
@@ -94,8 +93,8 @@ struct HeadTrainArgs {
   float* dvpre;                       // [n]
   float* loss_parts;                  // [n][2]: KL row sum, squared value error (caller sums / n)
   float* dhid;                        // [n][675] gradient at the head BatchNorm outputs, ReLU mask applied
-  float* dzh;                         // [n][3][225]
-  float* partial;                     // [AZG_TRAIN_PARTIALS][3][C]
+  float* hsums;                       // [3][2]: sum dy, sum dy * x_hat of the head BatchNorms
+  float* partial;                     // [3 * C][AZG_TRAIN_PARTIALS]
   unsigned* counter;
   __nv_bfloat16* g;                   // out: dL/da_L, padded layout
   // gradients (flat-buffer slices)

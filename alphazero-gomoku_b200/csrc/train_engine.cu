@@ -66,9 +66,10 @@ struct azg_train {
   CUtensorMap tm_dz_in, tm_dz_wg, tm_g_st[2], tm_wf, tm_wb;
   __nv_bfloat16 *wf = nullptr, *wb = nullptr;
   float *wp_t = nullptr, *wv1_t = nullptr;
-  float *stats = nullptr, *sums = nullptr, *partial = nullptr, *stem_partial = nullptr;
+  float *stats = nullptr, *sums = nullptr, *partial = nullptr, *stem_partial = nullptr, *conv_stat = nullptr;
+  int fuse_stats = 1;
   float *zh = nullptr, *hstats = nullptr, *hidden = nullptr, *h1 = nullptr, *value = nullptr, *dlogits = nullptr, *dvpre = nullptr,
-        *dhid = nullptr, *dzh = nullptr, *norm_partial = nullptr, *scal = nullptr;
+        *dhid = nullptr, *hsums = nullptr, *norm_partial = nullptr, *scal = nullptr;
   unsigned* counters = nullptr;
   long long* step_dev = nullptr;
   int *n_dev = nullptr, *error_dev = nullptr, *pinned = nullptr;
@@ -108,9 +109,9 @@ extern "C" int azg_train_destroy(azg_train* t) {
   for (auto p : t->a) cudaFree(p);
   for (auto p : t->z) cudaFree(p);
   cudaFree(t->g[0]); cudaFree(t->g[1]); cudaFree(t->dz); cudaFree(t->gskip); cudaFree(t->wf); cudaFree(t->wb);
-  cudaFree(t->wp_t); cudaFree(t->wv1_t); cudaFree(t->stats); cudaFree(t->sums); cudaFree(t->partial); cudaFree(t->stem_partial);
+  cudaFree(t->wp_t); cudaFree(t->wv1_t); cudaFree(t->stats); cudaFree(t->sums); cudaFree(t->partial); cudaFree(t->stem_partial); cudaFree(t->conv_stat);
   cudaFree(t->zh); cudaFree(t->hstats); cudaFree(t->hidden); cudaFree(t->h1); cudaFree(t->value); cudaFree(t->dlogits);
-  cudaFree(t->dvpre); cudaFree(t->dhid); cudaFree(t->dzh); cudaFree(t->norm_partial); cudaFree(t->scal); cudaFree(t->counters);
+  cudaFree(t->dvpre); cudaFree(t->dhid); cudaFree(t->hsums); cudaFree(t->norm_partial); cudaFree(t->scal); cudaFree(t->counters);
   cudaFree(t->step_dev); cudaFree(t->n_dev); cudaFree(t->error_dev); cudaFree(t->segs_dev); cudaFree(t->block_seg_dev);
   if (t->pinned) cudaFreeHost(t->pinned);
   delete t;
@@ -136,6 +137,7 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   cudaDeviceGetAttribute(&t->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
   t->conv_mode = t->C == 64 ? 3 : 1;
   { const char* v = getenv("AZG_WGRAD_DESC"); t->wgrad_variant = v ? atoi(v) : 0; }
+  { const char* v = getenv("AZG_TRAIN_FUSE_STATS"); t->fuse_stats = v ? atoi(v) : 1; }     // 0: separate statistics pass over z (experiment switch)
   const int C = t->C, L = t->L, B = t->max_batch;
   layout_params(t->lay, C, L);
   t->rows = AZG_NET_FRONT + (size_t)B * 256 + AZG_NET_BACK;
@@ -155,7 +157,8 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   if (!rc) rc = talloc(t, &t->stats, (size_t)(L + 1) * 2 * C);
   if (!rc) rc = talloc(t, &t->sums, (size_t)2 * C);
   if (!rc) rc = talloc(t, &t->partial, (size_t)AZG_TRAIN_PARTIALS * 3 * C);
-  if (!rc) rc = talloc(t, &t->stem_partial, (size_t)t->n_stem_partial * 27 * C);
+  if (!rc) rc = talloc(t, &t->stem_partial, (size_t)B * 27 * C);
+  if (!rc) rc = talloc(t, &t->conv_stat, (size_t)2 * C * AZG_CONV_STAT_SLOTS);
   if (!rc) rc = talloc(t, &t->zh, (size_t)B * 675);
   if (!rc) rc = talloc(t, &t->hstats, (size_t)8);
   if (!rc) rc = talloc(t, &t->hidden, (size_t)B * 675);
@@ -164,7 +167,7 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   if (!rc) rc = talloc(t, &t->dlogits, (size_t)B * 225);
   if (!rc) rc = talloc(t, &t->dvpre, (size_t)B);
   if (!rc) rc = talloc(t, &t->dhid, (size_t)B * 675);
-  if (!rc) rc = talloc(t, &t->dzh, (size_t)B * 675);
+  if (!rc) rc = talloc(t, &t->hsums, (size_t)8);
   if (!rc) rc = talloc(t, &t->norm_partial, (size_t)AZG_TRAIN_PARTIALS);
   if (!rc) rc = talloc(t, &t->scal, (size_t)4);
   if (!rc) rc = talloc(t, &t->counters, (size_t)8);
@@ -268,7 +271,7 @@ static HeadTrainArgs head_args(azg_train* t, int count, const float* pi, const f
   h.wp = t->params + l.policy_fc_w; h.wv1 = t->params + l.value_fc1_w;
   h.pi = pi; h.zt = zt;
   h.zh = t->zh; h.hstats = t->hstats; h.hidden = t->hidden; h.h1 = t->h1; h.value = t->value; h.dlogits = t->dlogits;
-  h.dvpre = t->dvpre; h.loss_parts = loss_parts; h.dhid = t->dhid; h.dzh = t->dzh; h.partial = t->partial; h.counter = t->counters + 2;
+  h.dvpre = t->dvpre; h.loss_parts = loss_parts; h.dhid = t->dhid; h.hsums = t->hsums; h.partial = t->partial; h.counter = t->counters + 2;
   h.g = t->g[0];
   h.d_w1p = t->grads + l.policy_conv_w; h.d_w1v = t->grads + l.value_conv_w;
   h.d_bn_gamma[0] = t->grads + l.policy_bn_w; h.d_bn_gamma[1] = t->grads + l.value_bn_w;
@@ -302,8 +305,9 @@ extern "C" int azg_train_forward_backward(azg_train* t, const float* planes, con
   AZG_CUDA(cudaMemsetAsync(t->grads, 0, (size_t)l.total * sizeof(float), s));      // the wgrad kernel accumulates with reductions
   const float mom = (float)t->cfg.bn_momentum, eps = (float)t->cfg.bn_eps;
   auto bn_fwd = [&](int idx, const float* gamma, const float* beta, float* rmean, float* rvar, const __nv_bfloat16* residual) -> int {
-    BnStatsArgs st{t->z[idx], count, t->partial, t->counters + 0, t->stats + (size_t)idx * 2 * C, rmean, rvar, mom, eps};
-    int r = azg_bn_stats_launch(C, st, s);
+    const bool fused = idx > 0 && t->fuse_stats;             // the convolution's epilogue already summed z and z^2 per channel
+    BnStatsArgs st{t->z[idx], count, fused ? t->conv_stat : t->partial, t->counters + 0, t->stats + (size_t)idx * 2 * C, rmean, rvar, mom, eps};
+    int r = fused ? azg_bn_finalize_launch(C, st, azg_conv3x3_stat_slots(t->max_batch, t->n_sm, C), s) : azg_bn_stats_launch(C, st, s);
     if (r) return r;
     BnApplyArgs ap{t->z[idx], t->stats + (size_t)idx * 2 * C, gamma, beta, residual, t->a[idx], count};
     return azg_bn_apply_launch(C, ap, t->n_sm, s);
@@ -315,6 +319,7 @@ extern "C" int azg_train_forward_backward(azg_train* t, const float* planes, con
   if ((rc = bn_fwd(0, t->params + l.bn_w, t->params + l.bn_b, const_cast<float*>(t->stat_ptrs.bn[2]), const_cast<float*>(t->stat_ptrs.bn[3]), nullptr))) return rc;
   for (int i = 0; i < L; ++i) {
     ConvArgs ca = conv_args(t, i, nullptr, t->z[i + 1]);
+    if (t->fuse_stats) ca.stat_partial = t->conv_stat;
     if ((rc = azg_conv3x3_launch(C, t->conv_mode, t->tm_a_in[i], t->tm_wf, t->tm_z_st[i + 1], ca, t->n_sm, s))) return rc;
     if ((rc = bn_fwd(i + 1, t->params + l.res_bn_w[i], t->params + l.res_bn_b[i], const_cast<float*>(t->stat_ptrs.res_bn[i][2]),
                      const_cast<float*>(t->stat_ptrs.res_bn[i][3]), (i & 1) ? t->a[i - 1] : nullptr))) return rc;
@@ -342,7 +347,7 @@ extern "C" int azg_train_forward_backward(azg_train* t, const float* planes, con
     cur ^= 1;
   }
   if ((rc = bn_bwd(0, t->params + l.bn_w, t->grads + l.bn_w, t->grads + l.bn_b, false))) return rc;
-  st.dz = t->dz; st.partial = t->stem_partial; st.n_partial = count < t->n_stem_partial ? count : t->n_stem_partial; st.dw = t->grads + l.conv_w;
+  st.dz = t->dz; st.partial = t->stem_partial; st.dw = t->grads + l.conv_w;
   if ((rc = azg_stem_train_wgrad_launch(C, st, s))) return rc;
   t->last_count = count; t->last_g = cur;
   return AZG_OK;

@@ -59,12 +59,16 @@ __device__ __forceinline__ bool last_block_arrives(unsigned* counter) {
 // ------------------------------------------------------------------------------------------------
 // trunk BatchNorm: batch statistics
 // ------------------------------------------------------------------------------------------------
-// Thread = (row lane rl, 8-channel group cg); a block covers RL = 256 / (C/8) rows per iteration.
+// Reduction kernels: thread = (row lane rl, 8-channel group cg); a block of kRedThreads covers RL rows per iteration.
+// Every block leaves its per-channel partial sums in partial[output][block] (stride AZG_TRAIN_PARTIALS); the last
+// block to finish adds them: one warp per output, lanes over the blocks, shuffle tree - a fixed order.
+constexpr int kRedThreads = 512;
+
 template <int C, bool BWD>
 __device__ __forceinline__ void channel_reduce(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ g,
                                                const __nv_bfloat16* __restrict__ a, const float* __restrict__ stats,
                                                int n_boards, float* __restrict__ partial) {
-  constexpr int CG = C / 8, RL = kEwThreads / CG;
+  constexpr int CG = C / 8, RL = kRedThreads / CG;
   __shared__ float red[RL][2][C];
   const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
   float s0[8], s1[8];
@@ -76,49 +80,102 @@ __device__ __forceinline__ void channel_reduce(const __nv_bfloat16* __restrict__
     for (int i = 0; i < 8; ++i) { mean[i] = stats[cg * 8 + i]; rstd[i] = stats[C + cg * 8 + i]; }
   }
   const long long n_rows = (long long)n_boards * 256;
-  for (long long r = (long long)blockIdx.x * RL + rl; r < n_rows; r += (long long)gridDim.x * RL) {
-    const size_t off = ((size_t)AZG_NET_FRONT + (size_t)r) * C + (size_t)cg * 8;
-    float zf[8];
-    unpack8(ptx::ldg128(z + off), zf);
-    if (!BWD) {
+  const long long step = (long long)gridDim.x * RL;
+  constexpr int U = 4;                                     // rows in flight per thread: the passes are latency bound otherwise
+  for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < n_rows; r0 += U * step) {
+    uint4 zq[U], gq[U], aq[U];
+    bool live[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s0[i] += zf[i]; s1[i] = fmaf(zf[i], zf[i], s1[i]); }
-    } else {
-      float gf[8], af[8];
-      unpack8(ptx::ldg128(g + off), gf);
-      unpack8(ptx::ldg128(a + off), af);
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * step;
+      live[u] = r < n_rows && !is_pad_row((int)(r & 255));   // pad rows are zero in z and g: nothing to add, nothing to read
+      if (live[u]) {
+        const size_t off = ((size_t)AZG_NET_FRONT + (size_t)r) * C + (size_t)cg * 8;
+        zq[u] = ptx::ldg128(z + off);
+        if (BWD) { gq[u] = ptx::ldg128(g + off); aq[u] = ptx::ldg128(a + off); }
+      }
+    }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float dy = af[i] > 0.f ? gf[i] : 0.f;
-        s0[i] += dy;
-        s1[i] = fmaf(dy, (zf[i] - mean[i]) * rstd[i], s1[i]);
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) continue;
+      float zf[8];
+      unpack8(zq[u], zf);
+      if (!BWD) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s0[i] += zf[i]; s1[i] = fmaf(zf[i], zf[i], s1[i]); }
+      } else {
+        float gf[8], af[8];
+        unpack8(gq[u], gf);
+        unpack8(aq[u], af);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dy = af[i] > 0.f ? gf[i] : 0.f;
+          s0[i] += dy;
+          s1[i] = fmaf(dy, (zf[i] - mean[i]) * rstd[i], s1[i]);
+        }
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) { red[rl][0][cg * 8 + i] = s0[i]; red[rl][1][cg * 8 + i] = s1[i]; }
   __syncthreads();
-  for (int t = threadIdx.x; t < 2 * C; t += kEwThreads) {
+  for (int t = threadIdx.x; t < 2 * C; t += kRedThreads) {
     const int k = t / C, c = t % C;
     float acc = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < RL; ++j) acc += red[j][k][c];
-    partial[((size_t)blockIdx.x * 2 + k) * C + c] = acc;
+    partial[(size_t)t * AZG_TRAIN_PARTIALS + blockIdx.x] = acc;
+  }
+}
+
+// Sum of partial[o][0 .. n_blocks) for the calling WARP's output o, in double, identical in every lane.
+__device__ __forceinline__ double warp_sum_partials(const float* __restrict__ partial, int o, int n_blocks) {
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int b = lane; b < n_blocks; b += 32) s += (double)partial[(size_t)o * AZG_TRAIN_PARTIALS + b];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  return s;
+}
+// The same for N outputs o0, o0 + stride, ... at once: all loads are issued before any is used (the tail of the
+// last block is a chain of L2 round trips otherwise).
+template <int N>
+__device__ __forceinline__ void warp_sum_partials_n(const float* __restrict__ partial, int o0, int stride, int n_blocks, double (&out)[N]) {
+  const int lane = threadIdx.x & 31;
+  constexpr int R = (AZG_TRAIN_PARTIALS + 31) / 32;
+  float v[N][R];
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int b = lane + 32 * j;
+      v[k][j] = b < n_blocks ? partial[(size_t)(o0 + k * stride) * AZG_TRAIN_PARTIALS + b] : 0.f;
+    }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) s += (double)v[k][j];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    out[k] = s;
   }
 }
 
 template <int C>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kRedThreads)
 bn_stats_kernel(BnStatsArgs p) {
   channel_reduce<C, false>(p.z, nullptr, nullptr, nullptr, p.n_boards, p.partial);
   if (!last_block_arrives(p.counter)) return;
   const double n = (double)p.n_boards * 225.0;
-  for (int c = threadIdx.x; c < C; c += kEwThreads) {
-    double s = 0.0, q = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) {
-      s += (double)p.partial[((size_t)b * 2 + 0) * C + c];
-      q += (double)p.partial[((size_t)b * 2 + 1) * C + c];
-    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = kRedThreads / 32, PER = C / NW;                 // channels per warp: 8 (C = 128) or 4
+  double sums[2 * PER];
+  warp_sum_partials_n<2 * PER>(p.partial, warp, NW, (int)gridDim.x, sums);     // outputs warp, warp + NW, ...: [0, C) sums, [C, 2C) squares
+  for (int k = 0; k < PER; ++k) {
+    const int c = warp + k * NW;
+    const double s = sums[k], q = sums[PER + k];
+    if (lane != 0) continue;
     const double mean = s / n;
     double var = q / n - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -128,6 +185,31 @@ bn_stats_kernel(BnStatsArgs p) {
     p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
     p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)unbiased;
   }
+}
+
+// The same finish for statistics that the convolution's epilogue collected (net_conv.cu STATS): partial is
+// [2 * C][AZG_CONV_STAT_SLOTS], n_slots of each row are valid; warp = channel.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(BnStatsArgs p, int C, int n_slots) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int j = lane; j < n_slots; j += 32) {
+    s += (double)p.partial[(size_t)c * AZG_CONV_STAT_SLOTS + j];
+    q += (double)p.partial[(size_t)(C + c) * AZG_CONV_STAT_SLOTS + j];
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); q += __shfl_xor_sync(0xffffffffu, q, d); }
+  if (lane != 0) return;
+  const double n = (double)p.n_boards * 225.0;
+  const double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  p.stats[c] = (float)mean;
+  p.stats[C + c] = (float)(1.0 / sqrt(var + (double)p.eps));
+  const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+  p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
+  p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)unbiased;
 }
 
 // a = relu(gamma * (z - mean) * rstd + beta (+ residual)), pad rows zero
@@ -173,16 +255,19 @@ bn_apply_kernel(BnApplyArgs p) {
 
 // backward: sums of dy and dy * x_hat per channel, dgamma / dbeta
 template <int C>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kRedThreads)
 bn_bwd_reduce_kernel(BnBwdArgs p) {
   channel_reduce<C, true>(p.z, p.g, p.a, p.stats, p.n_boards, p.partial);
   if (!last_block_arrives(p.counter)) return;
-  for (int t = threadIdx.x; t < 2 * C; t += kEwThreads) {
-    const int k = t / C, c = t % C;
-    double s = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += (double)p.partial[((size_t)b * 2 + k) * C + c];
-    p.sums[k * C + c] = (float)s;
-    if (k == 0) p.dbeta[c] = (float)s; else p.dgamma[c] = (float)s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = kRedThreads / 32, PER = 2 * C / NW;
+  double sums[PER];
+  warp_sum_partials_n<PER>(p.partial, warp, NW, (int)gridDim.x, sums);
+  if (lane != 0) return;
+  for (int j = 0; j < PER; ++j) {
+    const int t = warp + j * NW, k = t / C, c = t % C;
+    p.sums[k * C + c] = (float)sums[j];
+    if (k == 0) p.dbeta[c] = (float)sums[j]; else p.dgamma[c] = (float)sums[j];
   }
 }
 
@@ -233,82 +318,91 @@ bn_bwd_apply_kernel(BnBwdArgs p) {
 // ------------------------------------------------------------------------------------------------
 // stem: conv 3x3, 3 planes -> C (network.py:94)
 // ------------------------------------------------------------------------------------------------
-// One board per block iteration.  Planes live zero-padded (17 x 17) in shared memory, weights as [27][C].
+// Block = one board at a time; thread = (pixel slice ps, channel c): its 27 weights sit in registers, the zero-padded
+// planes (17 x 17) in shared memory are read as broadcasts, a pixel row leaves as C consecutive bf16.
+constexpr int kStemSlices = 2;
+
+__device__ __forceinline__ void stem_load_planes(float (*xs)[17][17], const float* __restrict__ planes, int b) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 17 * 17; i += blockDim.x) (&xs[0][0][0])[i] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 675; i += blockDim.x) {
+    const int pl = i / 225, pix = i % 225;
+    xs[pl][pix / 15 + 1][pix % 15 + 1] = planes[(size_t)b * 675 + i];
+  }
+  __syncthreads();
+}
+
 template <int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(C * kStemSlices)
 stem_train_fwd_kernel(StemTrainArgs p) {
   __shared__ float xs[3][17][17];
-  __shared__ float ws[27][C];
-  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) ws[i % 27][i / 27] = p.w[i];           // [c][27] -> [27][c]
-  constexpr int CG = C / 8;
-  for (int b = blockIdx.x; b < p.n_boards; b += gridDim.x) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * 17 * 17; i += blockDim.x) (&xs[0][0][0])[i] = 0.f;
-    __syncthreads();
-    for (int i = threadIdx.x; i < 675; i += blockDim.x) {
-      const int pl = i / 225, pix = i % 225;
-      xs[pl][pix / 15 + 1][pix % 15 + 1] = p.planes[(size_t)b * 675 + i];
-    }
-    __syncthreads();
-    for (int item = threadIdx.x; item < 225 * CG; item += blockDim.x) {
-      const int pix = item / CG, cg = item % CG;
-      const int r = pix / 15, c = pix % 15;
-      float acc[8];
+  const int c = threadIdx.x % C, ps = threadIdx.x / C;
+  float w[27];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 27; ++i) w[i] = p.w[c * 27 + i];
+  for (int b = blockIdx.x; b < p.n_boards; b += gridDim.x) {
+    stem_load_planes(xs, p.planes, b);
+    for (int pix = ps; pix < 225; pix += kStemSlices) {
+      const int r = pix / 15, cc = pix % 15;
+      float acc = 0.f;
 #pragma unroll
       for (int pl = 0; pl < 3; ++pl)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const float x = xs[pl][r + t / 3][c + t % 3];
-          const float* w = &ws[pl * 9 + t][cg * 8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(x, w[i], acc[i]);
-        }
-      const size_t row = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)((r + 1) * 16 + c);
-      ptx::stg128(p.z + row * C + (size_t)cg * 8, pack8(acc));
+        for (int t = 0; t < 9; ++t) acc = fmaf(xs[pl][r + t / 3][cc + t % 3], w[pl * 9 + t], acc);
+      const size_t row = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)((r + 1) * 16 + cc);
+      p.z[row * C + c] = __float2bfloat16_rn(acc);
     }
   }
 }
 
-// dW[plane*9+tap][c] = sum over boards, pixels of dz[pixel][c] * x[plane][pixel + tap]; thread = channel.
+// dW[plane*9+tap][c] = sum over boards, pixels of dz[pixel][c] * x[plane][pixel + tap].  One board per block,
+// thread = (pixel slice, channel); the slices are combined in shared memory and the block's 27 x C sums go to
+// partial[board][27 * C].  stem_reduce_kernel then adds the boards: thread = output, 64 boards per block in a fixed
+// order, one floating-point atomic per output and block of 64 boards (summation order across those few is not fixed -
+// like the tensor-core weight-gradient kernel).
 template <int C>
-__global__ void __launch_bounds__(C)
+__global__ void __launch_bounds__(256)
 stem_train_wgrad_kernel(StemTrainArgs p) {
+  constexpr int kStemWSlices = 256 / C;
   __shared__ float xs[3][17][17];
-  const int c = threadIdx.x;
+  __shared__ float red[kStemWSlices][27][C];
+  const int c = threadIdx.x % C, ps = threadIdx.x / C;
+  const int b = blockIdx.x;
   float acc[27];
 #pragma unroll
   for (int i = 0; i < 27; ++i) acc[i] = 0.f;
-  for (int b = blockIdx.x; b < p.n_boards; b += gridDim.x) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * 17 * 17; i += blockDim.x) (&xs[0][0][0])[i] = 0.f;
-    __syncthreads();
-    for (int i = threadIdx.x; i < 675; i += blockDim.x) {
-      const int pl = i / 225, pix = i % 225;
-      xs[pl][pix / 15 + 1][pix % 15 + 1] = p.planes[(size_t)b * 675 + i];
-    }
-    __syncthreads();
-    for (int pix = 0; pix < 225; ++pix) {
-      const int r = pix / 15, cc = pix % 15;
-      const size_t row = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)((r + 1) * 16 + cc);
-      const float d = __bfloat162float(p.dz[row * C + c]);
+  stem_load_planes(xs, p.planes, b);
+  const __nv_bfloat16* dzb = p.dz + ((size_t)AZG_NET_FRONT + (size_t)b * 256) * C + c;
+#pragma unroll 4
+  for (int pix = ps; pix < 225; pix += kStemWSlices) {
+    const int r = pix / 15, cc = pix % 15;
+    const float d = __bfloat162float(dzb[(size_t)((r + 1) * 16 + cc) * C]);
 #pragma unroll
-      for (int pl = 0; pl < 3; ++pl)
+    for (int pl = 0; pl < 3; ++pl)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[pl * 9 + t] = fmaf(d, xs[pl][r + t / 3][cc + t % 3], acc[pl * 9 + t]);
-    }
+      for (int t = 0; t < 9; ++t) acc[pl * 9 + t] = fmaf(d, xs[pl][r + t / 3][cc + t % 3], acc[pl * 9 + t]);
   }
 #pragma unroll
-  for (int i = 0; i < 27; ++i) p.partial[((size_t)blockIdx.x * 27 + i) * C + c] = acc[i];
+  for (int i = 0; i < 27; ++i) red[ps][i][c] = acc[i];
+  __syncthreads();
+  for (int t = threadIdx.x; t < 27 * C; t += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < kStemWSlices; ++k) v += (&red[k][0][0])[t];
+    p.partial[(size_t)b * 27 * C + t] = v;
+  }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_partial, int n, float* __restrict__ out) {
+__global__ void __launch_bounds__(128)
+stem_reduce_kernel(const float* __restrict__ partial, int n_boards, int n, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const int b0 = blockIdx.y * 64, b1 = min(n_boards, b0 + 64);
   float acc = 0.f;
-  for (int p = 0; p < n_partial; ++p) acc += partial[(size_t)p * n + i];
-  out[i] = acc;
+#pragma unroll 8
+  for (int b = b0; b < b1; ++b) acc += partial[(size_t)b * n + i];
+  atomicAdd(out + i, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -352,7 +446,7 @@ head_conv_fwd_kernel(HeadTrainArgs p) {
   }
 }
 
-// deterministic block sum of two doubles (1024 threads)
+// deterministic block sum of two doubles (any block size up to 1024)
 __device__ __forceinline__ void block_sum2(double& a, double& b) {
   __shared__ double sa[32], sb[32];
 #pragma unroll
@@ -367,35 +461,40 @@ __device__ __forceinline__ void block_sum2(double& a, double& b) {
   for (int s = 16; s >= 1; s >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, s); b += __shfl_xor_sync(0xffffffffu, b, s); }
 }
 
-// BatchNorm2d(2) / BatchNorm2d(1) in training mode + ReLU: one block per head channel h (0, 1 policy; 2 value)
-__global__ void __launch_bounds__(1024)
-head_bn_fwd_kernel(HeadTrainArgs p) {
-  const int h = blockIdx.x;
+// BatchNorm2d(2) / BatchNorm2d(1) of the heads in training mode: batch statistics of the three 1x1-conv channels
+// (0, 1 policy; 2 value).  Blocks sum slices of the batch, the last block finishes (warp h = channel h).  The
+// normalisation + ReLU itself is applied by head_fc_fwd_kernel while it loads its boards.
+__global__ void __launch_bounds__(512)
+head_stats_kernel(HeadTrainArgs p) {
   const int n = p.n_boards * 225;
-  double s = 0.0, q = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float z = p.zh[(size_t)(i / 225) * 675 + h * 225 + i % 225];
-    s += z; q += (double)z * z;
+  double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* zr = p.zh + (size_t)(i / 225) * 675 + i % 225;
+#pragma unroll
+    for (int h = 0; h < 3; ++h) { const float z = zr[h * 225]; acc[h][0] += z; acc[h][1] += (double)z * z; }
   }
-  block_sum2(s, q);
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    block_sum2(acc[h][0], acc[h][1]);
+    if (threadIdx.x == 0) {
+      p.partial[(size_t)(h * 2) * AZG_TRAIN_PARTIALS + blockIdx.x] = (float)acc[h][0];
+      p.partial[(size_t)(h * 2 + 1) * AZG_TRAIN_PARTIALS + blockIdx.x] = (float)acc[h][1];
+    }
+  }
+  if (!last_block_arrives(p.counter)) return;
+  const int h = threadIdx.x >> 5;
+  if (h >= 3) return;
+  const double s = warp_sum_partials(p.partial, h * 2, (int)gridDim.x), q = warp_sum_partials(p.partial, h * 2 + 1, (int)gridDim.x);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = s / n;
   double var = q / n - mean * mean;
   if (var < 0.0) var = 0.0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
   const int which = h < 2 ? 0 : 1, ch = h < 2 ? h : 0;
-  const float gamma = p.bn_gamma[which][ch], beta = p.bn_beta[which][ch];
-  if (threadIdx.x == 0) {
-    p.hstats[h * 2] = (float)mean;
-    p.hstats[h * 2 + 1] = rstd;
-    const double unbiased = n > 1 ? var * n / (n - 1.0) : var;
-    p.bn_rmean[which][ch] = (1.f - p.momentum) * p.bn_rmean[which][ch] + p.momentum * (float)mean;
-    p.bn_rvar[which][ch] = (1.f - p.momentum) * p.bn_rvar[which][ch] + p.momentum * (float)unbiased;
-  }
-  const float sc = gamma * rstd, sh = beta - (float)mean * sc;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const size_t o = (size_t)(i / 225) * 675 + h * 225 + i % 225;
-    p.hidden[o] = fmaxf(fmaf(p.zh[o], sc, sh), 0.f);
-  }
+  p.hstats[h * 2] = (float)mean;
+  p.hstats[h * 2 + 1] = (float)(1.0 / sqrt(var + (double)p.eps));
+  const double unbiased = n > 1 ? var * n / (n - 1.0) : var;
+  p.bn_rmean[which][ch] = (1.f - p.momentum) * p.bn_rmean[which][ch] + p.momentum * (float)mean;
+  p.bn_rvar[which][ch] = (1.f - p.momentum) * p.bn_rvar[which][ch] + p.momentum * (float)unbiased;
 }
 
 // dense layers + loss, NB boards per block: logits = hidden_p Wp^T + bp; h1 = relu(hidden_v Wv1^T + bv1);
@@ -410,9 +509,16 @@ head_fc_fwd_kernel(HeadTrainArgs p) {
   const int b0 = blockIdx.x * kFcBoards;
   const int nb = min(kFcBoards, p.n_boards - b0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < kFcBoards * 675; i += blockDim.x) {
-    const int k = i / 675;
-    hs[k][i % 675] = k < nb ? p.hidden[(size_t)(b0 + k) * 675 + i % 675] : 0.f;
+  for (int i = tid; i < kFcBoards * 675; i += blockDim.x) {      // hidden = relu(bn(zh)), kept for the backward pass
+    const int k = i / 675, f = i % 675, h = f / 225;
+    float v = 0.f;
+    if (k < nb) {
+      const int which = h < 2 ? 0 : 1, ch = h < 2 ? h : 0;
+      const float sc = p.bn_gamma[which][ch] * p.hstats[h * 2 + 1], sh = p.bn_beta[which][ch] - p.hstats[h * 2] * sc;
+      v = fmaxf(fmaf(p.zh[(size_t)(b0 + k) * 675 + f], sc, sh), 0.f);
+      p.hidden[(size_t)(b0 + k) * 675 + f] = v;
+    }
+    hs[k][f] = v;
   }
   __syncthreads();
   float logit[kFcBoards];
@@ -602,29 +708,41 @@ head_fc_wgrad_kernel(HeadTrainArgs p) {
   }
 }
 
-// head BatchNorm backward: one block per head channel
-__global__ void __launch_bounds__(1024)
-head_bn_bwd_kernel(HeadTrainArgs p) {
-  const int h = blockIdx.x;
+// head BatchNorm backward, reduction part: sums of dy and dy * x_hat per head channel -> hsums, dgamma, dbeta
+__global__ void __launch_bounds__(512)
+head_bn_bwd_reduce_kernel(HeadTrainArgs p) {
   const int n = p.n_boards * 225;
-  const float mean = p.hstats[h * 2], rstd = p.hstats[h * 2 + 1];
-  double s1 = 0.0, s2 = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const size_t o = (size_t)(i / 225) * 675 + h * 225 + i % 225;
-    const float dy = p.dhid[o];
-    s1 += dy;
-    s2 += (double)dy * ((p.zh[o] - mean) * rstd);
+  double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+  float mean[3], rstd[3];
+#pragma unroll
+  for (int h = 0; h < 3; ++h) { mean[h] = p.hstats[h * 2]; rstd[h] = p.hstats[h * 2 + 1]; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const size_t o = (size_t)(i / 225) * 675 + i % 225;
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+      const float dy = p.dhid[o + h * 225];
+      acc[h][0] += dy;
+      acc[h][1] += (double)dy * ((p.zh[o + h * 225] - mean[h]) * rstd[h]);
+    }
   }
-  block_sum2(s1, s2);
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    block_sum2(acc[h][0], acc[h][1]);
+    if (threadIdx.x == 0) {
+      p.partial[(size_t)(h * 2) * AZG_TRAIN_PARTIALS + blockIdx.x] = (float)acc[h][0];
+      p.partial[(size_t)(h * 2 + 1) * AZG_TRAIN_PARTIALS + blockIdx.x] = (float)acc[h][1];
+    }
+  }
+  if (!last_block_arrives(p.counter)) return;
+  const int h = threadIdx.x >> 5;
+  if (h >= 3) return;
+  const double s1 = warp_sum_partials(p.partial, h * 2, (int)gridDim.x), s2 = warp_sum_partials(p.partial, h * 2 + 1, (int)gridDim.x);
+  if ((threadIdx.x & 31) != 0) return;
   const int which = h < 2 ? 0 : 1, ch = h < 2 ? h : 0;
-  const float gamma = p.bn_gamma[which][ch];
-  if (threadIdx.x == 0) { p.d_bn_gamma[which][ch] = (float)s2; p.d_bn_beta[which][ch] = (float)s1; }
-  const float m1 = (float)(s1 / n), m2 = (float)(s2 / n), k0 = gamma * rstd;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const size_t o = (size_t)(i / 225) * 675 + h * 225 + i % 225;
-    const float xh = (p.zh[o] - mean) * rstd;
-    p.dzh[o] = k0 * (p.dhid[o] - m1 - xh * m2);
-  }
+  p.hsums[h * 2] = (float)s1;
+  p.hsums[h * 2 + 1] = (float)s2;
+  p.d_bn_gamma[which][ch] = (float)s2;
+  p.d_bn_beta[which][ch] = (float)s1;
 }
 
 // 1x1 convolutions backward: g[row][c] = sum_h dzh[h][row] * w1[h][c] (pad rows zero) and
@@ -641,6 +759,17 @@ head_conv_bwd_kernel(HeadTrainArgs p) {
     w[0][i] = p.w1p[cg * 8 + i]; w[1][i] = p.w1p[C + cg * 8 + i]; w[2][i] = p.w1v[cg * 8 + i];
     acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
   }
+  float hk0[3], hm1[3], hm2[3], hmean[3], hrstd[3];
+  {
+    const float inv_n = 1.0f / ((float)p.n_boards * 225.0f);
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+      const int which = h < 2 ? 0 : 1, ch = h < 2 ? h : 0;
+      hmean[h] = p.hstats[h * 2]; hrstd[h] = p.hstats[h * 2 + 1];
+      hk0[h] = p.bn_gamma[which][ch] * hrstd[h];
+      hm1[h] = p.hsums[h * 2] * inv_n; hm2[h] = p.hsums[h * 2 + 1] * inv_n;
+    }
+  }
   const long long n_rows = (long long)p.n_boards * 256;
   for (long long r = (long long)blockIdx.x * RL + rl; r < n_rows; r += (long long)gridDim.x * RL) {
     const int qi = (int)(r & 255);
@@ -651,8 +780,12 @@ head_conv_bwd_kernel(HeadTrainArgs p) {
       for (int i = 0; i < 8; ++i) g[i] = 0.f;
     } else {
       const int pix = ((qi >> 4) - 1) * 15 + (qi & 15);
-      const float* d = p.dzh + (size_t)(r >> 8) * 675 + pix;
-      const float d0 = d[0], d1 = d[225], d2 = d[450];
+      const size_t ho = (size_t)(r >> 8) * 675 + pix;
+      float dh[3];
+#pragma unroll
+      for (int h = 0; h < 3; ++h)         // head BatchNorm backward, applied on the fly
+        dh[h] = hk0[h] * (p.dhid[ho + h * 225] - hm1[h] - (p.zh[ho + h * 225] - hmean[h]) * hrstd[h] * hm2[h]);
+      const float d0 = dh[0], d1 = dh[1], d2 = dh[2];
       float af[8];
       unpack8(ptx::ldg128(p.act + off), af);
 #pragma unroll
@@ -675,14 +808,18 @@ head_conv_bwd_kernel(HeadTrainArgs p) {
     float a = 0.f;
 #pragma unroll 4
     for (int jx = 0; jx < RL; ++jx) a += red[jx][h][c];
-    p.partial[((size_t)blockIdx.x * 3 + h) * C + c] = a;
+    p.partial[(size_t)t * AZG_TRAIN_PARTIALS + blockIdx.x] = a;
   }
   if (!last_block_arrives(p.counter)) return;
-  for (int t = threadIdx.x; t < 3 * C; t += kEwThreads) {
-    const int h = t / C, c = t % C;
-    double s = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += (double)p.partial[((size_t)b * 3 + h) * C + c];
-    if (h < 2) p.d_w1p[h * C + c] = (float)s; else p.d_w1v[c] = (float)s;
+  constexpr int NW = kEwThreads / 32, BATCH = 8;
+  for (int t0 = threadIdx.x >> 5; t0 < 3 * C; t0 += NW * BATCH) {          // 3C / (8 warps * 8) = 6 (C = 128) or 3 rounds
+    double sums[BATCH];
+    warp_sum_partials_n<BATCH>(p.partial, t0, NW, (int)gridDim.x, sums);
+    if ((threadIdx.x & 31) != 0) continue;
+    for (int j = 0; j < BATCH; ++j) {
+      const int t = t0 + j * NW, h = t / C, c = t % C;
+      if (h < 2) p.d_w1p[h * C + c] = (float)sums[j]; else p.d_w1v[c] = (float)sums[j];
+    }
   }
 }
 
@@ -782,12 +919,17 @@ int ew_grid(int n_boards, int C, int n_sm) {
 int azg_bn_stats_launch(int C, const BnStatsArgs& a, cudaStream_t s) {
   return dispatch_c(C, [&](auto c) {
     constexpr int CC = decltype(c)::value;
-    int grid = a.n_boards * 256 / (kEwThreads / (CC / 8));
+    int grid = a.n_boards * 256 / (kRedThreads / (CC / 8));
     if (grid > AZG_TRAIN_PARTIALS) grid = AZG_TRAIN_PARTIALS;
     if (grid < 1) grid = 1;
-    bn_stats_kernel<CC><<<grid, kEwThreads, 0, s>>>(a);
+    bn_stats_kernel<CC><<<grid, kRedThreads, 0, s>>>(a);
     return azg_check_launch("bn_stats_kernel");
   });
+}
+
+int azg_bn_finalize_launch(int C, const BnStatsArgs& a, int n_slots, cudaStream_t s) {
+  bn_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(a, C, n_slots);
+  return azg_check_launch("bn_finalize_kernel");
 }
 
 int azg_bn_apply_launch(int C, const BnApplyArgs& a, int n_sm, cudaStream_t s) {
@@ -801,10 +943,10 @@ int azg_bn_apply_launch(int C, const BnApplyArgs& a, int n_sm, cudaStream_t s) {
 int azg_bn_bwd_reduce_launch(int C, const BnBwdArgs& a, cudaStream_t s) {
   return dispatch_c(C, [&](auto c) {
     constexpr int CC = decltype(c)::value;
-    int grid = a.n_boards * 256 / (kEwThreads / (CC / 8));
+    int grid = a.n_boards * 256 / (kRedThreads / (CC / 8));
     if (grid > AZG_TRAIN_PARTIALS) grid = AZG_TRAIN_PARTIALS;
     if (grid < 1) grid = 1;
-    bn_bwd_reduce_kernel<CC><<<grid, kEwThreads, 0, s>>>(a);
+    bn_bwd_reduce_kernel<CC><<<grid, kRedThreads, 0, s>>>(a);
     return azg_check_launch("bn_bwd_reduce_kernel");
   });
 }
@@ -820,24 +962,21 @@ int azg_bn_bwd_apply_launch(int C, const BnBwdArgs& a, int n_sm, cudaStream_t s)
 int azg_stem_train_fwd_launch(int C, const StemTrainArgs& a, cudaStream_t s) {
   return dispatch_c(C, [&](auto c) {
     constexpr int CC = decltype(c)::value;
-    stem_train_fwd_kernel<CC><<<a.n_boards < 1184 ? a.n_boards : 1184, 256, 0, s>>>(a);
+    stem_train_fwd_kernel<CC><<<a.n_boards < 1184 ? a.n_boards : 1184, CC * kStemSlices, 0, s>>>(a);
     return azg_check_launch("stem_train_fwd_kernel");
   });
 }
 
-int azg_stem_train_wgrad_launch(int C, const StemTrainArgs& a, cudaStream_t s) {
+int azg_stem_train_wgrad_launch(int C, const StemTrainArgs& a, cudaStream_t s) {       // a.dw must be zero (it is: the step clears the gradient vector)
   int rc = dispatch_c(C, [&](auto c) {
     constexpr int CC = decltype(c)::value;
-    stem_train_wgrad_kernel<CC><<<a.n_partial, CC, 0, s>>>(a);
+    stem_train_wgrad_kernel<CC><<<a.n_boards, 256, 0, s>>>(a);
     return azg_check_launch("stem_train_wgrad_kernel");
   });
   if (rc) return rc;
-  return azg_reduce_partials_launch(a.partial, a.n_partial, 27 * C, a.dw, s);
-}
-
-int azg_reduce_partials_launch(const float* partial, int n_partial, int n, float* out, cudaStream_t s) {
-  reduce_partials_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, n_partial, n, out);
-  return azg_check_launch("reduce_partials_kernel");
+  const int n = 27 * C;
+  stem_reduce_kernel<<<dim3((n + 127) / 128, (a.n_boards + 63) / 64), 128, 0, s>>>(a.partial, a.n_boards, n, a.dw);
+  return azg_check_launch("stem_reduce_kernel");
 }
 
 int azg_head_train_fwd_launch(const HeadTrainArgs& a, int n_sm, cudaStream_t s) {
@@ -849,8 +988,10 @@ int azg_head_train_fwd_launch(const HeadTrainArgs& a, int n_sm, cudaStream_t s) 
     return azg_check_launch("head_conv_fwd_kernel");
   });
   if (rc) return rc;
-  head_bn_fwd_kernel<<<3, 1024, 0, s>>>(a);
-  if ((rc = azg_check_launch("head_bn_fwd_kernel"))) return rc;
+  int hgrid = (a.n_boards * 225 + 2047) / 2048;
+  if (hgrid > AZG_TRAIN_PARTIALS) hgrid = AZG_TRAIN_PARTIALS;
+  head_stats_kernel<<<hgrid, 512, 0, s>>>(a);
+  if ((rc = azg_check_launch("head_stats_kernel"))) return rc;
   head_fc_fwd_kernel<<<(a.n_boards + kFcBoards - 1) / kFcBoards, 256, 0, s>>>(a);
   return azg_check_launch("head_fc_fwd_kernel");
 }
@@ -862,8 +1003,10 @@ int azg_head_train_bwd_launch(const HeadTrainArgs& a, int n_sm, cudaStream_t s) 
   constexpr int n_out = 225 * 450 + 225 + 64 * 225 + 64 + 64 + 1;
   head_fc_wgrad_kernel<<<(n_out + 255) / 256, 256, 0, s>>>(a);
   if ((rc = azg_check_launch("head_fc_wgrad_kernel"))) return rc;
-  head_bn_bwd_kernel<<<3, 1024, 0, s>>>(a);
-  if ((rc = azg_check_launch("head_bn_bwd_kernel"))) return rc;
+  int hgrid = (a.n_boards * 225 + 2047) / 2048;
+  if (hgrid > AZG_TRAIN_PARTIALS) hgrid = AZG_TRAIN_PARTIALS;
+  head_bn_bwd_reduce_kernel<<<hgrid, 512, 0, s>>>(a);
+  if ((rc = azg_check_launch("head_bn_bwd_reduce_kernel"))) return rc;
   return dispatch_c(a.C, [&](auto c) {
     constexpr int CC = decltype(c)::value;
     int grid = a.n_boards * 256 / (kEwThreads / (CC / 8));

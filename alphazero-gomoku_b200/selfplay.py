@@ -18,6 +18,20 @@ from .engine import POS_WORDS, SearchEngine
 from .nn_engine import NetEngine
 
 ROW = 901          # floats per example: planes 3*225, pi 225, z
+PACKED_WORDS = 244  # uint32 per packed ply: stones 16, side to move, z, pi 225, pad (include/azgomoku_b200.h)
+
+
+def expand_examples(packed: torch.Tensor, use_symmetries: bool = True) -> torch.Tensor:
+    """Packed plies int32[n, 244] (device) -> example rows float32[n * 8, 901] in the reference's symmetry order
+    (train.py:405-410): what ``play_game_and_collect`` appends for these plies."""
+    n = int(packed.shape[0])
+    k = 8 if use_symmetries else 1
+    out = torch.empty((n * k, ROW), dtype=torch.float32, device=packed.device)
+    if n:
+        src = packed.contiguous()
+        with torch.cuda.device(packed.device):
+            check(lib.azg_examples_expand(ptr(src), n, int(use_symmetries), ptr(out), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out
 
 
 def trunk_flops(channels: int) -> int:
@@ -33,10 +47,13 @@ class SelfPlay:
                  queue_len: int = 32, node_capacity: int = 8192, noise: bool = True, alpha: float = 0.05,
                  eps: float = 0.15, noise_plies: int = 10, temp_threshold: float = 10.0, max_moves: int = 225,
                  use_symmetries: bool = True, example_capacity: int = 1 << 20, seed: int = 12345, device="cuda:0",
-                 game_base: int = 0, max_games: int | None = None):
+                 game_base: int = 0, max_games: int | None = None, packed_examples: bool = False):
         """``max_games``: play exactly that many games to completion (train.py:671-694 plays
         ``games_per_iteration`` full games): finished slots restart only while fewer than ``max_games`` games
-        have been started, afterwards they retire (``active`` mask) - no game is cut off or counted twice."""
+        have been started, afterwards they retire (``active`` mask) - no game is cut off or counted twice.
+        ``packed_examples``: keep finished games as one 976-byte record per ply (stones, side, z, pi) and expand the
+        8 symmetries only when rows are asked for (``drain_examples``) - ``drain_packed`` is what ranks exchange;
+        ``example_capacity`` then counts plies."""
         self.device = torch.device(device)
         self.G, self.n_sims, self.temp_threshold, self.max_moves = n_games, n_sims, float(temp_threshold), max_moves
         self.use_symmetries = use_symmetries
@@ -59,7 +76,13 @@ class SelfPlay:
         self.winners = torch.empty(n_games, dtype=torch.int32, device=dev)
         self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
         self.capacity = example_capacity
-        self.examples = torch.empty((example_capacity, ROW), dtype=torch.float32, device=dev) if example_capacity else None
+        self.packed = bool(packed_examples)
+        if not example_capacity:
+            self.examples = None
+        elif self.packed:
+            self.examples = torch.empty((example_capacity, PACKED_WORDS), dtype=torch.int32, device=dev)
+        else:
+            self.examples = torch.empty((example_capacity, ROW), dtype=torch.float32, device=dev)
         empty = torch.zeros((n_games, POS_WORDS), dtype=torch.int32, device=dev)
         empty[:, 16] = 1          # player 1 to move
         empty[:, 17] = -1         # no last move
@@ -179,9 +202,17 @@ class SelfPlay:
         check(lib.azg_search_result(eng._h, ptr(self._pi), ptr(self._visits)))
         check(lib.azg_selfplay_choose(eng._h, ptr(self._pi), C.c_float(self.temp_threshold), self.draw, ptr(self.actions)))
         check(lib.azg_search_advance(eng._h, ptr(self.actions), 1, self._reserve(), ptr(self._status)))
-        check(lib.azg_selfplay_finish(eng._h, ptr(self._status), self.max_moves, int(self.use_symmetries), ptr(self.examples),
-                                      self.capacity, ptr(self.cursor), ptr(self.done), ptr(self.winners)))
+        self._finish(self._status)
         self._restart()
+
+    def _finish(self, status):
+        eng = self.engine
+        if self.packed:
+            check(lib.azg_selfplay_finish_packed(eng._h, ptr(status), self.max_moves, ptr(self.examples), self.capacity,
+                                                 ptr(self.cursor), ptr(self.done), ptr(self.winners)))
+        else:
+            check(lib.azg_selfplay_finish(eng._h, ptr(status), self.max_moves, int(self.use_symmetries), ptr(self.examples),
+                                          self.capacity, ptr(self.cursor), ptr(self.done), ptr(self.winners)))
 
     def _reserve(self) -> int:
         """Free nodes a slab needs for another run: one per simulation plus one per flush (see enable_graph)."""
@@ -226,8 +257,7 @@ class SelfPlay:
         self.last_pi = pi
         check(lib.azg_selfplay_choose(eng._h, ptr(pi), C.c_float(self.temp_threshold), self.draw, ptr(self.actions)))
         status = eng.advance(self.actions, gc=True, reserve=self._reserve())
-        check(lib.azg_selfplay_finish(eng._h, ptr(status), self.max_moves, int(self.use_symmetries), ptr(self.examples),
-                                      self.capacity, ptr(self.cursor), ptr(self.done), ptr(self.winners)))
+        self._finish(status)
         self._restart()
         self.total_launches += 4
         return status
@@ -236,8 +266,19 @@ class SelfPlay:
     def n_examples(self) -> int:
         return min(int(self.cursor.item()), self.capacity)
 
+    def drain_packed(self) -> torch.Tensor:
+        """Packed plies of the games finished since the last drain, int32[n, 244] (``packed_examples`` mode)."""
+        if not self.packed:
+            raise RuntimeError("drain_packed needs SelfPlay(packed_examples=True)")
+        n = self.n_examples()
+        out = self.examples[:n].clone()
+        self.cursor.zero_()
+        return out
+
     def drain_examples(self) -> torch.Tensor:
         """Rows produced since the last drain, float32[n, 901] (planes 675, pi 225, z) on the device."""
+        if self.packed:
+            return expand_examples(self.drain_packed(), self.use_symmetries)
         n = self.n_examples()
         out = self.examples[:n].clone()
         self.cursor.zero_()

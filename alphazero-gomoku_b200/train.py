@@ -362,8 +362,18 @@ def _world():
     return (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
 
 
+def gather_examples(sp: SelfPlay) -> torch.Tensor:
+    """The exchange step of the loop (train.py:737-742 pickles every worker's expanded rows through a pipe): every
+    rank contributes the games it finished as PACKED plies (976 bytes each: stones as bits, side, z, pi), all ranks
+    all-gather those, and each expands the 8 symmetries locally - 29.5x fewer bytes on NVLink than the float rows
+    (symmetries are a pure function of the ply).  Returns the expanded rows float32[n, 901] of ALL ranks, rank-major."""
+    from .selfplay import expand_examples
+    packed = gather_rows(sp.drain_packed())
+    return expand_examples(packed, sp.use_symmetries)
+
+
 def gather_rows(rows: torch.Tensor) -> torch.Tensor:
-    """All-gather variable-length example rows [n_r, 901] from every rank (padded, with counts)."""
+    """All-gather variable-length rows [n_r, width] (example rows or packed plies) from every rank (padded, with counts)."""
     world, _ = _world()
     if world == 1:
         return rows
@@ -477,8 +487,8 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
         sp = SelfPlay(model_candidate, rule=0, n_games=G, n_sims=n_simulations, cpuct=cpuct, noise=True,
                       alpha=dirichlet_alpha, eps=dirichlet_epsilon, noise_plies=dirichlet_n_moves,
                       temp_threshold=float(temp_threshold), max_moves=board_size * board_size,
-                      example_capacity=max(my_games, G) * 225 * 8, seed=selfplay_base_seed + it, game_base=rank * G,
-                      node_capacity=max(4096, 4 * n_simulations), device=dev, max_games=my_games)
+                      example_capacity=max(my_games, G) * 225, seed=selfplay_base_seed + it, game_base=rank * G,
+                      node_capacity=max(4096, 4 * n_simulations), device=dev, max_games=my_games, packed_examples=True)
         # exactly my_games games are started and every one of them is played to the end (train.py:671-694):
         # slots restart only while games remain to be started, then retire
         finished = 0
@@ -490,7 +500,7 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
                 winners[int(x)] = winners.get(int(x), 0) + 1
             finished += len(w)
         assert finished == my_games
-        rows = gather_rows(sp.drain_examples())
+        rows = gather_examples(sp)
         sp.close()
         buffer.add_rows(rows)
         if rank == 0:

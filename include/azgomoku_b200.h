@@ -174,6 +174,16 @@ int azg_selfplay_choose(azg_engine* e, const float* pi, float temp_threshold, ui
 int azg_selfplay_finish(azg_engine* e, const int32_t* status, int max_moves, int use_symmetries, float* out,
                         int64_t capacity, uint64_t* cursor, int32_t* done_mask, int32_t* winners);
 
+/* The same, but one PACKED row per ply instead of 8 expanded ones: out uint32[capacity][AZG_PACKED_WORDS] =
+ * {stones[2][8], side to move, z (float bits), pi[225] (float bits), 0}.  976 bytes per ply against 8 x 3604: this
+ * is what the ranks exchange (train.py:737-742 pickles the expanded rows through a pipe). */
+#define AZG_PACKED_WORDS 244
+int azg_selfplay_finish_packed(azg_engine* e, const int32_t* status, int max_moves, uint32_t* out, int64_t capacity,
+                               uint64_t* cursor, int32_t* done_mask, int32_t* winners);
+/* Packed plies -> example rows float32[n * (8 or 1)][901] in the reference's symmetry order
+ * (train.py:405-410, new_mcts_alpha.py:42-56), on the current device. */
+int azg_examples_expand(const uint32_t* packed, int64_t n, int use_symmetries, float* out, void* stream);
+
 /* ------------------------------------------------------------------ leaf evaluator (policy/value ResNet)
  * Replaces AlphaZeroNet.forward + PyTorchModel.predict (network.py:85-117, 168-183): stem conv,
  * n_blocks residual blocks of two 3x3 convs (tcgen05 implicit GEMM, bf16 in / fp32 accumulate,

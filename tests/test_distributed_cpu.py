@@ -52,6 +52,10 @@ def _worker(rank, world, port, out):
     allrows = tr.gather_rows(rows)
     assert allrows.shape == (3 + 5, 901)
     assert torch.all(allrows[:3] == 1.0) and torch.all(allrows[3:] == 2.0)
+    packed = torch.full((2 + rank, 244), rank + 7, dtype=torch.int32)             # packed plies travel as int32 words
+    allpacked = tr.gather_rows(packed)
+    assert allpacked.dtype == torch.int32 and allpacked.shape == (5, 244)
+    assert torch.all(allpacked[:2] == 7) and torch.all(allpacked[2:] == 8)
 
     torch.manual_seed(0)
     net = mynet.AlphaZeroNet(n_res_blocks=1, channels=16)

@@ -321,3 +321,30 @@ def test_graph_mode_round_bound_small_queue():
     with pytest.raises(ValueError):
         sp.enable_graph()
     sp.close()
+
+
+def test_packed_examples_expand_to_the_same_rows():
+    """packed_examples mode (one 976-byte record per ply, the format ranks exchange) + azg_examples_expand ==
+    the rows the direct mode writes (8 symmetries per ply in the reference's order, labels included)."""
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import PACKED_WORDS, SelfPlay, expand_examples
+    torch.manual_seed(2)
+    model = PyTorchModel(n_res_blocks=1, channels=64, device="cuda:0")
+    rows = []
+    for packed in (False, True):
+        sp = SelfPlay(model, n_games=16, n_sims=32, noise=True, max_moves=60, node_capacity=2048,
+                      example_capacity=1 << 15, seed=11, max_games=16, packed_examples=packed)
+        while sp.games_running() > 0:
+            sp.step()
+        if packed:
+            p = sp.drain_packed()
+            assert p.dtype == torch.int32 and p.shape[1] == PACKED_WORDS and p.shape[0] * 8 == rows[0].shape[0]
+            assert p.shape[0] * PACKED_WORDS * 4 * 29 < rows[0].size * 4                 # > 29x fewer bytes
+            rows.append(expand_examples(p, True).cpu().numpy())
+            one = expand_examples(p[:3], False).cpu().numpy()                            # without symmetries: the identity image
+            assert one.shape == (3, 901) and np.array_equal(one, rows[1][0:24:8])
+        else:
+            rows.append(sp.drain_examples().cpu().numpy())
+        sp.close()
+    a, b = (np.unique(r, axis=0) for r in rows)            # game blocks land in reservation order: compare as sorted sets
+    assert rows[0].shape == rows[1].shape and np.array_equal(a, b)

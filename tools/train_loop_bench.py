@@ -6,9 +6,11 @@ phase by phase, with the SURVEY 8(d) settings (6x128 net, batch 128 per GPU, Ada
 
 Phases (every time is the MAX over ranks of a CUDA-event interval bracketed by barriers):
   self-play   each rank plays `--games` concurrent games for `--plies` plies on its own GPU (no collective);
-  gather      the examples of all ranks are all-gathered into every rank's HBM-resident replay buffer (NCCL);
+  gather      the finished games of all ranks are all-gathered as packed plies (976 B each) and expanded to the 8
+              symmetries on every rank into its HBM-resident replay buffer (NCCL);
   train       `--train-steps` data-parallel Adam steps: same global batch drawn on every rank, each rank takes
-              its 128-row slice, flat fp32 gradient all-reduce (1.89 M elements), clip, identical update.
+              its slice, runs the tensor-core forward/backward (CUDA graph), flat fp32 gradient all-reduce
+              (1.89 M elements), clip + Adam (second graph): identical update on every rank.
 Prints one JSON line on rank 0 and checks that all ranks end with bit-identical weights."""
 import argparse
 import json
@@ -59,8 +61,8 @@ def main():
     model = PyTorchModel(n_res_blocks=args.blocks, channels=args.channels, device=str(dev))
     tr.broadcast_model(model)
     sp = SelfPlay(model, n_games=args.games, n_sims=args.sims, noise=True, alpha=0.05, eps=0.15, noise_plies=10,
-                  temp_threshold=10.0, example_capacity=args.games * (args.plies + 2) * 8, seed=12345,
-                  game_base=rank * args.games, node_capacity=4096, device=str(dev))
+                  temp_threshold=10.0, example_capacity=args.games * (args.plies + 2), seed=12345,
+                  game_base=rank * args.games, node_capacity=4096, device=str(dev), packed_examples=True)
     sp.step()                                                   # warm-up ply (weight packing, allocator)
     sims0 = sp.total_sims
 
@@ -69,25 +71,32 @@ def main():
             sp.step()
     _, t_sp = timed(selfplay, dev)
     sims = (sp.total_sims - sims0) * world
-    rows_local = sp.drain_examples()                           # rows of the games that ended (8 symmetries each)
+    from alphazero_gomoku_b200.selfplay import expand_examples
+    packed_local = sp.drain_packed()                           # plies of the games that ended, 976 bytes each
     synthetic = 0
-    if rows_local.shape[0] < args.batch_per_gpu:               # too short a run for games to end: pad, and say so
-        synthetic = args.games * 8
-        extra = torch.zeros((synthetic, 901), device=dev)
-        extra[:, 450:675] = 1.0                                 # empty board: only the ones plane is set
-        extra[:, 675:900] = 1.0 / 225
-        rows_local = torch.cat([rows_local, extra])
-    rows, t_gather = timed(lambda: tr.gather_rows(rows_local), dev)
+    if packed_local.shape[0] * 8 < args.batch_per_gpu:         # too short a run for games to end: pad, and say so
+        synthetic = args.games
+        extra = torch.zeros((synthetic, 244), dtype=torch.int32, device=dev)
+        extra[:, 16] = 1
+        extra[:, 18:243] = torch.full((225,), 1.0 / 225).view(torch.int32).to(dev)
+        packed_local = torch.cat([packed_local, extra])
+
+    def exchange():
+        return expand_examples(tr.gather_rows(packed_local), True)     # all-gather packed plies, expand 8 symmetries locally
+    rows, t_gather = timed(exchange, dev)
     buf = tr.DeviceReplayBuffer(max(rows.shape[0], 1), dev)
     buf.add_rows(rows)
     gen = torch.Generator(device=dev)
     gen.manual_seed(17)
     B = args.batch_per_gpu * world
 
+    reduce = (lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)) if world > 1 else None
+
     def step():
         states, pis, zs = buf.sample(B, generator=gen)
         sl = slice(rank * args.batch_per_gpu, (rank + 1) * args.batch_per_gpu)
-        return tr.train_batch_dp(model, states[sl], pis[sl], zs[sl])
+        # train_batch_dp without its per-step host read of the losses: forward/backward graph, all-reduce, clip + Adam graph
+        return model.train_batch_async(states[sl], pis[sl], zs[sl], world=world, reduce_grads=reduce)
     for _ in range(3):
         step()
 
@@ -96,6 +105,8 @@ def main():
             last = step()
         return last
     losses, t_train = timed(train, dev)
+    losses = dict(zip(("policy_loss", "value_loss"), losses.tolist()))
+    tr.sync_batchnorm_buffers(model)
     # gradient all-reduce alone, same element count
     n_param = sum(p.numel() for p in model.net.parameters())
     flat = torch.zeros(n_param, device=dev)
@@ -113,8 +124,9 @@ def main():
             "workload": "self-play -> replay buffer -> Adam train loop (BASELINE configs[3])", "n_gpus": world,
             "net": f"{args.blocks}x{args.channels}", "games_per_gpu": args.games, "sims_per_move": args.sims, "plies": args.plies,
             "selfplay_ms": round(t_sp, 1), "selfplay_sims_per_s": round(sims / (t_sp * 1e-3), 1),
-            "examples_gathered": int(rows.shape[0]), "synthetic_rows_per_gpu": synthetic, "gather_ms": round(t_gather, 2),
-            "gather_GBps": round(rows.numel() * 4 / (t_gather * 1e-3) / 1e9, 1),
+            "examples_gathered": int(rows.shape[0]), "synthetic_plies_per_gpu": synthetic, "gather_ms": round(t_gather, 2),
+            "exchange": "all-gather of packed plies (976 B each) + local 8-symmetry expansion",
+            "exchanged_bytes": int(rows.shape[0] // 8 * 976), "expanded_bytes": int(rows.numel() * 4),
             "train_steps": args.train_steps, "global_batch": B, "train_ms_per_step": round(t_train / args.train_steps, 3),
             "train_positions_per_s": round(B * args.train_steps / (t_train * 1e-3), 1),
             "grad_allreduce_ms": round(t_ar / 20, 4), "grad_elements": n_param, "last_losses": losses,

@@ -61,9 +61,12 @@ struct azg_train {
   size_t rows = 0;
   ParamLayout lay{};
   std::vector<__nv_bfloat16*> a, z;              // [L+1] activations after / before BatchNorm+ReLU
-  __nv_bfloat16 *g[2] = {nullptr, nullptr}, *dz = nullptr, *gskip = nullptr;
+  __nv_bfloat16 *g[2] = {nullptr, nullptr}, *dzb[2] = {nullptr, nullptr}, *gskip = nullptr;     // dzb: dL/dz, double buffered (see the backward loop)
+  cudaStream_t side = nullptr;                   // the weight-gradient kernels run here, beside the next layer's BatchNorm passes
+  std::vector<cudaEvent_t> ev_fork, ev_join;
+  int overlap = 1, last_dz = 0;
   std::vector<CUtensorMap> tm_a_in, tm_a_wg, tm_z_st;
-  CUtensorMap tm_dz_in, tm_dz_wg, tm_g_st[2], tm_wf, tm_wb;
+  CUtensorMap tm_dz_in[2], tm_dz_wg[2], tm_g_st[2], tm_wf, tm_wb;
   __nv_bfloat16 *wf = nullptr, *wb = nullptr;
   float *wp_t = nullptr, *wv1_t = nullptr;
   float *stats = nullptr, *sums = nullptr, *partial = nullptr, *stem_partial = nullptr, *conv_stat = nullptr;
@@ -108,7 +111,10 @@ extern "C" int azg_train_destroy(azg_train* t) {
   cudaSetDevice(t->device);
   for (auto p : t->a) cudaFree(p);
   for (auto p : t->z) cudaFree(p);
-  cudaFree(t->g[0]); cudaFree(t->g[1]); cudaFree(t->dz); cudaFree(t->gskip); cudaFree(t->wf); cudaFree(t->wb);
+  cudaFree(t->g[0]); cudaFree(t->g[1]); cudaFree(t->dzb[0]); cudaFree(t->dzb[1]); cudaFree(t->gskip);
+  for (cudaEvent_t e : t->ev_fork) cudaEventDestroy(e);
+  for (cudaEvent_t e : t->ev_join) cudaEventDestroy(e);
+  if (t->side) cudaStreamDestroy(t->side); cudaFree(t->wf); cudaFree(t->wb);
   cudaFree(t->wp_t); cudaFree(t->wv1_t); cudaFree(t->stats); cudaFree(t->sums); cudaFree(t->partial); cudaFree(t->stem_partial); cudaFree(t->conv_stat);
   cudaFree(t->zh); cudaFree(t->hstats); cudaFree(t->hidden); cudaFree(t->h1); cudaFree(t->value); cudaFree(t->dlogits);
   cudaFree(t->dvpre); cudaFree(t->dhid); cudaFree(t->hsums); cudaFree(t->norm_partial); cudaFree(t->scal); cudaFree(t->counters);
@@ -138,6 +144,7 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   t->conv_mode = t->C == 64 ? 3 : 1;
   { const char* v = getenv("AZG_WGRAD_DESC"); t->wgrad_variant = v ? atoi(v) : 0; }
   { const char* v = getenv("AZG_TRAIN_FUSE_STATS"); t->fuse_stats = v ? atoi(v) : 1; }     // 0: separate statistics pass over z (experiment switch)
+  { const char* v = getenv("AZG_TRAIN_OVERLAP"); t->overlap = v ? atoi(v) : 1; }           // 0: weight gradients on the main stream
   const int C = t->C, L = t->L, B = t->max_batch;
   layout_params(t->lay, C, L);
   t->rows = AZG_NET_FRONT + (size_t)B * 256 + AZG_NET_BACK;
@@ -147,7 +154,8 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   for (int i = 0; i <= L && !rc; ++i) { rc = talloc(t, &t->a[i], act); if (!rc) rc = talloc(t, &t->z[i], act); }
   if (!rc) rc = talloc(t, &t->g[0], act);
   if (!rc) rc = talloc(t, &t->g[1], act);
-  if (!rc) rc = talloc(t, &t->dz, act);
+  if (!rc) rc = talloc(t, &t->dzb[0], act);
+  if (!rc) rc = talloc(t, &t->dzb[1], act);
   if (!rc) rc = talloc(t, &t->gskip, act);
   const size_t wl = (size_t)(L ? L : 1) * 9 * C * C;
   if (!rc) rc = talloc(t, &t->wf, wl);
@@ -184,8 +192,10 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
     if (!rc) rc = train_make_map(&t->tm_a_wg[i], t->a[i], t->rows, C, wg_rows);
     if (!rc) rc = train_make_map(&t->tm_z_st[i], t->z[i], t->rows, C, 32, 32);
   }
-  if (!rc) rc = train_make_map(&t->tm_dz_in, t->dz, t->rows, C, in_rows);
-  if (!rc) rc = train_make_map(&t->tm_dz_wg, t->dz, t->rows, C, 64);
+  for (int k = 0; k < 2 && !rc; ++k) {
+    rc = train_make_map(&t->tm_dz_in[k], t->dzb[k], t->rows, C, in_rows);
+    if (!rc) rc = train_make_map(&t->tm_dz_wg[k], t->dzb[k], t->rows, C, 64);
+  }
   if (!rc) rc = train_make_map(&t->tm_g_st[0], t->g[0], t->rows, C, 32, 32);
   if (!rc) rc = train_make_map(&t->tm_g_st[1], t->g[1], t->rows, C, 32, 32);
   if (!rc) rc = train_make_map(&t->tm_wf, t->wf, (uint64_t)(L ? L : 1) * 9 * C, C, (uint32_t)(C / 2));
@@ -212,6 +222,11 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   cudaMemcpy(t->segs_dev, segs.data(), segs.size() * sizeof(AdamSeg), cudaMemcpyHostToDevice);
   cudaMemcpy(t->block_seg_dev, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice);
   t->zero_shift.assign(C, 0.f);
+  if (cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking) != cudaSuccess) { azg_train_destroy(t); return azg_fail(AZG_E_CUDA, "cudaStreamCreate failed"); }
+  t->ev_fork.assign(L + 1, nullptr); t->ev_join.assign(L + 1, nullptr);
+  for (int i = 0; i <= L; ++i)
+    if (cudaEventCreateWithFlags(&t->ev_fork[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { azg_train_destroy(t); return azg_fail(AZG_E_CUDA, "cudaEventCreate failed"); }
   cudaError_t ce = cudaDeviceSynchronize();
   if (ce != cudaSuccess) { azg_train_destroy(t); return azg_fail(AZG_E_CUDA, cudaGetErrorString(ce)); }
   *out = t;
@@ -329,26 +344,41 @@ extern "C" int azg_train_forward_backward(azg_train* t, const float* planes, con
   // ---- backward
   if ((rc = azg_head_train_bwd_launch(h, t->n_sm, s))) return rc;
   int cur = 0;
-  auto bn_bwd = [&](int idx, const float* gamma, float* dgamma, float* dbeta, bool want_skip) -> int {
+  auto bn_bwd = [&](int idx, const float* gamma, float* dgamma, float* dbeta, bool want_skip, __nv_bfloat16* dz) -> int {
     BnBwdArgs b{};
     b.g = t->g[cur]; b.a = t->a[idx]; b.z = t->z[idx]; b.stats = t->stats + (size_t)idx * 2 * C; b.gamma = gamma; b.n_boards = count;
-    b.partial = t->partial; b.counter = t->counters + 1; b.sums = t->sums; b.dgamma = dgamma; b.dbeta = dbeta; b.dz = t->dz;
+    b.partial = t->partial; b.counter = t->counters + 1; b.sums = t->sums; b.dgamma = dgamma; b.dbeta = dbeta; b.dz = dz;
     b.gskip = want_skip ? t->gskip : nullptr;
     int r = azg_bn_bwd_reduce_launch(C, b, s);
     if (r) return r;
     return azg_bn_bwd_apply_launch(C, b, t->n_sm, s);
   };
+  // Per layer: BatchNorm backward (reduce, apply -> dz), then two independent tensor-core kernels that both read dz:
+  // the input gradient (needed by the next layer down, stays on this stream) and the weight gradient (needed only by the
+  // optimiser).  The weight gradient runs on a side stream next to the HBM-bound BatchNorm passes of the layer below;
+  // dz is double buffered so that those passes do not overwrite what it is still reading.
+  const bool ov = t->overlap != 0;
+  cudaStream_t ws = ov ? t->side : s;
   for (int i = L - 1; i >= 0; --i) {
-    if ((rc = bn_bwd(i + 1, t->params + l.res_bn_w[i], t->grads + l.res_bn_w[i], t->grads + l.res_bn_b[i], (i & 1) != 0))) return rc;
+    const int k = i & 1;
+    if (ov && i + 2 <= L - 1) AZG_CUDA(cudaStreamWaitEvent(s, t->ev_join[i + 2], 0));      // the kernel that last read dzb[k] is done
+    if ((rc = bn_bwd(i + 1, t->params + l.res_bn_w[i], t->grads + l.res_bn_w[i], t->grads + l.res_bn_b[i], (i & 1) != 0, t->dzb[k]))) return rc;
+    if (ov) { AZG_CUDA(cudaEventRecord(t->ev_fork[i], s)); AZG_CUDA(cudaStreamWaitEvent(ws, t->ev_fork[i], 0)); }
     WgradArgs wa{count, t->grads + l.res_conv_w[i], t->error_dev, t->wgrad_variant};
-    if ((rc = azg_wgrad3x3_launch(C, t->tm_dz_wg, t->tm_a_wg[i], wa, t->n_sm, s))) return rc;
+    if ((rc = azg_wgrad3x3_launch(C, t->tm_dz_wg[k], t->tm_a_wg[i], wa, t->n_sm, ws))) return rc;
+    if (ov) AZG_CUDA(cudaEventRecord(t->ev_join[i], ws));
     ConvArgs ca = conv_args(t, i, (i & 1) ? nullptr : t->gskip, t->g[cur ^ 1]);
-    if ((rc = azg_conv3x3_launch(C, t->conv_mode, t->tm_dz_in, t->tm_wb, t->tm_g_st[cur ^ 1], ca, t->n_sm, s))) return rc;
+    if ((rc = azg_conv3x3_launch(C, t->conv_mode, t->tm_dz_in[k], t->tm_wb, t->tm_g_st[cur ^ 1], ca, t->n_sm, s))) return rc;
     cur ^= 1;
   }
-  if ((rc = bn_bwd(0, t->params + l.bn_w, t->grads + l.bn_w, t->grads + l.bn_b, false))) return rc;
-  st.dz = t->dz; st.partial = t->stem_partial; st.dw = t->grads + l.conv_w;
+  const int ks = L >= 2 ? 1 : (L & 1);                     // buffer of the stem's dz: the one layer 1 used (layer 0 may still be read)
+  if (ov && L >= 2) AZG_CUDA(cudaStreamWaitEvent(s, t->ev_join[1], 0));
+  if (ov && L == 1) AZG_CUDA(cudaStreamWaitEvent(s, t->ev_join[0], 0));
+  if ((rc = bn_bwd(0, t->params + l.bn_w, t->grads + l.bn_w, t->grads + l.bn_b, false, t->dzb[L >= 1 ? ks : 0]))) return rc;
+  st.dz = t->dzb[L >= 1 ? ks : 0]; st.partial = t->stem_partial; st.dw = t->grads + l.conv_w;
   if ((rc = azg_stem_train_wgrad_launch(C, st, s))) return rc;
+  if (ov && L >= 1) AZG_CUDA(cudaStreamWaitEvent(s, t->ev_join[0], 0));                   // join: every weight gradient has landed
+  t->last_dz = L >= 1 ? ks : 0;
   t->last_count = count; t->last_g = cur;
   return AZG_OK;
 }
@@ -415,7 +445,7 @@ extern "C" int azg_train_read_activation(azg_train* t, int what, int layer, floa
   if (!t || !out || t->last_count < 1) return azg_fail(AZG_E_ARG, "azg_train_read_activation: nothing to read");
   if ((what == 0 || what == 1) && (layer < 0 || layer > t->L)) return azg_fail(AZG_E_ARG, "azg_train_read_activation: bad layer");
   AZG_USE_DEVICE(t->device);
-  const __nv_bfloat16* src = what == 0 ? t->a[layer] : what == 1 ? t->z[layer] : what == 2 ? t->g[t->last_g] : t->dz;
+  const __nv_bfloat16* src = what == 0 ? t->a[layer] : what == 1 ? t->z[layer] : what == 2 ? t->g[t->last_g] : t->dzb[t->last_dz];
   const size_t total = (size_t)t->last_count * t->C * 225;
   train_unpad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, t->C, t->last_count, out);
   return azg_check_launch("train_unpad_kernel");
@@ -444,19 +474,19 @@ extern "C" int azg_train_debug_conv_grads(azg_train* t, const float* dz, const f
   const int C = t->C;
   const size_t total = (size_t)count * C * 225, act = t->rows * C;
   int rc;
-  AZG_CUDA(cudaMemsetAsync(t->dz, 0, act * 2, s));
+  AZG_CUDA(cudaMemsetAsync(t->dzb[0], 0, act * 2, s));
   AZG_CUDA(cudaMemsetAsync(t->a[layer], 0, act * 2, s));
-  train_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dz, C, count, t->dz);
+  train_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dz, C, count, t->dzb[0]);
   train_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, C, count, t->a[layer]);
   set_count_kernel<<<1, 1, 0, s>>>(t->n_dev, count);
   float* scratch = nullptr;                                   // [9][C][C] accumulator, separate from the bound gradients
   AZG_CUDA(cudaMalloc((void**)&scratch, (size_t)9 * C * C * sizeof(float)));
   AZG_CUDA(cudaMemsetAsync(scratch, 0, (size_t)9 * C * C * sizeof(float), s));
   WgradArgs wa{count, scratch, t->error_dev, t->wgrad_variant};
-  if ((rc = azg_wgrad3x3_launch(C, t->tm_dz_wg, t->tm_a_wg[layer], wa, t->n_sm, s))) { cudaFree(scratch); return rc; }
+  if ((rc = azg_wgrad3x3_launch(C, t->tm_dz_wg[0], t->tm_a_wg[layer], wa, t->n_sm, s))) { cudaFree(scratch); return rc; }
   train_export_conv_kernel<<<(C * C * 9 + 255) / 256, 256, 0, s>>>(scratch, C, dw_out);
   ConvArgs ca = conv_args(t, layer, nullptr, t->g[0]);
-  if ((rc = azg_conv3x3_launch(C, t->conv_mode, t->tm_dz_in, t->tm_wb, t->tm_g_st[0], ca, t->n_sm, s))) { cudaFree(scratch); return rc; }
+  if ((rc = azg_conv3x3_launch(C, t->conv_mode, t->tm_dz_in[0], t->tm_wb, t->tm_g_st[0], ca, t->n_sm, s))) { cudaFree(scratch); return rc; }
   train_unpad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(t->g[0], C, count, da_out);
   cudaError_t e = cudaStreamSynchronize(s);
   cudaFree(scratch);

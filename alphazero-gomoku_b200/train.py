@@ -373,19 +373,36 @@ def gather_examples(sp: SelfPlay) -> torch.Tensor:
 
 
 def gather_rows(rows: torch.Tensor) -> torch.Tensor:
-    """All-gather variable-length rows [n_r, width] (example rows or packed plies) from every rank (padded, with counts)."""
+    """All-gather variable-length rows [n_r, width] (example rows or packed plies) from every rank: one small
+    all-gather of the counts (the only host synchronisation), one all-gather of the padded blocks into a single
+    tensor, then the valid prefixes concatenated rank-major."""
     world, _ = _world()
     if world == 1:
         return rows
-    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n)
-    m = int(max(int(c.item()) for c in counts))
-    pad = torch.zeros((m, rows.shape[1]), dtype=rows.dtype, device=rows.device)
-    pad[: rows.shape[0]] = rows
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad)
-    return torch.cat([p[: int(c.item())] for p, c in zip(parts, counts)], dim=0)
+    into_tensor = dist.get_backend() == "nccl"            # gloo (CPU tests) only has the list form
+
+    def all_gather(block):
+        if into_tensor:
+            out = torch.empty((world,) + tuple(block.shape), dtype=block.dtype, device=block.device)
+            dist.all_gather_into_tensor(out, block)
+            return out
+        parts = [torch.empty_like(block) for _ in range(world)]
+        dist.all_gather(parts, block)
+        return torch.stack(parts)
+
+    counts = all_gather(torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)).reshape(-1).tolist()
+    m = max(counts)
+    if m == 0:
+        return rows[:0]
+    if rows.shape[0] == m:
+        pad = rows.contiguous()
+    else:
+        pad = torch.zeros((m, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        pad[: rows.shape[0]] = rows
+    parts = all_gather(pad)
+    if all(c == m for c in counts):
+        return parts.reshape(world * m, rows.shape[1])
+    return torch.cat([parts[r, :c] for r, c in enumerate(counts)], dim=0)
 
 
 def train_batch_dp(model: PyTorchModel, states, pis, zs) -> dict:

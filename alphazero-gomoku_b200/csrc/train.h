@@ -3,7 +3,8 @@
 #pragma once
 #include "net.h"
 
-#define AZG_TRAIN_PARTIALS 160        // max blocks of the per-channel reduction kernels (about one per SM); partial[output][block]
+#define AZG_TRAIN_PARTIALS 320        // capacity of partial[output][block]; the reduction kernels launch azg_train_red_blocks() <= this
+int azg_train_red_blocks();           // default: one block per SM; AZG_TRAIN_RED_BLOCKS overrides (experiment switch)
 
 // ---- trunk BatchNorm, training mode (batch statistics over boards x 225 pixels) -------------------------------------
 struct BnStatsArgs {

@@ -14,6 +14,7 @@
 // the last block to finish (ticket counter) adds them in block order.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 #include "train.h"
 #include "ptx.cuh"
 
@@ -170,12 +171,16 @@ bn_stats_kernel(BnStatsArgs p) {
   const double n = (double)p.n_boards * 225.0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NW = kRedThreads / 32, PER = C / NW;                 // channels per warp: 8 (C = 128) or 4
-  double sums[2 * PER];
-  warp_sum_partials_n<2 * PER>(p.partial, warp, NW, (int)gridDim.x, sums);     // outputs warp, warp + NW, ...: [0, C) sums, [C, 2C) squares
-  for (int k = 0; k < PER; ++k) {
-    const int c = warp + k * NW;
-    const double s = sums[k], q = sums[PER + k];
+  for (int k = 0; k < PER; k += 2) {                                 // two channels (four sums) per round: few registers
+    const int c0 = warp + k * NW;
+    double sums[4];
+    double sq[2];
+    warp_sum_partials_n<2>(p.partial, c0, NW, (int)gridDim.x, reinterpret_cast<double(&)[2]>(sums[0]));       // sums of channels c0, c0 + NW
+    warp_sum_partials_n<2>(p.partial, C + c0, NW, (int)gridDim.x, sq);                                        // their sums of squares
     if (lane != 0) continue;
+    for (int j = 0; j < 2; ++j) {
+    const int c = c0 + j * NW;
+    const double s = sums[j], q = sq[j];
     const double mean = s / n;
     double var = q / n - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -184,6 +189,7 @@ bn_stats_kernel(BnStatsArgs p) {
     const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
     p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
     p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)unbiased;
+    }
   }
 }
 
@@ -261,13 +267,15 @@ bn_bwd_reduce_kernel(BnBwdArgs p) {
   if (!last_block_arrives(p.counter)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NW = kRedThreads / 32, PER = 2 * C / NW;
-  double sums[PER];
-  warp_sum_partials_n<PER>(p.partial, warp, NW, (int)gridDim.x, sums);
-  if (lane != 0) return;
-  for (int j = 0; j < PER; ++j) {
-    const int t = warp + j * NW, k = t / C, c = t % C;
-    p.sums[k * C + c] = (float)sums[j];
-    if (k == 0) p.dbeta[c] = (float)sums[j]; else p.dgamma[c] = (float)sums[j];
+  for (int j0 = 0; j0 < PER; j0 += 4) {                               // four outputs per round: few registers
+    double sums[4];
+    warp_sum_partials_n<4>(p.partial, warp + j0 * NW, NW, (int)gridDim.x, sums);
+    if (lane != 0) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int t = warp + (j0 + j) * NW, k = t / C, c = t % C;
+      p.sums[k * C + c] = (float)sums[j];
+      if (k == 0) p.dbeta[c] = (float)sums[j]; else p.dgamma[c] = (float)sums[j];
+    }
   }
 }
 
@@ -811,8 +819,8 @@ head_conv_bwd_kernel(HeadTrainArgs p) {
     p.partial[(size_t)t * AZG_TRAIN_PARTIALS + blockIdx.x] = a;
   }
   if (!last_block_arrives(p.counter)) return;
-  constexpr int NW = kEwThreads / 32, BATCH = 8;
-  for (int t0 = threadIdx.x >> 5; t0 < 3 * C; t0 += NW * BATCH) {          // 3C / (8 warps * 8) = 6 (C = 128) or 3 rounds
+  constexpr int NW = kEwThreads / 32, BATCH = 4;
+  for (int t0 = threadIdx.x >> 5; t0 < 3 * C; t0 += NW * BATCH) {          // 3C / (8 warps * 4) = 12 (C = 128) or 6 rounds
     double sums[BATCH];
     warp_sum_partials_n<BATCH>(p.partial, t0, NW, (int)gridDim.x, sums);
     if ((threadIdx.x & 31) != 0) continue;
@@ -916,11 +924,26 @@ int ew_grid(int n_boards, int C, int n_sm) {
 
 }  // namespace
 
+int azg_train_red_blocks() {
+  static int v = 0;
+  if (!v) {
+    // the backward reduction needs 126 registers x 512 threads = one block per SM: more blocks than SMs would run as
+    // a second wave on a few SMs and double the kernel's time (measured: 160 blocks 38 us, SMs idle half of it)
+    const char* e = getenv("AZG_TRAIN_RED_BLOCKS");
+    int dev = 0, n_sm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    v = e ? atoi(e) : n_sm;
+    if (v < 1) v = 1;
+    if (v > AZG_TRAIN_PARTIALS) v = AZG_TRAIN_PARTIALS;
+  }
+  return v;
+}
+
 int azg_bn_stats_launch(int C, const BnStatsArgs& a, cudaStream_t s) {
   return dispatch_c(C, [&](auto c) {
     constexpr int CC = decltype(c)::value;
     int grid = a.n_boards * 256 / (kRedThreads / (CC / 8));
-    if (grid > AZG_TRAIN_PARTIALS) grid = AZG_TRAIN_PARTIALS;
+    if (grid > azg_train_red_blocks()) grid = azg_train_red_blocks();
     if (grid < 1) grid = 1;
     bn_stats_kernel<CC><<<grid, kRedThreads, 0, s>>>(a);
     return azg_check_launch("bn_stats_kernel");
@@ -944,7 +967,7 @@ int azg_bn_bwd_reduce_launch(int C, const BnBwdArgs& a, cudaStream_t s) {
   return dispatch_c(C, [&](auto c) {
     constexpr int CC = decltype(c)::value;
     int grid = a.n_boards * 256 / (kRedThreads / (CC / 8));
-    if (grid > AZG_TRAIN_PARTIALS) grid = AZG_TRAIN_PARTIALS;
+    if (grid > azg_train_red_blocks()) grid = azg_train_red_blocks();
     if (grid < 1) grid = 1;
     bn_bwd_reduce_kernel<CC><<<grid, kRedThreads, 0, s>>>(a);
     return azg_check_launch("bn_bwd_reduce_kernel");
@@ -989,7 +1012,7 @@ int azg_head_train_fwd_launch(const HeadTrainArgs& a, int n_sm, cudaStream_t s) 
   });
   if (rc) return rc;
   int hgrid = (a.n_boards * 225 + 2047) / 2048;
-  if (hgrid > AZG_TRAIN_PARTIALS) hgrid = AZG_TRAIN_PARTIALS;
+  if (hgrid > azg_train_red_blocks()) hgrid = azg_train_red_blocks();
   head_stats_kernel<<<hgrid, 512, 0, s>>>(a);
   if ((rc = azg_check_launch("head_stats_kernel"))) return rc;
   head_fc_fwd_kernel<<<(a.n_boards + kFcBoards - 1) / kFcBoards, 256, 0, s>>>(a);
@@ -1004,13 +1027,13 @@ int azg_head_train_bwd_launch(const HeadTrainArgs& a, int n_sm, cudaStream_t s) 
   head_fc_wgrad_kernel<<<(n_out + 255) / 256, 256, 0, s>>>(a);
   if ((rc = azg_check_launch("head_fc_wgrad_kernel"))) return rc;
   int hgrid = (a.n_boards * 225 + 2047) / 2048;
-  if (hgrid > AZG_TRAIN_PARTIALS) hgrid = AZG_TRAIN_PARTIALS;
+  if (hgrid > azg_train_red_blocks()) hgrid = azg_train_red_blocks();
   head_bn_bwd_reduce_kernel<<<hgrid, 512, 0, s>>>(a);
   if ((rc = azg_check_launch("head_bn_bwd_reduce_kernel"))) return rc;
   return dispatch_c(a.C, [&](auto c) {
     constexpr int CC = decltype(c)::value;
     int grid = a.n_boards * 256 / (kEwThreads / (CC / 8));
-    if (grid > AZG_TRAIN_PARTIALS) grid = AZG_TRAIN_PARTIALS;
+    if (grid > azg_train_red_blocks()) grid = azg_train_red_blocks();
     if (grid < 1) grid = 1;
     head_conv_bwd_kernel<CC><<<grid, kEwThreads, 0, s>>>(a);
     return azg_check_launch("head_conv_bwd_kernel");

@@ -1,7 +1,7 @@
 """Small end-to-end workload that launches every kernel of the library at least once (rules, search with tree reuse
 and GC, both rules, noise, network at 64 and 128 channels, batched self-play) at sizes a checker tool finishes in
-minutes.  Written as a `compute-sanitizer --tool memcheck` target; that tool is closed on the shared GPU pool, so the
-run recorded for this round is the plain one (exits 0).
+minutes, plus the training step and the packed example format.  Written as a `compute-sanitizer` target (memcheck /
+racecheck); profiles/README.md records what the pool allowed.
 
     python tools/sanitize_target.py [--no-net]
 """
@@ -62,6 +62,27 @@ def main():
             sp.step()
         torch.cuda.synchronize()
         sp.close()
+    # training step (forward, backward, clip + Adam) at both widths, without CUDA graphs
+    for blocks, ch in ((1, 64), (1, 128)):
+        torch.manual_seed(0)
+        net = PyTorchModel(n_res_blocks=blocks, channels=ch, device="cuda:0")
+        net.train_graphs = False
+        x = torch.zeros((6, 3, 15, 15), device="cuda")
+        x[:, 2] = 1.0
+        x[1, 0, 7, 7] = 1.0
+        pi = torch.full((6, 225), 1.0 / 225, device="cuda")
+        z = torch.tensor([[1.0], [-1.0], [0.0], [1.0], [0.0], [-1.0]], device="cuda")
+        for _ in range(2):
+            net.train_batch(x, pi, z)
+        net._trainer.check()
+    # packed example exchange format
+    from alphazero_gomoku_b200.selfplay import expand_examples
+    sp = SelfPlay(net, n_games=4, n_sims=24, node_capacity=512, example_capacity=256, max_moves=3, packed_examples=True, max_games=5)
+    while sp.games_running() > 0:
+        sp.step()
+    expand_examples(sp.drain_packed(), True)
+    torch.cuda.synchronize()
+    sp.close()
     print("sanitize target done")
 
 

@@ -92,3 +92,5 @@ struct WgradArgs {
 };
 int azg_wgrad3x3_a_rows();
 int azg_wgrad3x3_launch(int C, const CUtensorMap& tm_dz, const CUtensorMap& tm_a, const WgradArgs& a, int n_sm, cudaStream_t stream);
+// cluster-of-three variant (multicast operands): tm = {dz box 24 rows, dz box 16 rows, a box 32 rows, a box 34 rows}
+int azg_wgrad3x3_cluster_launch(int C, const CUtensorMap* tm, const WgradArgs& a, int n_sm, cudaStream_t stream);

@@ -65,7 +65,9 @@ struct azg_train {
   cudaStream_t side = nullptr;                   // the weight-gradient kernels run here, beside the next layer's BatchNorm passes
   std::vector<cudaEvent_t> ev_fork, ev_join;
   int overlap = 1, last_dz = 0;
-  std::vector<CUtensorMap> tm_a_in, tm_a_wg, tm_z_st;
+  std::vector<CUtensorMap> tm_a_in, tm_a_wg, tm_z_st, tm_a_c32, tm_a_c34;      // *_c*: boxes of the cluster weight-gradient kernel
+  CUtensorMap tm_dz_c24[2], tm_dz_c16[2];
+  int wgrad_cluster = 0;
   CUtensorMap tm_dz_in[2], tm_dz_wg[2], tm_g_st[2], tm_wf, tm_wb;
   __nv_bfloat16 *wf = nullptr, *wb = nullptr;
   float *wp_t = nullptr, *wv1_t = nullptr;
@@ -145,6 +147,10 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   { const char* v = getenv("AZG_WGRAD_DESC"); t->wgrad_variant = v ? atoi(v) : 0; }
   { const char* v = getenv("AZG_TRAIN_FUSE_STATS"); t->fuse_stats = v ? atoi(v) : 1; }     // 0: separate statistics pass over z (experiment switch)
   { const char* v = getenv("AZG_TRAIN_OVERLAP"); t->overlap = v ? atoi(v) : 1; }           // 0: weight gradients on the main stream
+  // 1: clusters of three CTAs sharing their operands by TMA multicast (2.4x less L2 -> SMEM traffic).  Measured slower:
+  // 71 vs 41 us per launch alone, the same step time when overlapped - the kernel is not bound by L2 traffic but by the
+  // 128 x 128 x 16 cta_group::1 UMMA reading 8 KB of shared memory per 64 cycles, and the clusters add lock-step latency.
+  { const char* v = getenv("AZG_WGRAD_CLUSTER"); t->wgrad_cluster = v ? atoi(v) : 0; }
   const int C = t->C, L = t->L, B = t->max_batch;
   layout_params(t->lay, C, L);
   t->rows = AZG_NET_FRONT + (size_t)B * 256 + AZG_NET_BACK;
@@ -186,15 +192,19 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   if (rc) { azg_train_destroy(t); return rc; }
   // TMA descriptors
   const uint32_t in_rows = (uint32_t)azg_conv3x3_rows(t->conv_mode), wg_rows = (uint32_t)azg_wgrad3x3_a_rows();
-  t->tm_a_in.resize(L + 1); t->tm_a_wg.resize(L + 1); t->tm_z_st.resize(L + 1);
+  t->tm_a_in.resize(L + 1); t->tm_a_wg.resize(L + 1); t->tm_z_st.resize(L + 1); t->tm_a_c32.resize(L + 1); t->tm_a_c34.resize(L + 1);
   for (int i = 0; i <= L && !rc; ++i) {
     rc = train_make_map(&t->tm_a_in[i], t->a[i], t->rows, C, in_rows);
     if (!rc) rc = train_make_map(&t->tm_a_wg[i], t->a[i], t->rows, C, wg_rows);
     if (!rc) rc = train_make_map(&t->tm_z_st[i], t->z[i], t->rows, C, 32, 32);
+    if (!rc) rc = train_make_map(&t->tm_a_c32[i], t->a[i], t->rows, C, 32);
+    if (!rc) rc = train_make_map(&t->tm_a_c34[i], t->a[i], t->rows, C, 34);
   }
   for (int k = 0; k < 2 && !rc; ++k) {
     rc = train_make_map(&t->tm_dz_in[k], t->dzb[k], t->rows, C, in_rows);
     if (!rc) rc = train_make_map(&t->tm_dz_wg[k], t->dzb[k], t->rows, C, 64);
+    if (!rc) rc = train_make_map(&t->tm_dz_c24[k], t->dzb[k], t->rows, C, 24);
+    if (!rc) rc = train_make_map(&t->tm_dz_c16[k], t->dzb[k], t->rows, C, 16);
   }
   if (!rc) rc = train_make_map(&t->tm_g_st[0], t->g[0], t->rows, C, 32, 32);
   if (!rc) rc = train_make_map(&t->tm_g_st[1], t->g[1], t->rows, C, 32, 32);
@@ -296,6 +306,16 @@ static HeadTrainArgs head_args(azg_train* t, int count, const float* pi, const f
   return h;
 }
 
+// weight gradient of trunk layer `layer` from dzb[k] and a[layer] into dw ([9][C][C], accumulated)
+static int launch_wgrad(azg_train* t, int k, int layer, int count, float* dw, cudaStream_t s) {
+  WgradArgs wa{count, dw, t->error_dev, t->wgrad_variant};
+  if (t->wgrad_cluster) {
+    const CUtensorMap tm[4] = {t->tm_dz_c24[k], t->tm_dz_c16[k], t->tm_a_c32[layer], t->tm_a_c34[layer]};
+    return azg_wgrad3x3_cluster_launch(t->C, tm, wa, t->n_sm, s);
+  }
+  return azg_wgrad3x3_launch(t->C, t->tm_dz_wg[k], t->tm_a_wg[layer], wa, t->n_sm, s);
+}
+
 static ConvArgs conv_args(azg_train* t, int layer, const __nv_bfloat16* residual, __nv_bfloat16* out) {
   ConvArgs a{};
   a.n_boards = t->n_dev; a.max_boards = t->max_batch; a.layer = layer; a.relu = 0; a.shift_host = t->zero_shift.data();
@@ -364,8 +384,7 @@ extern "C" int azg_train_forward_backward(azg_train* t, const float* planes, con
     if (ov && i + 2 <= L - 1) AZG_CUDA(cudaStreamWaitEvent(s, t->ev_join[i + 2], 0));      // the kernel that last read dzb[k] is done
     if ((rc = bn_bwd(i + 1, t->params + l.res_bn_w[i], t->grads + l.res_bn_w[i], t->grads + l.res_bn_b[i], (i & 1) != 0, t->dzb[k]))) return rc;
     if (ov) { AZG_CUDA(cudaEventRecord(t->ev_fork[i], s)); AZG_CUDA(cudaStreamWaitEvent(ws, t->ev_fork[i], 0)); }
-    WgradArgs wa{count, t->grads + l.res_conv_w[i], t->error_dev, t->wgrad_variant};
-    if ((rc = azg_wgrad3x3_launch(C, t->tm_dz_wg[k], t->tm_a_wg[i], wa, t->n_sm, ws))) return rc;
+    if ((rc = launch_wgrad(t, k, i, count, t->grads + l.res_conv_w[i], ws))) return rc;
     if (ov) AZG_CUDA(cudaEventRecord(t->ev_join[i], ws));
     ConvArgs ca = conv_args(t, i, (i & 1) ? nullptr : t->gskip, t->g[cur ^ 1]);
     if ((rc = azg_conv3x3_launch(C, t->conv_mode, t->tm_dz_in[k], t->tm_wb, t->tm_g_st[cur ^ 1], ca, t->n_sm, s))) return rc;
@@ -482,8 +501,7 @@ extern "C" int azg_train_debug_conv_grads(azg_train* t, const float* dz, const f
   float* scratch = nullptr;                                   // [9][C][C] accumulator, separate from the bound gradients
   AZG_CUDA(cudaMalloc((void**)&scratch, (size_t)9 * C * C * sizeof(float)));
   AZG_CUDA(cudaMemsetAsync(scratch, 0, (size_t)9 * C * C * sizeof(float), s));
-  WgradArgs wa{count, scratch, t->error_dev, t->wgrad_variant};
-  if ((rc = azg_wgrad3x3_launch(C, t->tm_dz_wg[0], t->tm_a_wg[layer], wa, t->n_sm, s))) { cudaFree(scratch); return rc; }
+  if ((rc = launch_wgrad(t, 0, layer, count, scratch, s))) { cudaFree(scratch); return rc; }
   train_export_conv_kernel<<<(C * C * 9 + 255) / 256, 256, 0, s>>>(scratch, C, dw_out);
   ConvArgs ca = conv_args(t, layer, nullptr, t->g[0]);
   if ((rc = azg_conv3x3_launch(C, t->conv_mode, t->tm_dz_in[0], t->tm_wb, t->tm_g_st[0], ca, t->n_sm, s))) { cudaFree(scratch); return rc; }

@@ -222,6 +222,9 @@ bn_finalize_kernel(BnStatsArgs p, int C, int n_slots) {
 template <int C>
 __global__ void __launch_bounds__(kEwThreads)
 bn_apply_kernel(BnApplyArgs p) {
+  // the next kernel in the stream is the convolution that consumes `out`: let it set up its barriers, tensor memory
+  // and resident weights on the side while this pass runs (it waits for this grid's completion before reading)
+  ptx::grid_dep_launch();
   constexpr int CG = C / 8;
   const long long total = (long long)p.n_boards * 256 * CG;
   const long long stride = (long long)gridDim.x * kEwThreads;          // a multiple of CG: the channel group of a thread is fixed
@@ -283,6 +286,7 @@ bn_bwd_reduce_kernel(BnBwdArgs p) {
 template <int C>
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(BnBwdArgs p) {
+  ptx::grid_dep_launch();                 // the input-gradient convolution follows: see bn_apply_kernel
   constexpr int CG = C / 8;
   const long long total = (long long)p.n_boards * 256 * CG;
   const long long stride = (long long)gridDim.x * kEwThreads;
@@ -351,15 +355,24 @@ stem_train_fwd_kernel(StemTrainArgs p) {
   for (int i = 0; i < 27; ++i) w[i] = p.w[c * 27 + i];
   for (int b = blockIdx.x; b < p.n_boards; b += gridDim.x) {
     stem_load_planes(xs, p.planes, b);
-    for (int pix = ps; pix < 225; pix += kStemSlices) {
-      const int r = pix / 15, cc = pix % 15;
-      float acc = 0.f;
+    for (int r = ps; r < 15; r += kStemSlices) {          // a board row per iteration; a 3-column window slides along it
+      float c0[9], c1[9], c2[9];                            // [plane * 3 + kernel row]: columns cc-1, cc, cc+1 (padded coordinates)
 #pragma unroll
-      for (int pl = 0; pl < 3; ++pl)
+      for (int q = 0; q < 9; ++q) { c0[q] = xs[q / 3][r + q % 3][0]; c1[q] = xs[q / 3][r + q % 3][1]; }
+      __nv_bfloat16* zr = p.z + ((size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)((r + 1) * 16)) * C + c;
+#pragma unroll 3
+      for (int cc = 0; cc < 15; ++cc) {
+        float acc = 0.f;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc = fmaf(xs[pl][r + t / 3][cc + t % 3], w[pl * 9 + t], acc);
-      const size_t row = (size_t)AZG_NET_FRONT + (size_t)b * 256 + (size_t)((r + 1) * 16 + cc);
-      p.z[row * C + c] = __float2bfloat16_rn(acc);
+        for (int q = 0; q < 9; ++q) {
+          c2[q] = xs[q / 3][r + q % 3][cc + 2];
+          const int wi = (q / 3) * 9 + (q % 3) * 3;       // weight index of (plane, kernel row, kernel column 0)
+          acc = fmaf(c0[q], w[wi], acc); acc = fmaf(c1[q], w[wi + 1], acc); acc = fmaf(c2[q], w[wi + 2], acc);
+        }
+        zr[(size_t)cc * C] = __float2bfloat16_rn(acc);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { c0[q] = c1[q]; c1[q] = c2[q]; }
+      }
     }
   }
 }
@@ -382,14 +395,24 @@ stem_train_wgrad_kernel(StemTrainArgs p) {
   for (int i = 0; i < 27; ++i) acc[i] = 0.f;
   stem_load_planes(xs, p.planes, b);
   const __nv_bfloat16* dzb = p.dz + ((size_t)AZG_NET_FRONT + (size_t)b * 256) * C + c;
-#pragma unroll 4
-  for (int pix = ps; pix < 225; pix += kStemWSlices) {
-    const int r = pix / 15, cc = pix % 15;
-    const float d = __bfloat162float(dzb[(size_t)((r + 1) * 16 + cc) * C]);
+  for (int r = ps; r < 15; r += kStemWSlices) {            // a board row per iteration: its 15 gradients are fetched at once
+    float d[15];
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl)
+    for (int cc = 0; cc < 15; ++cc) d[cc] = __bfloat162float(dzb[(size_t)((r + 1) * 16 + cc) * C]);
+    float c0[9], c1[9], c2[9];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc[pl * 9 + t] = fmaf(d, xs[pl][r + t / 3][cc + t % 3], acc[pl * 9 + t]);
+    for (int q = 0; q < 9; ++q) { c0[q] = xs[q / 3][r + q % 3][0]; c1[q] = xs[q / 3][r + q % 3][1]; }
+#pragma unroll
+    for (int cc = 0; cc < 15; ++cc) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        c2[q] = xs[q / 3][r + q % 3][cc + 2];
+        const int wi = (q / 3) * 9 + (q % 3) * 3;
+        acc[wi] = fmaf(d[cc], c0[q], acc[wi]); acc[wi + 1] = fmaf(d[cc], c1[q], acc[wi + 1]); acc[wi + 2] = fmaf(d[cc], c2[q], acc[wi + 2]);
+      }
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { c0[q] = c1[q]; c1[q] = c2[q]; }
+    }
   }
 #pragma unroll
   for (int i = 0; i < 27; ++i) red[ps][i][c] = acc[i];
@@ -507,7 +530,7 @@ head_stats_kernel(HeadTrainArgs p) {
 
 // dense layers + loss, NB boards per block: logits = hidden_p Wp^T + bp; h1 = relu(hidden_v Wv1^T + bv1);
 // value = tanh(h1 w2 + b2); KL row sum, squared error, dlogits, dvpre.
-constexpr int kFcBoards = 4;
+constexpr int kFcBoards = 2;
 __global__ void __launch_bounds__(256)
 head_fc_fwd_kernel(HeadTrainArgs p) {
   __shared__ float hs[kFcBoards][675];
@@ -534,6 +557,7 @@ head_fc_fwd_kernel(HeadTrainArgs p) {
   if (j < 225) {
 #pragma unroll
     for (int k = 0; k < kFcBoards; ++k) logit[k] = p.bp[j];
+#pragma unroll 10
     for (int i = 0; i < 450; ++i) {
       const float w = p.wp_t[(size_t)i * 225 + j];
 #pragma unroll
@@ -547,6 +571,7 @@ head_fc_fwd_kernel(HeadTrainArgs p) {
     float acc[kFcBoards];
 #pragma unroll
     for (int k = 0; k < kFcBoards; ++k) acc[k] = p.bv1[tid];
+#pragma unroll 9
     for (int i = 0; i < 225; ++i) {
       const float w = p.wv1_t[(size_t)i * 64 + tid];
 #pragma unroll
@@ -651,68 +676,77 @@ head_fc_bwd_data_kernel(HeadTrainArgs p) {
   __syncthreads();
   if (tid < 450) {
     float acc = 0.f;
+#pragma unroll 9
     for (int jj = 0; jj < 225; ++jj) acc = fmaf(dl[jj], p.wp[(size_t)jj * 450 + tid], acc);
     const size_t o = (size_t)b * 675 + tid;
     p.dhid[o] = p.hidden[o] > 0.f ? acc : 0.f;
   }
   if (tid < 225) {
     float acc = 0.f;
+#pragma unroll 8
     for (int t = 0; t < 64; ++t) acc = fmaf(dh1[t], p.wv1[(size_t)t * 225 + tid], acc);
     const size_t o = (size_t)b * 675 + 450 + tid;
     p.dhid[o] = p.hidden[o] > 0.f ? acc : 0.f;
   }
 }
 
-// weight gradients of the dense layers: one thread per output element, loop over the batch (fixed order)
+// weight gradients of the dense layers: thread = output element, blockIdx.y = slice of the batch (a thread that walked
+// the whole batch alone was bound by 512+ dependent L2 round trips); the slices meet in floating-point atomics on the
+// zeroed gradient vector.
+constexpr int kFcSplit = 16;
 __global__ void __launch_bounds__(256)
 head_fc_wgrad_kernel(HeadTrainArgs p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int B = p.n_boards;
+  const int per = (p.n_boards + kFcSplit - 1) / kFcSplit;
+  const int b0 = blockIdx.y * per, b1 = min(p.n_boards, b0 + per);
+  if (b0 >= b1) return;
   constexpr int N_WP = 225 * 450, N_BP = 225, N_WV = 64 * 225, N_BV = 64, N_W2 = 64;
   if (i < N_WP) {
     const int j = i / 450, k = i % 450;
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc = fmaf(p.dlogits[(size_t)b * 225 + j], p.hidden[(size_t)b * 675 + k], acc);
-    p.d_wp[i] = acc;
+#pragma unroll 8
+    for (int b = b0; b < b1; ++b) acc = fmaf(p.dlogits[(size_t)b * 225 + j], p.hidden[(size_t)b * 675 + k], acc);
+    atomicAdd(p.d_wp + i, acc);
     return;
   }
   int r = i - N_WP;
   if (r < N_BP) {
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += p.dlogits[(size_t)b * 225 + r];
-    p.d_bp[r] = acc;
+    for (int b = b0; b < b1; ++b) acc += p.dlogits[(size_t)b * 225 + r];
+    atomicAdd(p.d_bp + r, acc);
     return;
   }
   r -= N_BP;
   if (r < N_WV) {
     const int t = r / 225, k = r % 225;
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) {
+#pragma unroll 8
+    for (int b = b0; b < b1; ++b) {
       const float d = p.h1[(size_t)b * 64 + t] > 0.f ? p.dvpre[b] * p.w2[t] : 0.f;
       acc = fmaf(d, p.hidden[(size_t)b * 675 + 450 + k], acc);
     }
-    p.d_wv1[r] = acc;
+    atomicAdd(p.d_wv1 + r, acc);
     return;
   }
   r -= N_WV;
   if (r < N_BV) {
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += p.h1[(size_t)b * 64 + r] > 0.f ? p.dvpre[b] * p.w2[r] : 0.f;
-    p.d_bv1[r] = acc;
+    for (int b = b0; b < b1; ++b) acc += p.h1[(size_t)b * 64 + r] > 0.f ? p.dvpre[b] * p.w2[r] : 0.f;
+    atomicAdd(p.d_bv1 + r, acc);
     return;
   }
   r -= N_BV;
   if (r < N_W2) {
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc = fmaf(p.dvpre[b], p.h1[(size_t)b * 64 + r], acc);
-    p.d_w2[r] = acc;
+    for (int b = b0; b < b1; ++b) acc = fmaf(p.dvpre[b], p.h1[(size_t)b * 64 + r], acc);
+    atomicAdd(p.d_w2 + r, acc);
     return;
   }
   r -= N_W2;
   if (r == 0) {
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += p.dvpre[b];
-    p.d_b2[0] = acc;
+    for (int b = b0; b < b1; ++b) acc += p.dvpre[b];
+    atomicAdd(p.d_b2, acc);
   }
 }
 
@@ -1024,7 +1058,7 @@ int azg_head_train_bwd_launch(const HeadTrainArgs& a, int n_sm, cudaStream_t s) 
   int rc = azg_check_launch("head_fc_bwd_data_kernel");
   if (rc) return rc;
   constexpr int n_out = 225 * 450 + 225 + 64 * 225 + 64 + 64 + 1;
-  head_fc_wgrad_kernel<<<(n_out + 255) / 256, 256, 0, s>>>(a);
+  head_fc_wgrad_kernel<<<dim3((n_out + 255) / 256, kFcSplit), 256, 0, s>>>(a);
   if ((rc = azg_check_launch("head_fc_wgrad_kernel"))) return rc;
   int hgrid = (a.n_boards * 225 + 2047) / 2048;
   if (hgrid > azg_train_red_blocks()) hgrid = azg_train_red_blocks();
@@ -1033,7 +1067,8 @@ int azg_head_train_bwd_launch(const HeadTrainArgs& a, int n_sm, cudaStream_t s) 
   return dispatch_c(a.C, [&](auto c) {
     constexpr int CC = decltype(c)::value;
     int grid = a.n_boards * 256 / (kEwThreads / (CC / 8));
-    if (grid > azg_train_red_blocks()) grid = azg_train_red_blocks();
+    const int cap = 2 * azg_train_red_blocks() < AZG_TRAIN_PARTIALS ? 2 * azg_train_red_blocks() : AZG_TRAIN_PARTIALS;      // 62 registers, 256 threads: two blocks per SM
+    if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     head_conv_bwd_kernel<CC><<<grid, kEwThreads, 0, s>>>(a);
     return azg_check_launch("head_conv_bwd_kernel");

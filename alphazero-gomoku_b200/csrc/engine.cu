@@ -3,6 +3,7 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.cuh"
 #include "host.h"
@@ -68,6 +69,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
   while (h < 2 * cfg->node_capacity) h <<= 1;
   d.hcap = h;
   d.noise_on = cfg->noise_on; d.noise_plies = cfg->noise_plies; d.n_sims = 0; d.game_base = cfg->game_base;
+  { const char* v = getenv("AZG_FILL_L1"); d.fill_l1 = v ? atoi(v) : 1; }        // experiment switch, see tree.cu ldx
   d.cpuct = (float)cfg->cpuct; d.cpuct64 = cfg->cpuct; d.eps = cfg->eps; d.alpha = cfg->alpha; d.seed = cfg->seed;
   const size_t G = d.G, C = d.cap;
   int rc = AZG_OK;

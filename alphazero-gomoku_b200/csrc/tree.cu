@@ -88,6 +88,15 @@ __device__ __forceinline__ void node_fill(const azg_dev& e, int g, int node, uin
   }
 }
 
+// Loads of a game's slab inside FILL.  One warp owns a game and is the only reader and writer of its slab while the
+// kernel runs.  L1 = false: every load goes to L2 (ld.cg) because the back-up updates N and W with L2 atomics that an
+// L1 line would not see.  L1 = true (Gomoku): the back-up is a plain load-add-store by the owning warp - a path never
+// contains the same (node, action) twice there, which Pente's captures could in principle produce - so ordinary
+// L1-cached loads stay coherent (same SM, write-through) and the root and the upper levels of the tree, read by every
+// simulation of a launch, come from L1 instead of paying an L2 round trip per level.
+template <bool L1, typename T>
+__device__ __forceinline__ T ldx(const T* p) { return L1 ? __ldca(p) : __ldcg(p); }
+
 // Everything the selection step needs from one node, fetched with ONE round trip: the child
 // arrays (lane L: children 8L..8L+7), the flags, and the stored key for the transposition check.
 struct NodeData {
@@ -97,26 +106,27 @@ struct NodeData {
   uint32_t keyw;     // lanes 0..15: key word l of the node
 };
 
+template <bool L1 = false>
 __device__ __forceinline__ void node_load(const azg_dev& e, int g, int node, NodeData& nd) {
   const int l = lane_id();
   const size_t off = azg_node_off(e, g, node);
   const size_t base = off * AZG_ROW;
-  nd.meta = __ldcg(&e.meta[off]);
-  nd.keyw = l < 16 ? __ldcg(&e.key[off * 16 + l]) : 0u;
+  nd.meta = ldx<L1>(&e.meta[off]);
+  nd.keyw = l < 16 ? ldx<L1>(&e.key[off * 16 + l]) : 0u;
   if (l < 28) {
     const float4* P = reinterpret_cast<const float4*>(e.P + base + 8 * l);
     const int4* Nn = reinterpret_cast<const int4*>(e.Nv + base + 8 * l);
     const int4* Ww = reinterpret_cast<const int4*>(e.W + base + 8 * l);
-    const float4 pa = __ldcg(P), pb = __ldcg(P + 1);
-    const int4 na = __ldcg(Nn), nb = __ldcg(Nn + 1);
-    const int4 wa = __ldcg(Ww), wb = __ldcg(Ww + 1);
+    const float4 pa = ldx<L1>(P), pb = ldx<L1>(P + 1);
+    const int4 na = ldx<L1>(Nn), nb = ldx<L1>(Nn + 1);
+    const int4 wa = ldx<L1>(Ww), wb = ldx<L1>(Ww + 1);
     nd.p[0] = pa.x; nd.p[1] = pa.y; nd.p[2] = pa.z; nd.p[3] = pa.w; nd.p[4] = pb.x; nd.p[5] = pb.y; nd.p[6] = pb.z; nd.p[7] = pb.w;
     nd.n[0] = na.x; nd.n[1] = na.y; nd.n[2] = na.z; nd.n[3] = na.w; nd.n[4] = nb.x; nd.n[5] = nb.y; nd.n[6] = nb.z; nd.n[7] = nb.w;
     nd.w[0] = wa.x; nd.w[1] = wa.y; nd.w[2] = wa.z; nd.w[3] = wa.w; nd.w[4] = wb.x; nd.w[5] = wb.y; nd.w[6] = wb.z; nd.w[7] = wb.w;
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { nd.p[j] = 0.f; nd.n[j] = 0; nd.w[j] = 0; }
-    if (l == 28) { nd.p[0] = __ldcg(e.P + base + 224); nd.n[0] = __ldcg(e.Nv + base + 224); nd.w[0] = __ldcg(e.W + base + 224); }
+    if (l == 28) { nd.p[0] = ldx<L1>(e.P + base + 224); nd.n[0] = ldx<L1>(e.Nv + base + 224); nd.w[0] = ldx<L1>(e.W + base + 224); }
   }
 }
 
@@ -132,6 +142,7 @@ __device__ __forceinline__ bool node_key_matches(const NodeData& nd, const WPos&
 // Transposition lookup that also fetches the node: the candidate's arrays are requested together
 // with its key, so a hit costs two dependent memory round trips (probe window, node) instead of
 // three.  The full key is always compared (the tag only selects candidates).
+template <bool L1 = false>
 __device__ __forceinline__ int table_find_load(const azg_dev& e, int g, const WPos& p, unsigned long long h, int* ins,
                                                NodeData& nd) {
   const unsigned long long* tab = e.slots + (size_t)g * (size_t)e.hcap;
@@ -140,13 +151,13 @@ __device__ __forceinline__ int table_find_load(const azg_dev& e, int g, const WP
   int win = (int)((uint32_t)h & (uint32_t)(nwin - 1));
   const int l = lane_id();
   for (int t = 0; t < nwin; ++t) {
-    const unsigned long long s = __ldcg(&tab[(win << 5) + l]);
+    const unsigned long long s = ldx<L1>(&tab[(win << 5) + l]);
     uint32_t mm = __ballot_sync(AZG_FULL, s != 0ULL && (uint32_t)(s >> 32) == tag);
     while (mm) {
       const int src = __ffs(mm) - 1;
       mm &= mm - 1;
       const int node = (int)__shfl_sync(AZG_FULL, (uint32_t)s, src) - 1;
-      node_load(e, g, node, nd);
+      node_load<L1>(e, g, node, nd);
       if (node_key_matches(nd, p)) return node;
     }
     const uint32_t em = __ballot_sync(AZG_FULL, s == 0ULL);
@@ -234,7 +245,8 @@ __device__ __forceinline__ int puct_select(const azg_dev& e, int g, const NodeDa
 // ------------------------------------------------------------------------------------------------
 // FILL
 // ------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
+template <bool L1>
+__device__ __forceinline__ void fill_body(const azg_dev& e) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= e.G) return;
   const int l = lane_id();
@@ -264,7 +276,7 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
       pos = wpos_load(&ctl->scratch);
       depth = __ldcg(&ctl->depth);
       node = __ldcg(&ctl->resume_node);
-      node_load(e, g, node, nd);
+      node_load<L1>(e, g, node, nd);
       select_here = true;                       // fall through to selection at the evaluated leaf
       resume = false;
     } else {
@@ -281,8 +293,8 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
         if (!wpos_any_empty(pos)) { v = 0; break; }
         const unsigned long long h = wpos_hash(pos);
         int ins = -1;
-        if (depth == 0 && root_node >= 0) { node = root_node; node_load(e, g, node, nd); }   // the root key is fixed for the run
-        else node = table_find_load(e, g, pos, h, &ins, nd);
+        if (depth == 0 && root_node >= 0) { node = root_node; node_load<L1>(e, g, node, nd); }   // the root key is fixed for the run
+        else node = table_find_load<L1>(e, g, pos, h, &ins, nd);
         if (node < 0) {                                        // new_mcts_alpha.py:114-132
           if (ins < 0) { err |= AZG_ERR_HASH; break; }
           if (n_free > 0) node = __ldcg(&freelist[--n_free]);
@@ -320,8 +332,13 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
     for (int d = l; d < depth; d += 32) {
       const uint32_t pe = __ldcg(&path[d]);
       const size_t idx = azg_node_off(e, g, (int)(pe >> 8)) * AZG_ROW + (pe & 255u);
-      atomicAdd(&e.Nv[idx], 1);
-      if (v != 0) atomicAdd(&e.W[idx], ((depth - d) & 1) ? -v : v);
+      if (L1) {           // the owning warp is the only writer, and a Gomoku path holds every (node, action) once
+        e.Nv[idx] = __ldca(&e.Nv[idx]) + 1;
+        if (v != 0) e.W[idx] = __ldca(&e.W[idx]) + (((depth - d) & 1) ? -v : v);
+      } else {
+        atomicAdd(&e.Nv[idx], 1);
+        if (v != 0) atomicAdd(&e.W[idx], ((depth - d) & 1) ? -v : v);
+      }
     }
     __threadfence_block();
     __syncwarp();
@@ -344,6 +361,11 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
     ctl->visits += visits;
     ctl->sims += sims;
   }
+}
+
+extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
+  if (e.rule == AZG_RULE_GOMOKU && e.fill_l1) fill_body<true>(e);
+  else fill_body<false>(e);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -254,3 +254,31 @@ def test_world_average_and_checkpoint_roundtrip(tmp_path):
     big = make_model(1, 256, seed=1)
     out = big.train_batch(X[:8], P[:8], Z[:8])
     assert np.isfinite(out["total_loss"])
+
+
+@pytest.mark.parametrize("ch,n", [(64, 2), (128, 33), (64, 129), (128, 300)])
+def test_ragged_batch_sizes_against_oracle(ch, n):
+    """Batch sizes that are no multiple of anything the kernels tile by (2 = the smallest BatchNorm allows, 33, 129, 300:
+    partly filled clusters, CTAs without boards in the weight-gradient grid, head blocks with one board): losses against
+    the fp32 oracle and head gradients (well conditioned) to 3 %; a second call with another size on the same engine."""
+    z = load_golden("train_steps.npz")
+    X0, P0, Z0 = unpack_planes(z["curve/planes_bits"]), z["curve/pi"], z["curve/z"]
+    reps = (n + len(X0) - 1) // len(X0)
+    X, P, Z = np.tile(X0, (reps, 1, 1, 1))[:n], np.tile(P0, (reps, 1))[:n], np.tile(Z0, (reps, 1))[:n]
+    model = make_model(1, ch, seed=7)
+    sd = {k: v.detach().cpu().clone() for k, v in model.net.state_dict().items()}
+    tr = model._ensure_trainer(max(n, 64))
+    model.net.train()
+    for m in (n, max(2, n // 2)):
+        losses = tr.forward_backward(torch.from_numpy(X[:m]), torch.from_numpy(P[:m]), torch.from_numpy(Z[:m])).cpu().numpy()
+        tr.check()
+        torch.set_num_threads(8)
+        kl, mse, grads, _ = otrain.gradients(sd, torch.from_numpy(X[:m]), torch.from_numpy(P[:m]), torch.from_numpy(Z[:m]))
+        assert abs(losses[0] - kl) <= TOL["loss_rel"] * kl and abs(losses[1] - mse) <= TOL["value_rel"] * mse + 1e-3, (m, losses, kl, mse)
+        got = tr.gradients()
+        for k in ("policy_fc.weight", "policy_fc.bias", "value_fc2.weight"):
+            assert rel(got[k].cpu(), grads[k]) <= 0.05, (m, k, rel(got[k].cpu(), grads[k]))
+        for k in ("res_blocks.0.conv1.weight", "res_blocks.0.conv2.weight", "conv.weight"):
+            assert cos(got[k].cpu(), grads[k]) >= (0.9 if m < 8 else TOL["grad_cos"]), (m, k, cos(got[k].cpu(), grads[k]))
+        # the running statistics were touched by the forward pass: restore them for the second size
+        model.net.load_state_dict(sd)

@@ -3,7 +3,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_dp_smoke.py
 
 Every rank plays its share of the games on its own GPU, examples are all-gathered, the Adam step
-uses NCCL-averaged gradients; at the end all ranks must hold bit-identical weights."""
+uses NCCL-averaged gradients; at the end all ranks must hold a bit-identical state_dict (weights and
+BatchNorm buffers)."""
 import os
 import sys
 import tempfile
@@ -25,7 +26,8 @@ def main():
                               batch_size=64 * dist.get_world_size(), epochs_per_iter=1, temp_threshold=8, eval_games=4,
                               eval_mcts_simulations=16, win_rate_threshold=0.0, cpuct=1.2, model_dir=out, dirichlet_alpha=0.3,
                               dirichlet_epsilon=0.25, dirichlet_n_moves=30, n_res_blocks=1, channels=64)
-    flat = torch.cat([p.detach().reshape(-1) for p in best.net.parameters()])
+    # parameters AND buffers (BatchNorm running statistics are averaged over the ranks after every training phase)
+    flat = torch.cat([p.detach().reshape(-1).double() for p in list(best.net.parameters()) + list(best.net.buffers())])
     parts = [torch.empty_like(flat) for _ in range(dist.get_world_size())]
     dist.all_gather(parts, flat)
     same = all(torch.equal(parts[0], q) for q in parts[1:])

@@ -61,6 +61,8 @@ struct azg_dev {
   float* P;                     // [G][cap][AZG_ROW]
   int32_t* Nv;                  // [G][cap][AZG_ROW]
   int32_t* W;                   // [G][cap][AZG_ROW]
+  int32_t* child;               // [G][cap][AZG_ROW] Gomoku only (else null): what playing action a from this node leads to -
+                                //   0 unknown, 1 terminal with a winner, 2 terminal draw, n + 4 = node n (tree.cu, fill_body)
   uint32_t* key;                // [G][cap][16]
   uint32_t* meta;               // [G][cap]  bit0 alive, bit1-2 player, bits 4-7 p64 slot+1
   unsigned long long* slots;    // [G][hcap] (tag<<32)|(node+1), 0 empty

@@ -74,6 +74,18 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
   const size_t G = d.G, C = d.cap;
   int rc = AZG_OK;
   int64_t& tot = e->bytes;
+  {
+    // Gomoku: per-node child codes (see tree.cu): a re-visited child costs one load, no win test, hash or table probe.
+    // A recorded experiment, OFF by default (AZG_CHILD_CODES=1 enables it): exact, but measured SLOWER - single game
+    // 160 -> 184 ms per 5 000-simulation move (6x128), batched step -0.4 %, +912 bytes per node (95 -> 126 GB at 2 048
+    // x 16 384 nodes).  Most descents end after a few levels at a NEW child (the reference resets N/W on every flush, so
+    // placeholder children of equal prior are walked round-robin), where the code is unknown and only costs: one more
+    // 32-byte load per lane and node, a shuffle, a zeroed row per new node and a store per new edge.
+    const char* v = getenv("AZG_CHILD_CODES");
+    const bool want = d.rule == AZG_RULE_GOMOKU && (v ? atoi(v) != 0 : false);
+    d.child = nullptr;
+    if (want && (rc = dev_alloc(&d.child, G * C * AZG_ROW, &tot))) { azg_destroy(e); return rc; }
+  }
   if ((rc = dev_alloc(&d.ctl, G, &tot)) || (rc = dev_alloc(&d.P, G * C * AZG_ROW, &tot)) ||
       (rc = dev_alloc(&d.Nv, G * C * AZG_ROW, &tot)) || (rc = dev_alloc(&d.W, G * C * AZG_ROW, &tot)) ||
       (rc = dev_alloc(&d.key, G * C * 16, &tot)) || (rc = dev_alloc(&d.meta, G * C, &tot)) ||
@@ -114,7 +126,7 @@ extern "C" int azg_destroy(azg_engine* e) {
   if (!e) return AZG_OK;
   cudaSetDevice(e->cfg.device);
   azg_dev& d = e->dev;
-  cudaFree(d.ctl); cudaFree(d.P); cudaFree(d.Nv); cudaFree(d.W); cudaFree(d.key); cudaFree(d.meta); cudaFree(d.slots);
+  cudaFree(d.ctl); cudaFree(d.P); cudaFree(d.Nv); cudaFree(d.W); cudaFree(d.child); cudaFree(d.key); cudaFree(d.meta); cudaFree(d.slots);
   cudaFree(d.freelist); cudaFree(d.path); cudaFree(d.P64); cudaFree(d.leaf_game); cudaFree(d.leaf_node);
   cudaFree(d.counters); cudaFree(e->stats_dev);
   cudaFree(e->sp.ex_key); cudaFree(e->sp.ex_player); cudaFree(e->sp.ex_pi); cudaFree(e->sp.n_plies); cudaFree(e->sp.n_done);

@@ -65,6 +65,12 @@ __device__ __forceinline__ void node_write_key(const azg_dev& e, int g, int node
   const uint32_t x1 = __shfl_sync(AZG_FULL, p.w1, (l & 7) << 2);
   if (l < 16) e.key[off * 16 + l] = (l < 8 ? x0 : x1);
   if (l == 16) e.meta[off] = AZG_META_ALIVE | ((uint32_t)p.player << 1);
+  if (e.child) {                                   // a new node knows nothing about its children yet
+    const size_t base = off * AZG_ROW;
+    int4* c = reinterpret_cast<int4*>(e.child + base + 8 * l);
+    if (l < 28) { c[0] = make_int4(0, 0, 0, 0); c[1] = make_int4(0, 0, 0, 0); }
+    else if (l == 28) e.child[base + 224] = 0;
+  }
 }
 
 // children arrays of a node: lane L < 28 owns elements 8L..8L+7, lane 28 owns element 224.
@@ -102,11 +108,13 @@ __device__ __forceinline__ T ldx(const T* p) { return L1 ? __ldca(p) : __ldcg(p)
 struct NodeData {
   float p[8];
   int n[8], w[8];
+  int c[8];          // child codes (only loaded when the engine keeps them)
   uint32_t meta;
   uint32_t keyw;     // lanes 0..15: key word l of the node
 };
+enum { AZG_CHILD_UNKNOWN = 0, AZG_CHILD_WON = 1, AZG_CHILD_DRAW = 2, AZG_CHILD_NODE0 = 4 };
 
-template <bool L1 = false>
+template <bool L1 = false, bool CC = false>
 __device__ __forceinline__ void node_load(const azg_dev& e, int g, int node, NodeData& nd) {
   const int l = lane_id();
   const size_t off = azg_node_off(e, g, node);
@@ -123,10 +131,18 @@ __device__ __forceinline__ void node_load(const azg_dev& e, int g, int node, Nod
     nd.p[0] = pa.x; nd.p[1] = pa.y; nd.p[2] = pa.z; nd.p[3] = pa.w; nd.p[4] = pb.x; nd.p[5] = pb.y; nd.p[6] = pb.z; nd.p[7] = pb.w;
     nd.n[0] = na.x; nd.n[1] = na.y; nd.n[2] = na.z; nd.n[3] = na.w; nd.n[4] = nb.x; nd.n[5] = nb.y; nd.n[6] = nb.z; nd.n[7] = nb.w;
     nd.w[0] = wa.x; nd.w[1] = wa.y; nd.w[2] = wa.z; nd.w[3] = wa.w; nd.w[4] = wb.x; nd.w[5] = wb.y; nd.w[6] = wb.z; nd.w[7] = wb.w;
+    if (CC) {
+      const int4* Cc = reinterpret_cast<const int4*>(e.child + base + 8 * l);
+      const int4 ca = ldx<L1>(Cc), cb = ldx<L1>(Cc + 1);
+      nd.c[0] = ca.x; nd.c[1] = ca.y; nd.c[2] = ca.z; nd.c[3] = ca.w; nd.c[4] = cb.x; nd.c[5] = cb.y; nd.c[6] = cb.z; nd.c[7] = cb.w;
+    }
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { nd.p[j] = 0.f; nd.n[j] = 0; nd.w[j] = 0; }
-    if (l == 28) { nd.p[0] = ldx<L1>(e.P + base + 224); nd.n[0] = ldx<L1>(e.Nv + base + 224); nd.w[0] = ldx<L1>(e.W + base + 224); }
+    for (int j = 0; j < 8; ++j) { nd.p[j] = 0.f; nd.n[j] = 0; nd.w[j] = 0; nd.c[j] = 0; }
+    if (l == 28) {
+      nd.p[0] = ldx<L1>(e.P + base + 224); nd.n[0] = ldx<L1>(e.Nv + base + 224); nd.w[0] = ldx<L1>(e.W + base + 224);
+      if (CC) nd.c[0] = ldx<L1>(e.child + base + 224);
+    }
   }
 }
 
@@ -142,7 +158,7 @@ __device__ __forceinline__ bool node_key_matches(const NodeData& nd, const WPos&
 // Transposition lookup that also fetches the node: the candidate's arrays are requested together
 // with its key, so a hit costs two dependent memory round trips (probe window, node) instead of
 // three.  The full key is always compared (the tag only selects candidates).
-template <bool L1 = false>
+template <bool L1 = false, bool CC = false>
 __device__ __forceinline__ int table_find_load(const azg_dev& e, int g, const WPos& p, unsigned long long h, int* ins,
                                                NodeData& nd) {
   const unsigned long long* tab = e.slots + (size_t)g * (size_t)e.hcap;
@@ -157,7 +173,7 @@ __device__ __forceinline__ int table_find_load(const azg_dev& e, int g, const WP
       const int src = __ffs(mm) - 1;
       mm &= mm - 1;
       const int node = (int)__shfl_sync(AZG_FULL, (uint32_t)s, src) - 1;
-      node_load<L1>(e, g, node, nd);
+      node_load<L1, CC>(e, g, node, nd);
       if (node_key_matches(nd, p)) return node;
     }
     const uint32_t em = __ballot_sync(AZG_FULL, s == 0ULL);
@@ -245,7 +261,7 @@ __device__ __forceinline__ int puct_select(const azg_dev& e, int g, const NodeDa
 // ------------------------------------------------------------------------------------------------
 // FILL
 // ------------------------------------------------------------------------------------------------
-template <bool L1>
+template <bool L1, bool CC>
 __device__ __forceinline__ void fill_body(const azg_dev& e) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= e.G) return;
@@ -271,12 +287,13 @@ __device__ __forceinline__ void fill_body(const azg_dev& e) {
     WPos pos;
     NodeData nd;
     int depth, node = -1, v = 0;
+    int par_node = -1, par_a = 0;              // where this position was reached from (child codes)
     bool select_here = false;
     if (resume) {
       pos = wpos_load(&ctl->scratch);
       depth = __ldcg(&ctl->depth);
       node = __ldcg(&ctl->resume_node);
-      node_load<L1>(e, g, node, nd);
+      node_load<L1, CC>(e, g, node, nd);
       select_here = true;                       // fall through to selection at the evaluated leaf
       resume = false;
     } else {
@@ -289,12 +306,13 @@ __device__ __forceinline__ void fill_body(const azg_dev& e) {
       if (!select_here) {
         ++visits;
         const int won = wpos_winner(pos, e.rule);            // new_mcts_alpha.py:106-112
-        if (won != 0) { v = -1; break; }
-        if (!wpos_any_empty(pos)) { v = 0; break; }
+        if (won != 0) { v = -1; if (CC && par_node >= 0 && l == 0) e.child[azg_node_off(e, g, par_node) * AZG_ROW + par_a] = AZG_CHILD_WON; break; }
+        if (!wpos_any_empty(pos)) { v = 0; if (CC && par_node >= 0 && l == 0) e.child[azg_node_off(e, g, par_node) * AZG_ROW + par_a] = AZG_CHILD_DRAW; break; }
         const unsigned long long h = wpos_hash(pos);
         int ins = -1;
-        if (depth == 0 && root_node >= 0) { node = root_node; node_load<L1>(e, g, node, nd); }   // the root key is fixed for the run
-        else node = table_find_load<L1>(e, g, pos, h, &ins, nd);
+        if (depth == 0 && root_node >= 0) { node = root_node; node_load<L1, CC>(e, g, node, nd); }   // the root key is fixed for the run
+        else node = table_find_load<L1, CC>(e, g, pos, h, &ins, nd);
+        if (CC && node >= 0 && par_node >= 0 && l == 0) e.child[azg_node_off(e, g, par_node) * AZG_ROW + par_a] = node + AZG_CHILD_NODE0;
         if (node < 0) {                                        // new_mcts_alpha.py:114-132
           if (ins < 0) { err |= AZG_ERR_HASH; break; }
           if (n_free > 0) node = __ldcg(&freelist[--n_free]);
@@ -303,6 +321,7 @@ __device__ __forceinline__ void fill_body(const azg_dev& e) {
           ++n_live;
           node_write_key(e, g, node, pos);
           table_put(e, g, ins, h, node);
+          if (CC && par_node >= 0 && l == 0) e.child[azg_node_off(e, g, par_node) * AZG_ROW + par_a] = node + AZG_CHILD_NODE0;
           if (depth == 0) root_node = node;
           if (l == 0) ctl->pending[n_pending] = node;
           ++n_pending;
@@ -324,6 +343,23 @@ __device__ __forceinline__ void fill_body(const azg_dev& e) {
       if (l == 0) __stcg(&path[depth], ((uint32_t)node << 8) | (uint32_t)a);
       ++depth;
       wpos_play(pos, e.rule, a);
+      if (CC) {
+        // Child codes (Gomoku): what this (node, action) led to the last time.  A terminal child needs no win test, a known
+        // child no hash and no table probe - its arrays are fetched at once and the stored key is compared as always; a
+        // stale code (slot reused, never the case for a live parent in Gomoku) just falls back to the full path.
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if ((a & 7) == j) mine = nd.c[j];
+        const int code = __shfl_sync(AZG_FULL, mine, a >> 3);
+        par_node = node; par_a = a;
+        if (code == AZG_CHILD_WON) { ++visits; v = -1; break; }
+        if (code == AZG_CHILD_DRAW) { ++visits; v = 0; break; }
+        if (code >= AZG_CHILD_NODE0) {
+          const int child = code - AZG_CHILD_NODE0;
+          node_load<L1, CC>(e, g, child, nd);
+          if ((nd.meta & AZG_META_ALIVE) && node_key_matches(nd, pos)) { ++visits; node = child; select_here = true; }
+        }
+      }
     }
     if (parked || err) break;
     // back-up: the leaf value alternates sign up the path (new_mcts_alpha.py:146-151)
@@ -364,10 +400,10 @@ __device__ __forceinline__ void fill_body(const azg_dev& e) {
 }
 
 extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
-  if (e.rule == AZG_RULE_GOMOKU && e.fill_l1) fill_body<true>(e);
-  else fill_body<false>(e);
+  if (e.rule == AZG_RULE_GOMOKU && e.fill_l1) {
+    if (e.child) fill_body<true, true>(e); else fill_body<true, false>(e);
+  } else fill_body<false, false>(e);
 }
-
 // ------------------------------------------------------------------------------------------------
 // leaf batch assembly: exclusive scan of the per-game queue lengths (single block)
 // ------------------------------------------------------------------------------------------------

@@ -47,7 +47,9 @@ def parse():
     ap.add_argument("--blocks", type=int, default=6)
     ap.add_argument("--channels", type=int, default=128)
     ap.add_argument("--rule", default="gomoku", choices=["gomoku", "pente"])
-    ap.add_argument("--node-capacity", type=int, default=16384)
+    ap.add_argument("--node-capacity", type=int, default=0,
+                    help="nodes per game slab; default 16 384 for Gomoku, 24 576 for Pente (its garbage collector can only use a "
+                         "capture-count bound, so about 16 plies of trees stay alive: soak high-water marks 4 432 and 19 216 nodes)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true",
@@ -540,6 +542,8 @@ def run_ours(args):
 
 def main():
     args = parse()
+    if not args.node_capacity:
+        args.node_capacity = 24576 if args.rule == "pente" else 16384
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -505,7 +505,7 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
                       alpha=dirichlet_alpha, eps=dirichlet_epsilon, noise_plies=dirichlet_n_moves,
                       temp_threshold=float(temp_threshold), max_moves=board_size * board_size,
                       example_capacity=max(my_games, G) * 225, seed=selfplay_base_seed + it, game_base=rank * G,
-                      node_capacity=max(4096, 4 * n_simulations), device=dev, max_games=my_games, packed_examples=True)
+                      node_capacity=max(4096, 8 * n_simulations), device=dev, max_games=my_games, packed_examples=True)    # soak: high-water 5.5 x sims
         # exactly my_games games are started and every one of them is played to the end (train.py:671-694):
         # slots restart only while games remain to be started, then retire
         finished = 0

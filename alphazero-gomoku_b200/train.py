@@ -228,7 +228,7 @@ def evaluate_models(model_new: PyTorchModel, model_best: PyTorchModel, game_name
     boards = np.zeros((G, 225), np.int8)
     lasts = np.asarray(first_stones, np.int32).copy()
     boards[np.arange(G), lasts] = 1
-    engines = [SearchEngine(0, G, cpuct=cpuct, queue_len=32, node_capacity=max(4096, 3 * n_simulations), noise=False, device=dev)
+    engines = [SearchEngine(0, G, cpuct=cpuct, queue_len=32, node_capacity=max(4096, 8 * n_simulations), noise=False, device=dev)
                for _ in range(2)]
     models = [model_new, model_best]
     played = [np.asarray(first_stones, np.int32).copy()]

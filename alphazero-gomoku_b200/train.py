@@ -517,6 +517,10 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
                 winners[int(x)] = winners.get(int(x), 0) + 1
             finished += len(w)
         assert finished == my_games
+        st = sp.engine.stats()
+        if st["dropped_trees"] or st["games_in_error"]:      # a dropped tree loses tree reuse for one move: say so, never silently
+            print(f"[self-play] WARNING rank {rank}: {st['dropped_trees']} trees dropped (node slabs full), {st['games_in_error']} games in "
+                  f"error (bits {st['error_bits']:#x}); raise node_capacity (high-water mark {st['max_nodes']} nodes per game)")
         rows = gather_examples(sp)
         sp.close()
         buffer.add_rows(rows)

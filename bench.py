@@ -513,9 +513,9 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "conv3x3_pair_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None,
                          # DRAM bytes per launch from the committed ncu --set full capture (65 536 positions per launch, the
-                         # same size as the bench's rounds): mean of a layer without (8.58 GB) and with residual (12.89 GB)
-                         "traffic": 10.885e9 if (args.channels == 128 and args.games * 32 == 65536) else None,
-                         "traffic_source": "profiles/conv3x3_r01_final2_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum, mean of a layer without (8.72 GB) and with residual (13.05 GB)",
+                         # same size as the bench's rounds): mean of a layer without (8.56 GB) and with residual (13.01 GB)
+                         "traffic": 10.787e9 if (args.channels == 128 and args.games * 32 == 65536) else None,
+                         "traffic_source": "profiles/conv3x3_r02_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum, mean of a layer without (4.33 + 4.23 GB) and with residual (8.77 + 4.24 GB)",
                          "algorithmic_bytes_per_launch": int((evals / max(rounds, 1)) * 225 * args.channels * 2 * 2.5),
                          "peak_source": peak_src,
                          "launches": int(conv_launches), "avg_launch_ms": trunk_ms / max(conv_launches, 1),

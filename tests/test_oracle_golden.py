@@ -162,3 +162,23 @@ def test_train_step_oracle_against_reference_steps():
         # fp32 summation order of the convolutions differs with the thread count: compare at the tensor's own scale
         assert torch.allclose(opt.m[k], st["exp_avg"], rtol=1e-3, atol=1e-3 * float(st["exp_avg"].abs().max())), k
         assert torch.allclose(opt.v[k], st["exp_avg_sq"], rtol=1e-3, atol=1e-3 * float(st["exp_avg_sq"].abs().max())), k
+
+
+def test_byte_compiled_reference_agrees_with_oracle():
+    """oracle/_ref (the unmodified reference, byte-compiled by oracle/build_ref.py; present wherever the build ran) is what
+    bench.py's CPU arm executes: run it side by side with the oracle on a small search with tree reuse."""
+    from oracle import build_ref
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not built here")
+    assert build_ref.activate()
+    from games.gomoku import Gomoku                      # the reference's own modules, from oracle/_ref
+    from mcts.new_mcts_alpha import MCTS
+    ref = MCTS(Gomoku, 70, fakes.Hashed(), cpuct=1.0, batch_size=32, add_dirichlet_noise=False)
+    orc = Search(rules.GOMOKU, 70, fakes.Hashed(), cpuct=1.0, queue_len=32, noise=False)
+    g, pos = Gomoku(15), rules.Position(rules.GOMOKU)
+    for _ in range(3):
+        pi_ref, pi_orc = ref.run(g, len(g.move_history)), orc.run(pos, pos.plies)
+        assert np.array_equal(pi_ref, pi_orc)
+        a = int(np.argmax(pi_ref))
+        g.do_move(divmod(a, 15))
+        rules.play(pos, a)

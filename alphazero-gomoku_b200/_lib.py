@@ -27,7 +27,7 @@ class azg_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("rule", C.c_int32), ("n_games", C.c_int32), ("queue_len", C.c_int32),
                 ("node_capacity", C.c_int32), ("noise_on", C.c_int32), ("noise_plies", C.c_int32),
                 ("game_base", C.c_int32), ("cpuct", C.c_double), ("alpha", C.c_double), ("eps", C.c_double),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("fast_warps", C.c_int32), ("virtual_loss", C.c_int32)]
 
 
 MAX_LAYERS = 80

@@ -53,6 +53,7 @@ struct azg_ctl {
 // Engine-wide device view handed to kernels by value.
 struct azg_dev {
   int32_t G, rule, queue_len, cap, hcap, noise_on, noise_plies, n_sims, game_base;
+  int32_t fast_warps, virtual_loss;   // fast (non-parity) mode: warps per game walking the tree concurrently, virtual loss per edge
   int32_t fill_l1;              // Gomoku: the FILL kernel reads the slab through L1 and backs up with plain stores (tree.cu ldx)
   float cpuct;
   double eps, alpha, cpuct64;   // cpuct64: the Python float the reference multiplies with at a float64 root

@@ -54,6 +54,8 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
   if (cfg->n_games < 1 || cfg->queue_len < 1 || cfg->queue_len > AZG_MAX_QUEUE || cfg->node_capacity < 64 ||
       cfg->node_capacity >= (1 << 24) || (cfg->rule != 0 && cfg->rule != 1))
     return azg_fail(AZG_E_ARG, "azg_create: n_games>=1, 1<=queue_len<=64, 64<=node_capacity<2^24, rule in {0,1}");
+  if (cfg->fast_warps < 0 || cfg->fast_warps > 16 || cfg->virtual_loss < 0)
+    return azg_fail(AZG_E_ARG, "azg_create: fast_warps must be 0 (exact) .. 16, virtual_loss >= 0");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
     cudaGetLastError();
@@ -69,6 +71,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
   while (h < 2 * cfg->node_capacity) h <<= 1;
   d.hcap = h;
   d.noise_on = cfg->noise_on; d.noise_plies = cfg->noise_plies; d.n_sims = 0; d.game_base = cfg->game_base;
+  d.fast_warps = cfg->fast_warps; d.virtual_loss = cfg->virtual_loss > 0 ? cfg->virtual_loss : 1;
   { const char* v = getenv("AZG_FILL_L1"); d.fill_l1 = v ? atoi(v) : 1; }        // experiment switch, see tree.cu ldx
   d.cpuct = (float)cfg->cpuct; d.cpuct64 = cfg->cpuct; d.eps = cfg->eps; d.alpha = cfg->alpha; d.seed = cfg->seed;
   const size_t G = d.G, C = d.cap;
@@ -173,7 +176,8 @@ extern "C" int azg_search_begin(azg_engine* e, const int32_t* plies, int n_sims)
 extern "C" int azg_search_fill(azg_engine* e, int32_t* n_leaves_host, int32_t* n_active_host, int32_t* n_roots_host) {
   if (!e) return azg_fail(AZG_E_ARG, "null engine");
   AZG_USE_DEVICE(e->cfg.device);
-  azg_fill_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev);
+  if (e->dev.fast_warps > 0) azg_fill_fast_kernel<<<e->dev.G, 32 * e->dev.fast_warps, 0, e->stream>>>(e->dev);      // non-parity option
+  else azg_fill_kernel<<<warp_grid(e->dev.G), 128, 0, e->stream>>>(e->dev);
   azg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->dev);
   int rc = azg_check_launch("azg_search_fill");
   if (rc) return rc;

@@ -3,6 +3,7 @@
 #include "common.cuh"
 extern "C" {
 __global__ void azg_fill_kernel(azg_dev e);
+__global__ void azg_fill_fast_kernel(azg_dev e);
 __global__ void azg_scan_kernel(azg_dev e);
 __global__ void azg_leaf_planes_kernel(azg_dev e, float* out);
 __global__ void azg_commit_kernel(azg_dev e, const float* probs, const double* noise);

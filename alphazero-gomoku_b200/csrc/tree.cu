@@ -405,6 +405,162 @@ extern "C" __global__ void __launch_bounds__(128) azg_fill_kernel(azg_dev e) {
   } else fill_body<false, false>(e);
 }
 // ------------------------------------------------------------------------------------------------
+// FILL, fast mode (NOT the reference's algorithm: an explicit non-parity option, azg_config.fast_warps > 0)
+// ------------------------------------------------------------------------------------------------
+// The reference walks its simulations one after the other, which is what the kernel above reproduces exactly and what
+// bounds the latency of a single game (one warp, ~3 us per tree level).  Here `fast_warps` warps of one block walk ONE
+// game's tree at the same time, kept apart by a virtual loss: on the way down every selected (node, action) gets
+// N += vl and W -= vl with L2 atomics, the back-up takes it out again and adds the real visit.  Lookups and selection
+// are lock-free; creating a node (slab allocation, key, placeholder priors, table entry, leaf queue) happens under a
+// per-game spin lock and the node is published in the table last.  Kept from the reference: the deferred-evaluation
+// queue (placeholder nodes with a uniform-legal prior, evaluated `queue_len` at a time, N and W reset on evaluation),
+// terminal values only, masked priors, root noise.  Dropped: the strict order of simulations and the quirk that the
+// simulation which fills the queue continues below its leaf.  Visit counts therefore differ from the reference's; the
+// tests check invariants, tactics and agreement of the chosen move instead (tests/test_fast_mode_gpu.py).
+#define AZG_FAST_MAX_WARPS 16
+#define AZG_FAST_MAX_DEPTH 160
+
+extern "C" __global__ void __launch_bounds__(32 * AZG_FAST_MAX_WARPS) azg_fill_fast_kernel(azg_dev e) {
+  __shared__ int s_state, s_sims_left, s_n_pending, s_lock, s_n_nodes, s_n_free, s_n_live, s_err, s_stop, s_root_node;
+  __shared__ unsigned int s_visits, s_sims;
+  __shared__ uint32_t s_path[AZG_FAST_MAX_WARPS][AZG_FAST_MAX_DEPTH];
+  const int g = blockIdx.x;
+  const int l = lane_id(), wib = threadIdx.x >> 5;
+  azg_ctl* ctl = e.ctl + g;
+  if (threadIdx.x == 0) {
+    s_state = __ldcg(&ctl->state);
+    s_sims_left = __ldcg(&ctl->sims_left); s_n_pending = __ldcg(&ctl->n_pending); s_n_nodes = __ldcg(&ctl->n_nodes);
+    s_n_free = __ldcg(&ctl->n_free); s_n_live = __ldcg(&ctl->n_live); s_root_node = __ldcg(&ctl->root_node);
+    s_lock = 0; s_err = 0; s_stop = 0; s_visits = 0; s_sims = 0;
+  }
+  __syncthreads();
+  if (s_state != AZG_ST_RUN) return;
+  const int vl = e.virtual_loss > 0 ? e.virtual_loss : 1;
+  int32_t* freelist = e.freelist + (size_t)g * e.cap;
+  const WPos root = wpos_load(&ctl->root);
+  uint32_t* path = s_path[wib];
+
+  while (true) {
+    int go = 0;
+    if (l == 0) {
+      if (!*(volatile int*)&s_stop && !*(volatile int*)&s_err) {
+        if (atomicSub(&s_sims_left, 1) > 0) go = 1; else atomicAdd(&s_sims_left, 1);
+      }
+    }
+    go = __shfl_sync(AZG_FULL, go, 0);
+    if (!go) break;
+    WPos pos = root;
+    NodeData nd;
+    int depth = 0, v = 0, visits = 0;
+    bool abort = false;
+    for (;;) {
+      ++visits;
+      const int won = wpos_winner(pos, e.rule);
+      if (won != 0) { v = -1; break; }
+      if (!wpos_any_empty(pos)) { v = 0; break; }
+      const unsigned long long h = wpos_hash(pos);
+      int ins = -1, node;
+      const int rn = *(volatile int*)&s_root_node;
+      if (depth == 0 && rn >= 0) { node = rn; node_load(e, g, node, nd); }
+      else node = table_find_load(e, g, pos, h, &ins, nd);
+      if (node < 0) {
+        // ---- create the leaf under the game's lock
+        int got = 0;
+        if (l == 0) {
+          for (int spin = 0; spin < (1 << 24); ++spin)
+            if (atomicCAS(&s_lock, 0, 1) == 0) { got = 1; break; }
+        }
+        got = __shfl_sync(AZG_FULL, got, 0);
+        if (!got) { if (l == 0) atomicOr(&s_err, AZG_ERR_HASH); abort = true; break; }
+        __threadfence_block();
+        node = table_find_load(e, g, pos, h, &ins, nd);         // somebody else may have made it meanwhile
+        bool done = false;
+        if (node < 0) {
+          int np = 0, nn = -1, fail = 0;                          // lane 0 allocates under the lock, the warp follows
+          if (l == 0) {
+            np = *(volatile int*)&s_n_pending;
+            if (ins < 0) fail = AZG_ERR_HASH;
+            else if (np >= e.queue_len) fail = -1;                // the queue filled up: this simulation is given back
+            else if (*(volatile int*)&s_n_free > 0) { const int k = *(volatile int*)&s_n_free - 1; nn = __ldcg(&freelist[k]); *(volatile int*)&s_n_free = k; }
+            else if (*(volatile int*)&s_n_nodes < e.cap) { nn = *(volatile int*)&s_n_nodes; *(volatile int*)&s_n_nodes = nn + 1; }
+            else fail = AZG_ERR_NODES;
+          }
+          np = __shfl_sync(AZG_FULL, np, 0); nn = __shfl_sync(AZG_FULL, nn, 0); fail = __shfl_sync(AZG_FULL, fail, 0);
+          if (fail) { if (fail > 0 && l == 0) atomicOr(&s_err, fail); abort = true; done = true; }
+          else {
+            node_write_key(e, g, nn, pos);
+            node_fill(e, g, nn, wpos_legal_byte(pos), __fdiv_rn(1.0f, (float)wpos_count_empty(pos)));
+            __threadfence_block();
+            __syncwarp();
+            table_put(e, g, ins, h, nn);                          // published last: lock-free readers find a complete node
+            if (l == 0) {
+              ctl->pending[np] = nn;
+              *(volatile int*)&s_n_pending = np + 1;
+              *(volatile int*)&s_n_live = *(volatile int*)&s_n_live + 1;
+              if (depth == 0) *(volatile int*)&s_root_node = nn;
+              if (np + 1 >= e.queue_len) *(volatile int*)&s_stop = 1;
+            }
+            v = 0;
+            done = true;
+          }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (l == 0) atomicExch(&s_lock, 0);
+        __syncwarp();
+        if (done) break;
+      }
+      const int a = puct_select(e, g, nd, wpos_legal_byte(pos));
+      if (depth >= AZG_FAST_MAX_DEPTH) { if (l == 0) atomicOr(&s_err, AZG_ERR_DEPTH); abort = true; break; }
+      if (l == 0) {
+        path[depth] = ((uint32_t)node << 8) | (uint32_t)a;
+        const size_t idx = azg_node_off(e, g, node) * AZG_ROW + a;
+        atomicAdd(&e.Nv[idx], vl);                              // virtual loss: this edge looks visited and lost to the others
+        atomicAdd(&e.W[idx], -vl);
+      }
+      ++depth;
+      wpos_play(pos, e.rule, a);
+    }
+    __syncwarp();
+    // back-up: take the virtual loss out, add the real visit (value alternates sign up the path)
+    for (int d = l; d < depth; d += 32) {
+      const uint32_t pe = path[d];
+      const size_t idx = azg_node_off(e, g, (int)(pe >> 8)) * AZG_ROW + (pe & 255u);
+      if (abort) { atomicAdd(&e.Nv[idx], -vl); atomicAdd(&e.W[idx], vl); }
+      else {
+        atomicAdd(&e.Nv[idx], 1 - vl);
+        atomicAdd(&e.W[idx], vl + (v != 0 ? (((depth - d) & 1) ? -v : v) : 0));
+      }
+    }
+    __syncwarp();
+    if (l == 0) {
+      atomicAdd(&s_visits, (unsigned)visits);
+      if (abort) atomicAdd(&s_sims_left, 1); else atomicAdd(&s_sims, 1u);
+    }
+    if (abort) break;                                           // queue full or error: this warp is done for this launch
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int state = AZG_ST_RUN;
+    const int left = s_sims_left < 0 ? 0 : s_sims_left;
+    if (s_err) state = AZG_ST_ERROR;
+    else if (s_n_pending >= e.queue_len) state = AZG_ST_NEED_EVAL;
+    else if (left <= 0) state = s_n_pending > 0 ? AZG_ST_NEED_FINAL : AZG_ST_DONE;
+    ctl->state = state;
+    ctl->err = __ldcg(&ctl->err) | s_err;
+    ctl->sims_left = left;
+    ctl->root_node = s_root_node;
+    ctl->n_pending = s_n_pending;
+    ctl->n_nodes = s_n_nodes;
+    ctl->n_free = s_n_free;
+    ctl->n_live = s_n_live;
+    ctl->susp = 0;
+    ctl->visits += s_visits;
+    ctl->sims += s_sims;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // leaf batch assembly: exclusive scan of the per-game queue lengths (single block)
 // ------------------------------------------------------------------------------------------------
 extern "C" __global__ void __launch_bounds__(1024) azg_scan_kernel(azg_dev e) {

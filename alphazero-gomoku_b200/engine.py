@@ -101,14 +101,17 @@ class Rules:
 class SearchEngine:
     def __init__(self, rule: int, n_games: int, cpuct: float = 1.0, queue_len: int = 32, node_capacity: int = 8192,
                  noise: bool = False, alpha: float = 0.03, eps: float = 0.03, noise_plies: int = 10, seed: int = 12345,
-                 device="cuda:0", game_base: int = 0):
+                 device="cuda:0", game_base: int = 0, fast_warps: int = 0, virtual_loss: int = 1):
+        """``fast_warps`` = 0: the reference's algorithm, exact visit counts.  1..16: the NON-PARITY fast mode - that many
+        warps walk each game's tree concurrently under a virtual loss (see tree.cu); for latency, not for parity."""
         if not torch.cuda.is_available():
             raise _lib.AzgError("no CUDA device: azgomoku_b200 has no CPU fallback")
         self.device = torch.device(device)
         self.rule, self.G, self.queue_len = rule, n_games, queue_len
         cfg = azg_config(device=self.device.index or 0, rule=rule, n_games=n_games, queue_len=queue_len,
                          node_capacity=node_capacity, noise_on=int(noise), noise_plies=noise_plies, game_base=int(game_base),
-                         cpuct=float(cpuct), alpha=float(alpha), eps=float(eps), seed=seed)
+                         cpuct=float(cpuct), alpha=float(alpha), eps=float(eps), seed=seed, fast_warps=int(fast_warps),
+                         virtual_loss=int(virtual_loss))
         h = C.c_void_p()
         check(lib.azg_create(C.byref(cfg), C.byref(h)))
         self._h = h

@@ -35,7 +35,10 @@ def game_fields(game_state):
 class MCTS:
     def __init__(self, game_class, n_simulations, nn_model, cpuct=1.0, batch_size=32, dirichlet_alpha=0.03,
                  epsilon=0.03, apply_dirichlet_n_first_moves=10, add_dirichlet_noise=True,
-                 node_capacity=65536, device="cuda:0", gc=True):
+                 node_capacity=65536, device="cuda:0", gc=True, fast_warps=0, virtual_loss=1):
+        """The reference's constructor arguments first (same names, order, defaults); the rest are engine extras.
+        ``fast_warps`` > 0 selects the non-parity fast mode (concurrent simulations under a virtual loss): several
+        times lower latency per move, visit counts no longer those of the reference."""
         self.game_class = game_class
         self.n_simulations = n_simulations
         self.nn_model = nn_model
@@ -50,7 +53,8 @@ class MCTS:
         self.rule = rule_of(game_class)
         self.engine = SearchEngine(self.rule, 1, cpuct=cpuct, queue_len=batch_size, node_capacity=node_capacity,
                                    noise=add_dirichlet_noise, alpha=dirichlet_alpha, eps=epsilon,
-                                   noise_plies=apply_dirichlet_n_first_moves, device=device)
+                                   noise_plies=apply_dirichlet_n_first_moves, device=device, fast_warps=fast_warps,
+                                   virtual_loss=virtual_loss)
         self.device = self.engine.device
         self.last_visits = None         # int32[225] root visit counts of the last run (N[root] in the reference)
         self.n_evals = 0

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AZG_ABI_VERSION 2
+#define AZG_ABI_VERSION 3
 #define AZG_BOARD 15
 #define AZG_ACTIONS 225
 
@@ -99,6 +99,10 @@ typedef struct azg_config {
   double alpha;            /* dirichlet_alpha */
   double eps;              /* epsilon */
   uint64_t seed;           /* Philox key for on-device noise / sampling */
+  int32_t fast_warps;      /* 0 (default): the reference's strictly sequential simulations, exact visit counts.
+                              1..16: NON-PARITY fast mode - that many warps walk one game's tree concurrently, kept apart
+                              by a virtual loss (north-star subsystem 1); visit counts differ from the reference's */
+  int32_t virtual_loss;    /* fast mode: N += vl, W -= vl on every edge of a simulation in flight (default 1) */
 } azg_config;
 
 int azg_create(const azg_config* cfg, azg_engine** out);

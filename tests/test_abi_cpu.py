@@ -19,7 +19,7 @@ def test_library_exports_header():
     assert len(syms) >= 20
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
-    assert lib.azg_abi_version() == 2
+    assert lib.azg_abi_version() == 3
 
 
 def test_binding_covers_header():

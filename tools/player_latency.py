@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--sims", type=int, default=5000)
     ap.add_argument("--moves", type=int, default=6)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--fast-warps", type=int, default=0, help="non-parity fast mode: warps per game walking the tree concurrently")
     args = ap.parse_args()
     import alphazero_gomoku_b200 as m
     from alphazero_gomoku_b200.games import Gomoku
@@ -30,7 +31,7 @@ def main():
     for blocks, ch in ((3, 64), (6, 128)):
         torch.manual_seed(0)
         net = PyTorchModel(n_res_blocks=blocks, channels=ch, device="cuda:0")
-        mcts = m.MCTS(Gomoku, args.sims, net, cpuct=1.0, add_dirichlet_noise=False)
+        mcts = m.MCTS(Gomoku, args.sims, net, cpuct=1.0, add_dirichlet_noise=False, fast_warps=args.fast_warps)
         game = Gomoku(15)
         times, evals = [], []
         for ply in range(args.moves + 1):

@@ -12,7 +12,7 @@
 #define AZG_N 15
 #define AZG_A 225
 #define AZG_ROW 228              // row stride (elements) of per-node child arrays: 912 B, 16-B aligned
-#define AZG_MAX_QUEUE 64         // upper bound for the reference's batch_size
+#define AZG_MAX_QUEUE 256        // upper bound for the reference's batch_size
 #define AZG_MAX_DEPTH 512        // path stack entries per game
 #define AZG_P64_SLOTS 8          // float64 prior rows per game (noised roots)
 #define AZG_FULL 0xffffffffu

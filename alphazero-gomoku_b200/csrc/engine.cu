@@ -53,7 +53,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
   if (!cfg || !out) return azg_fail(AZG_E_ARG, "azg_create: null argument");
   if (cfg->n_games < 1 || cfg->queue_len < 1 || cfg->queue_len > AZG_MAX_QUEUE || cfg->node_capacity < 64 ||
       cfg->node_capacity >= (1 << 24) || (cfg->rule != 0 && cfg->rule != 1))
-    return azg_fail(AZG_E_ARG, "azg_create: n_games>=1, 1<=queue_len<=64, 64<=node_capacity<2^24, rule in {0,1}");
+    return azg_fail(AZG_E_ARG, "azg_create: n_games>=1, 1<=queue_len<=256, 64<=node_capacity<2^24, rule in {0,1}");
   if (cfg->fast_warps < 0 || cfg->fast_warps > 16 || cfg->virtual_loss < 0)
     return azg_fail(AZG_E_ARG, "azg_create: fast_warps must be 0 (exact) .. 16, virtual_loss >= 0");
   int ndev = 0;

@@ -30,7 +30,9 @@ def _side_to_move(turn_number: int) -> int:
 
 class Player:
     def __init__(self, rules="gomoku", board_size=15, n_simulations=5000, c_puct=1.0, model_path=DEFAULT_SNAPSHOT,
-                 nn_model=PyTorchModel):
+                 nn_model=PyTorchModel, fast_warps=0, batch_size=32):
+        """Reference arguments first (player_alpha.py:26-27).  ``fast_warps`` > 0 / a longer ``batch_size`` select the engine's
+        non-parity fast search (lower latency per move, visit counts no longer the reference's); the defaults are exact."""
         self.rules, self.board_size = rules.lower(), board_size
         self.n_simulations, self.c_puct, self.model_path = n_simulations, c_puct, model_path
         self.net = nn_model(board_size=board_size)
@@ -44,7 +46,7 @@ class Player:
             raise ValueError(f"Unsupported rules: {self.rules}. Only 'gomoku' is supported.")
         self.game_class = Gomoku
         self.mcts = MCTS(game_class=Gomoku, n_simulations=n_simulations, nn_model=self.net, cpuct=c_puct,
-                         add_dirichlet_noise=False)
+                         add_dirichlet_noise=False, fast_warps=fast_warps, batch_size=batch_size)
 
     def play(self, board, turn_number, last_opponent_move):
         """Search from the given position and answer with the most visited move."""

@@ -89,7 +89,7 @@ typedef struct azg_config {
   int32_t device;          /* CUDA ordinal */
   int32_t rule;            /* AZG_RULE_* (game_class) */
   int32_t n_games;         /* G */
-  int32_t queue_len;       /* reference batch_size, 1..64 (default 32) */
+  int32_t queue_len;       /* reference batch_size, 1..256 (default 32) */
   int32_t node_capacity;   /* nodes per game slab */
   int32_t noise_on;        /* add_dirichlet_noise */
   int32_t noise_plies;     /* apply_dirichlet_n_first_moves */

@@ -251,3 +251,41 @@ def test_random_configurations_vs_oracle(seed):
             break
     assert eng.stats()["games_in_error"] == 0
     eng.close()
+
+
+@pytest.mark.parametrize("queue,rule", [(100, 0), (128, 1), (256, 0)])
+def test_long_queue_vs_oracle(queue, rule):
+    """The reference's batch_size is free (new_mcts_alpha.py:66); queues longer than the default 32 - up to the engine's
+    limit of 256 - keep the reference's visit counts, over two moves with tree reuse."""
+    import alphazero_gomoku_b200 as m
+    rng = np.random.default_rng(77 + queue)
+    G, n_sims = 4, 700
+    eng = m.SearchEngine(rule, G, queue_len=queue, node_capacity=16384, noise=False)
+    starts = []
+    for g in range(G):
+        p = orules.Position(rule)
+        for _ in range(int(rng.integers(0, 16))):
+            e = np.flatnonzero(p.cells == 0)
+            orules.play(p, int(e[int(rng.integers(0, len(e)))]))
+        assert not orules.game_over(p)
+        starts.append(p)
+    eng.set_roots(eng.rules.pack(np.stack([p.cells for p in starts]), [p.player for p in starts], [p.last for p in starts],
+                                 [p.caps for p in starts], [p.plies for p in starts]))
+    model = fakes.Spiky()
+    ev = lambda planes: torch.from_numpy(model.predict(planes.cpu().numpy())[0]).cuda()
+    searches = [Search(rule, n_sims, fakes.Spiky(), queue_len=queue, noise=False) for _ in range(G)]
+    for move in range(2):
+        pi, visits = eng.run(n_sims, ev, plies=torch.tensor([p.plies for p in starts], dtype=torch.int32))
+        pi, visits = pi.cpu().numpy(), visits.cpu().numpy()
+        acts = np.zeros(G, np.int32)
+        for g in range(G):
+            want = searches[g].run(starts[g], starts[g].plies)
+            assert np.array_equal(visits[g], searches[g].Nv[starts[g].key()].astype(np.int32)), (queue, g, move)
+            assert np.array_equal(pi[g], want), (queue, g, move)
+            acts[g] = int(np.argmax(want))
+            orules.play(starts[g], int(acts[g]))
+        eng.advance(torch.from_numpy(acts).cuda(), gc=True)
+        if any(orules.game_over(p) for p in starts):
+            break
+    assert eng.stats()["games_in_error"] == 0
+    eng.close()

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--moves", type=int, default=6)
     ap.add_argument("--out", default=None)
     ap.add_argument("--fast-warps", type=int, default=0, help="non-parity fast mode: warps per game walking the tree concurrently")
+    ap.add_argument("--batch-size", type=int, default=32, help="the reference's MCTS batch_size (deferred-evaluation queue length)")
     args = ap.parse_args()
     import alphazero_gomoku_b200 as m
     from alphazero_gomoku_b200.games import Gomoku
@@ -31,7 +32,8 @@ def main():
     for blocks, ch in ((3, 64), (6, 128)):
         torch.manual_seed(0)
         net = PyTorchModel(n_res_blocks=blocks, channels=ch, device="cuda:0")
-        mcts = m.MCTS(Gomoku, args.sims, net, cpuct=1.0, add_dirichlet_noise=False, fast_warps=args.fast_warps)
+        mcts = m.MCTS(Gomoku, args.sims, net, cpuct=1.0, add_dirichlet_noise=False, fast_warps=args.fast_warps,
+                      batch_size=args.batch_size)
         game = Gomoku(15)
         times, evals = [], []
         for ply in range(args.moves + 1):
@@ -49,16 +51,17 @@ def main():
             if game.is_game_over():
                 break
         ms = 1e3 * float(np.median(times))
-        line = {"path": "MCTS.run single game", "net": f"{blocks}x{ch}", "sims_per_move": args.sims,
+        line = {"path": "MCTS.run single game", "mode": "exact" if args.fast_warps == 0 else f"fast, {args.fast_warps} warps",
+                "batch_size": args.batch_size, "net": f"{blocks}x{ch}", "sims_per_move": args.sims,
                 "ms_per_move_median": round(ms, 2), "ms_per_move_all": [round(1e3 * t, 2) for t in times],
                 "sims_per_s": round(args.sims / (ms * 1e-3), 1), "evals_per_move": int(np.median(evals)),
-                "rounds_per_move": int(np.ceil(np.median(evals) / 32)),
-                "ms_per_round": round(ms / max(1.0, np.ceil(np.median(evals) / 32)), 4)}
+                "rounds_per_move": int(np.ceil(np.median(evals) / args.batch_size)),
+                "ms_per_round": round(ms / max(1.0, np.ceil(np.median(evals) / args.batch_size)), 4)}
         print(json.dumps(line), flush=True)
         lines.append(line)
         mcts.engine.close()
     if args.out:
-        with open(args.out, "w") as f:
+        with open(args.out, "a") as f:
             for line in lines:
                 f.write(json.dumps(line) + "\n")
 

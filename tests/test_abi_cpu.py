@@ -55,7 +55,7 @@ def test_argument_errors_are_codes_with_text():
     assert lib.azg_create(None, ctypes.byref(h)) < 0
     assert b"null" in lib.azg_last_error()
     cfg = _lib.azg_config()
-    cfg.n_games, cfg.queue_len, cfg.node_capacity, cfg.rule = 4, 65, 1024, 0          # queue_len > AZG_MAX_QUEUE
+    cfg.n_games, cfg.queue_len, cfg.node_capacity, cfg.rule = 4, 257, 1024, 0         # queue_len > AZG_MAX_QUEUE
     assert lib.azg_create(ctypes.byref(cfg), ctypes.byref(h)) < 0 and b"queue_len" in lib.azg_last_error()
     cfg.queue_len, cfg.rule = 32, 7
     assert lib.azg_create(ctypes.byref(cfg), ctypes.byref(h)) < 0

@@ -86,6 +86,9 @@ def main():
     del_me = exchange()                                                # NCCL connection set-up and the allocator's first
     del del_me                                                         # cudaMalloc of the row buffer are not the exchange
     rows, t_gather = timed(exchange, dev)
+    del rows
+    gathered, t_allgather = timed(lambda: tr.gather_rows(packed_local), dev)     # the two halves on their own
+    rows, t_expand = timed(lambda: expand_examples(gathered, True), dev)
     buf = tr.DeviceReplayBuffer(max(rows.shape[0], 1), dev)
     buf.add_rows(rows)
     gen = torch.Generator(device=dev)
@@ -127,6 +130,7 @@ def main():
             "net": f"{args.blocks}x{args.channels}", "games_per_gpu": args.games, "sims_per_move": args.sims, "plies": args.plies,
             "selfplay_ms": round(t_sp, 1), "selfplay_sims_per_s": round(sims / (t_sp * 1e-3), 1),
             "examples_gathered": int(rows.shape[0]), "synthetic_plies_per_gpu": synthetic, "gather_ms": round(t_gather, 2),
+            "gather_allgather_ms": round(t_allgather, 2), "gather_expand_ms": round(t_expand, 2),
             "exchange": "all-gather of packed plies (976 B each) + local 8-symmetry expansion",
             "exchanged_bytes": int(rows.shape[0] // 8 * 976), "expanded_bytes": int(rows.numel() * 4),
             "train_steps": args.train_steps, "global_batch": B, "train_ms_per_step": round(t_train / args.train_steps, 3),

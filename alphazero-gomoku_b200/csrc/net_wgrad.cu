@@ -24,6 +24,8 @@
 // Algorithmic FLOPs per launch = 2 * 9 * C * C * 225 * boards; algorithmic bytes = the two tensors
 // once (2 * boards * 225 * C * 2 B); each CTA row re-reads them, i.e. 3x from L2.
 #include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
 #include "net.h"
 #include "ptx.cuh"
 
@@ -37,7 +39,7 @@ struct WCfg {
   static constexpr int B_SLICE = ((B_ROWS * 128) + 1023) & ~1023;    // 9216
   static constexpr int A_BYTES = KC * A_SLICE, B_BYTES = KC * B_SLICE;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = C == 128 ? 6 : 8;                     // 204 KB / 136 KB in flight: the tiles come from L2 or HBM with ~1-2 us of latency
   static constexpr int TMEM_COLS = 3 * C <= 256 ? 256 : 512;
   static constexpr int TX = KC * (64 * 128 + B_ROWS * 128);          // bytes TMA delivers per stage
   static constexpr int SMEM = 1024 + STAGES * STAGE + 256;
@@ -324,7 +326,21 @@ int launch_wgrad_cluster(const CUtensorMap* tm, const WgradArgs& a, int n_sm, cu
   using K = WClusterCfg<C>;
   cudaError_t e = cudaFuncSetAttribute(wgrad3x3_cluster_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
-  int S = n_sm / 3;
+  // Clusters of three do not tile every GPC: ask how many can be resident at once and launch exactly one wave
+  // (n_sm / 3 clusters would leave the remainder for a second wave that doubles the kernel's duration).
+  static int resident = 0;
+  if (resident == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(3 * (n_sm / 3)); cfg.blockDim = dim3(kWThreads); cfg.dynamicSmemBytes = K::SMEM;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 3; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, wgrad3x3_cluster_kernel<C>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = n_sm / 3; }
+    resident = n;
+    if (getenv("AZG_WGRAD_VERBOSE")) fprintf(stderr, "wgrad3x3_cluster_kernel<%d>: %d clusters of 3 resident on %d SMs\n", C, n, n_sm);
+  }
+  int S = resident < n_sm / 3 ? resident : n_sm / 3;
   if (S > a.n_boards) S = a.n_boards;
   if (S < 1) S = 1;
   wgrad3x3_cluster_kernel<C><<<3 * S, kWThreads, K::SMEM, stream>>>(tm[0], tm[1], tm[2], tm[3], a);

@@ -29,12 +29,14 @@ struct BnApplyArgs {
   const __nv_bfloat16* residual;      // block input added before the ReLU (second layer of a block), or null
   __nv_bfloat16* out;                 // a = relu(bn(z) (+ residual)), pad rows zero
   int n_boards;
+  uint8_t* mask;                      // [n_boards * 256][C / 8]: bit i of a byte = [a > 0] of channel 8 * group + i (what the backward pass reads
+                                      // instead of a: 1/16 of the bytes), or null
 };
 int azg_bn_apply_launch(int C, const BnApplyArgs& a, int n_sm, cudaStream_t s);
 
 struct BnBwdArgs {
   const __nv_bfloat16* g;             // dL/da (gradient of the layer output, after the ReLU)
-  const __nv_bfloat16* a;             // layer output (ReLU mask)
+  const uint8_t* mask;                // ReLU mask of the layer output, one bit per element (bn_apply wrote it)
   const __nv_bfloat16* z;             // conv output (for x_hat)
   const float* stats;                 // [2][C] batch mean, rstd
   const float* gamma;

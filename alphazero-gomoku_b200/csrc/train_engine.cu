@@ -61,6 +61,7 @@ struct azg_train {
   size_t rows = 0;
   ParamLayout lay{};
   std::vector<__nv_bfloat16*> a, z;              // [L+1] activations after / before BatchNorm+ReLU
+  std::vector<uint8_t*> relu_mask;               // [L+1] one bit per element of a: [a > 0], read by the BatchNorm backward passes instead of a
   __nv_bfloat16 *g[2] = {nullptr, nullptr}, *dzb[2] = {nullptr, nullptr}, *gskip = nullptr;     // dzb: dL/dz, double buffered (see the backward loop)
   cudaStream_t side = nullptr;                   // the weight-gradient kernels run here, beside the next layer's BatchNorm passes
   std::vector<cudaEvent_t> ev_fork, ev_join;
@@ -113,6 +114,7 @@ extern "C" int azg_train_destroy(azg_train* t) {
   cudaSetDevice(t->device);
   for (auto p : t->a) cudaFree(p);
   for (auto p : t->z) cudaFree(p);
+  for (auto p : t->relu_mask) cudaFree(p);
   cudaFree(t->g[0]); cudaFree(t->g[1]); cudaFree(t->dzb[0]); cudaFree(t->dzb[1]); cudaFree(t->gskip);
   for (cudaEvent_t e : t->ev_fork) cudaEventDestroy(e);
   for (cudaEvent_t e : t->ev_join) cudaEventDestroy(e);
@@ -156,8 +158,12 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   t->rows = AZG_NET_FRONT + (size_t)B * 256 + AZG_NET_BACK;
   const size_t act = t->rows * C;
   int rc = AZG_OK;
-  t->a.assign(L + 1, nullptr); t->z.assign(L + 1, nullptr);
-  for (int i = 0; i <= L && !rc; ++i) { rc = talloc(t, &t->a[i], act); if (!rc) rc = talloc(t, &t->z[i], act); }
+  t->a.assign(L + 1, nullptr); t->z.assign(L + 1, nullptr); t->relu_mask.assign(L + 1, nullptr);
+  for (int i = 0; i <= L && !rc; ++i) {
+    rc = talloc(t, &t->a[i], act);
+    if (!rc) rc = talloc(t, &t->z[i], act);
+    if (!rc) rc = talloc(t, &t->relu_mask[i], (size_t)B * 256 * (C / 8));
+  }
   if (!rc) rc = talloc(t, &t->g[0], act);
   if (!rc) rc = talloc(t, &t->g[1], act);
   if (!rc) rc = talloc(t, &t->dzb[0], act);
@@ -344,7 +350,7 @@ extern "C" int azg_train_forward_backward(azg_train* t, const float* planes, con
     BnStatsArgs st{t->z[idx], count, fused ? t->conv_stat : t->partial, t->counters + 0, t->stats + (size_t)idx * 2 * C, rmean, rvar, mom, eps};
     int r = fused ? azg_bn_finalize_launch(C, st, azg_conv3x3_stat_slots(t->max_batch, t->n_sm, C), s) : azg_bn_stats_launch(C, st, s);
     if (r) return r;
-    BnApplyArgs ap{t->z[idx], t->stats + (size_t)idx * 2 * C, gamma, beta, residual, t->a[idx], count};
+    BnApplyArgs ap{t->z[idx], t->stats + (size_t)idx * 2 * C, gamma, beta, residual, t->a[idx], count, t->relu_mask[idx]};
     return azg_bn_apply_launch(C, ap, t->n_sm, s);
   };
   // ---- forward
@@ -366,7 +372,7 @@ extern "C" int azg_train_forward_backward(azg_train* t, const float* planes, con
   int cur = 0;
   auto bn_bwd = [&](int idx, const float* gamma, float* dgamma, float* dbeta, bool want_skip, __nv_bfloat16* dz) -> int {
     BnBwdArgs b{};
-    b.g = t->g[cur]; b.a = t->a[idx]; b.z = t->z[idx]; b.stats = t->stats + (size_t)idx * 2 * C; b.gamma = gamma; b.n_boards = count;
+    b.g = t->g[cur]; b.mask = t->relu_mask[idx]; b.z = t->z[idx]; b.stats = t->stats + (size_t)idx * 2 * C; b.gamma = gamma; b.n_boards = count;
     b.partial = t->partial; b.counter = t->counters + 1; b.sums = t->sums; b.dgamma = dgamma; b.dbeta = dbeta; b.dz = dz;
     b.gskip = want_skip ? t->gskip : nullptr;
     int r = azg_bn_bwd_reduce_launch(C, b, s);

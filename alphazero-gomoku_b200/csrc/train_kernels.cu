@@ -67,7 +67,7 @@ constexpr int kRedThreads = 512;
 
 template <int C, bool BWD>
 __device__ __forceinline__ void channel_reduce(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ g,
-                                               const __nv_bfloat16* __restrict__ a, const float* __restrict__ stats,
+                                               const uint8_t* __restrict__ mask, const float* __restrict__ stats,
                                                int n_boards, float* __restrict__ partial) {
   constexpr int CG = C / 8, RL = kRedThreads / CG;
   __shared__ float red[RL][2][C];
@@ -84,7 +84,8 @@ __device__ __forceinline__ void channel_reduce(const __nv_bfloat16* __restrict__
   const long long step = (long long)gridDim.x * RL;
   constexpr int U = 4;                                     // rows in flight per thread: the passes are latency bound otherwise
   for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < n_rows; r0 += U * step) {
-    uint4 zq[U], gq[U], aq[U];
+    uint4 zq[U], gq[U];
+    unsigned mq[U];
     bool live[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -93,7 +94,7 @@ __device__ __forceinline__ void channel_reduce(const __nv_bfloat16* __restrict__
       if (live[u]) {
         const size_t off = ((size_t)AZG_NET_FRONT + (size_t)r) * C + (size_t)cg * 8;
         zq[u] = ptx::ldg128(z + off);
-        if (BWD) { gq[u] = ptx::ldg128(g + off); aq[u] = ptx::ldg128(a + off); }
+        if (BWD) { gq[u] = ptx::ldg128(g + off); mq[u] = mask[(size_t)r * CG + cg]; }
       }
     }
 #pragma unroll
@@ -105,12 +106,11 @@ __device__ __forceinline__ void channel_reduce(const __nv_bfloat16* __restrict__
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s0[i] += zf[i]; s1[i] = fmaf(zf[i], zf[i], s1[i]); }
       } else {
-        float gf[8], af[8];
+        float gf[8];
         unpack8(gq[u], gf);
-        unpack8(aq[u], af);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float dy = af[i] > 0.f ? gf[i] : 0.f;
+          const float dy = ((mq[u] >> i) & 1u) ? gf[i] : 0.f;
           s0[i] += dy;
           s1[i] = fmaf(dy, (zf[i] - mean[i]) * rstd[i], s1[i]);
         }
@@ -241,6 +241,7 @@ bn_apply_kernel(BnApplyArgs p) {
     const long long r = idx / CG;
     const size_t off = ((size_t)AZG_NET_FRONT + (size_t)r) * C + (size_t)cg * 8;
     float y[8];
+    unsigned bits = 0;
     if (is_pad_row((int)(r & 255))) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) y[i] = 0.f;
@@ -258,7 +259,15 @@ bn_apply_kernel(BnApplyArgs p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
     }
-    ptx::stg128(p.out + off, pack8(y));
+    const uint4 packed = pack8(y);
+    ptx::stg128(p.out + off, packed);
+    if (p.mask) {                         // the mask is taken from the ROUNDED output: exactly [a > 0]
+      float yr[8];
+      unpack8(packed, yr);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bits |= (yr[i] > 0.f ? 1u : 0u) << i;
+      p.mask[idx] = (uint8_t)bits;
+    }
   }
 }
 
@@ -266,7 +275,7 @@ bn_apply_kernel(BnApplyArgs p) {
 template <int C>
 __global__ void __launch_bounds__(kRedThreads)
 bn_bwd_reduce_kernel(BnBwdArgs p) {
-  channel_reduce<C, true>(p.z, p.g, p.a, p.stats, p.n_boards, p.partial);
+  channel_reduce<C, true>(p.z, p.g, p.mask, p.stats, p.n_boards, p.partial);
   if (!last_block_arrives(p.counter)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NW = kRedThreads / 32, PER = 2 * C / NW;
@@ -311,13 +320,13 @@ bn_bwd_apply_kernel(BnBwdArgs p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) dz[i] = dy[i] = 0.f;
     } else {
-      float zf[8], gf[8], af[8];
+      float zf[8], gf[8];
+      const unsigned m = p.mask[idx];
       unpack8(ptx::ldg128(p.z + off), zf);
       unpack8(ptx::ldg128(p.g + off), gf);
-      unpack8(ptx::ldg128(p.a + off), af);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        dy[i] = af[i] > 0.f ? gf[i] : 0.f;
+        dy[i] = ((m >> i) & 1u) ? gf[i] : 0.f;
         const float xh = (zf[i] - mean[i]) * rstd[i];
         dz[i] = k0[i] * (dy[i] - m1[i] - xh * m2[i]);
       }

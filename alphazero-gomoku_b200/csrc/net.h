@@ -28,6 +28,9 @@ struct ConvArgs {
   int prof_detail;                // also clock the phases of one epilogue warp (slightly intrusive)
   float* stat_partial;            // training forward: [2 * C][AZG_CONV_STAT_SLOTS] per-channel sum / sum of squares of the
                                   // outputs, one slot per epilogue warp (azg_conv3x3_stat_slots of them are written); null = off
+  const __nv_bfloat16* bwd_z;     // training, input gradient: with stat_partial, z (activation layout) and the ReLU bit mask
+  const uint8_t* bwd_mask;        // ([boards * 256][C / 8]) of the layer whose dL/da this launch produces; the two statistics are
+                                  // then sum(dy) and sum(dy * z), dy = out * [a > 0]; null = forward statistics
 };
 #define AZG_CONV_STAT_SLOTS 1184   // 74 clusters x 2 CTAs x 4 quadrants x 2 epilogue groups
 int azg_conv3x3_stat_slots(int max_boards, int n_sm, int C);

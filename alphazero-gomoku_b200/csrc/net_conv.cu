@@ -102,7 +102,7 @@ __device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
   }
 }
 
-template <int C, bool HEADS, int MODE, bool STATS = false>
+template <int C, bool HEADS, int MODE, int STATS = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(conv_threads<C>(), 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
                     const __grid_constant__ CUtensorMap tm_out, ConvArgs p,
@@ -300,10 +300,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     int it = 0;
     bool ok = true;
     long long t_tfull = 0, t_wr = 0, t_rt = 0, t_ld = 0, t_cs = 0, t_st = 0;
-    // STATS (training forward): per-channel sum and sum of squares of the bf16-rounded outputs, accumulated by this
-    // warp over all its boards (lane = channel within a 32-channel chunk) and left in stat_partial at the end
+    // STATS 1 (training forward): per-channel sum and sum of squares of the bf16-rounded outputs, accumulated by this
+    // warp over all its boards (lane = channel within a 32-channel chunk) and left in stat_partial at the end.
+    // STATS 2 (input gradient): the output is g = dL/da of the layer below; with that layer's ReLU bit mask and its
+    // pre-BatchNorm z the same two slots collect sum(dy) and sum(dy * z), dy = g * [a > 0] - the reductions of its
+    // BatchNorm backward pass, which then needs no pass of its own over g and z.
     float st_sum[STATS ? (HEADS ? C : C / 2) / 32 : 1], st_sq[STATS ? (HEADS ? C : C / 2) / 32 : 1];
-    if constexpr (STATS) {
+    if constexpr (STATS != 0) {
 #pragma unroll
       for (int c = 0; c < (HEADS ? C : C / 2) / 32; ++c) st_sum[c] = st_sq[c] = 0.f;
     }
@@ -347,6 +350,17 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
           const __nv_bfloat16* rrow = p.residual + grow * C;
 #pragma unroll
           for (int j = 0; j < NCH / 16; ++j) ptx::ldg256(rrow + ch0 + 16 * j, &res[8 * j]);
+        }
+      }
+      uint32_t bz[STATS == 2 ? NCH / 2 : 1], bm[STATS == 2 ? NCHUNK : 1];
+      if constexpr (STATS == 2) {
+        if (working) {
+          const __nv_bfloat16* zrow = p.bwd_z + grow * C + ch0;
+#pragma unroll
+          for (int j = 0; j < NCH / 16; ++j) ptx::ldg256(zrow + 16 * j, &bz[8 * j]);
+          const uint8_t* mrow = p.bwd_mask + ((size_t)b * 256 + (size_t)rank * 128 + (size_t)row) * (C / 8) + ch0 / 8;
+#pragma unroll
+          for (int c = 0; c < NCHUNK; ++c) bm[c] = *reinterpret_cast<const uint32_t*>(mrow + 4 * c);
         }
       }
       const long long t0 = clock64();
@@ -408,12 +422,19 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
           using IH = std::integral_constant<int, HEADS ? 0 : C / 2>;
           if (!HEADS && half) { if (has_res) math(IH{}, std::true_type{}); else math(IH{}, std::false_type{}); }
           else { if (has_res) math(I0{}, std::true_type{}); else math(I0{}, std::false_type{}); }
-          if constexpr (STATS) {
+          if constexpr (STATS != 0) {
             float zs[32], zq[32];
 #pragma unroll
             for (int h = 0; h < 16; ++h) {
               zs[2 * h] = __uint_as_float(outv[h] << 16); zs[2 * h + 1] = __uint_as_float(outv[h] & 0xffff0000u);
-              zq[2 * h] = zs[2 * h] * zs[2 * h]; zq[2 * h + 1] = zs[2 * h + 1] * zs[2 * h + 1];
+              if constexpr (STATS == 2) {
+                const uint32_t zw = bz[(STATS == 2 ? 16 * c : 0) + h];
+                if (!((bm[STATS == 2 ? c : 0] >> (2 * h)) & 1u)) zs[2 * h] = 0.f;
+                if (!((bm[STATS == 2 ? c : 0] >> (2 * h + 1)) & 1u)) zs[2 * h + 1] = 0.f;
+                zq[2 * h] = zs[2 * h] * __uint_as_float(zw << 16); zq[2 * h + 1] = zs[2 * h + 1] * __uint_as_float(zw & 0xffff0000u);
+              } else {
+                zq[2 * h] = zs[2 * h] * zs[2 * h]; zq[2 * h + 1] = zs[2 * h + 1] * zs[2 * h + 1];
+              }
             }
             warp_transpose_sum(zs, lane);
             warp_transpose_sum(zq, lane);
@@ -479,7 +500,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
     }
-    if constexpr (STATS) {
+    if constexpr (STATS != 0) {
       // slot = one epilogue warp's share of the rows: (cluster, CTA, quadrant[, group]); channel = ch0 + 32 c + lane
       const int slot = ((cid * 2 + (int)rank) * 4 + quad) * EG + grp;
       if (working) {
@@ -508,7 +529,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   if (warp == 1) ptx::tmem_dealloc<2>(tmem_base, K::TMEM_COLS);
 }
 
-template <int C, bool HEADS, int MODE, bool STATS = false>
+template <int C, bool HEADS, int MODE, int STATS = 0>
 int launch_conv(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtensorMap& tm_out, const ConvArgs& args, int n_sm,
                 cudaStream_t stream) {
   using K = Cfg<C, MODE>;
@@ -565,10 +586,16 @@ int azg_conv3x3_stat_slots(int max_boards, int n_sm, int C) {
 
 int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const CUtensorMap& tm_out,
                        const ConvArgs& args, int n_sm, cudaStream_t stream) {
-  if (args.stat_partial) {          // training forward: per-channel output statistics in the epilogue
+  if (args.stat_partial) {          // training: per-channel statistics in the epilogue (forward: of z; input gradient: BatchNorm backward sums)
     if (args.head_host) return azg_fail(AZG_E_ARG, "conv3x3: statistics and fused heads are separate variants");
-    if (C == 128 && mode == 1) return launch_conv<128, false, 1, true>(tm_act, tm_w, tm_out, args, n_sm, stream);
-    if (C == 64 && mode == 3) return launch_conv<64, false, 3, true>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (args.bwd_z) {
+      if (!args.bwd_mask) return azg_fail(AZG_E_ARG, "conv3x3: bwd_z needs bwd_mask");
+      if (C == 128 && mode == 1) return launch_conv<128, false, 1, 2>(tm_act, tm_w, tm_out, args, n_sm, stream);
+      if (C == 64 && mode == 3) return launch_conv<64, false, 3, 2>(tm_act, tm_w, tm_out, args, n_sm, stream);
+      return azg_fail(AZG_E_ARG, "conv3x3: the statistics epilogue is built for (128 channels, mode 1) and (64 channels, mode 3)");
+    }
+    if (C == 128 && mode == 1) return launch_conv<128, false, 1, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    if (C == 64 && mode == 3) return launch_conv<64, false, 3, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
     return azg_fail(AZG_E_ARG, "conv3x3: the statistics epilogue is built for (128 channels, mode 1) and (64 channels, mode 3)");
   }
   if (C == 128) {

@@ -50,6 +50,8 @@ struct BnBwdArgs {
   __nv_bfloat16* gskip;               // apply: dy = g * [a > 0] (gradient of the skip connection), or null
 };
 int azg_bn_bwd_reduce_launch(int C, const BnBwdArgs& a, cudaStream_t s);
+// the same sums from the statistics the input-gradient convolution left in conv_partial (ConvArgs.bwd_z): no pass over g and z
+int azg_bn_bwd_finalize_launch(int C, const BnBwdArgs& a, const float* conv_partial, int n_slots, cudaStream_t s);
 int azg_bn_bwd_apply_launch(int C, const BnBwdArgs& a, int n_sm, cudaStream_t s);
 
 // ---- stem (conv 3 -> C on the input planes) ---------------------------------------------------------------------------

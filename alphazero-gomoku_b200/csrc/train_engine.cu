@@ -73,7 +73,7 @@ struct azg_train {
   __nv_bfloat16 *wf = nullptr, *wb = nullptr;
   float *wp_t = nullptr, *wv1_t = nullptr;
   float *stats = nullptr, *sums = nullptr, *partial = nullptr, *stem_partial = nullptr, *conv_stat = nullptr;
-  int fuse_stats = 1;
+  int fuse_stats = 1, fuse_bwd = 1;
   float *zh = nullptr, *hstats = nullptr, *hidden = nullptr, *h1 = nullptr, *value = nullptr, *dlogits = nullptr, *dvpre = nullptr,
         *dhid = nullptr, *hsums = nullptr, *norm_partial = nullptr, *scal = nullptr;
   unsigned* counters = nullptr;
@@ -147,6 +147,7 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   cudaDeviceGetAttribute(&t->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
   t->conv_mode = t->C == 64 ? 3 : 1;
   { const char* v = getenv("AZG_WGRAD_DESC"); t->wgrad_variant = v ? atoi(v) : 0; }
+  { const char* v = getenv("AZG_TRAIN_FUSE_BWD"); t->fuse_bwd = v ? atoi(v) : 1; }             // 0: BatchNorm backward sums in their own pass over g and z
   { const char* v = getenv("AZG_TRAIN_FUSE_STATS"); t->fuse_stats = v ? atoi(v) : 1; }     // 0: separate statistics pass over z (experiment switch)
   { const char* v = getenv("AZG_TRAIN_OVERLAP"); t->overlap = v ? atoi(v) : 1; }           // 0: weight gradients on the main stream
   // 1: clusters of three CTAs sharing their operands by TMA multicast (2.4x less L2 -> SMEM traffic).  Measured slower:
@@ -370,12 +371,14 @@ extern "C" int azg_train_forward_backward(azg_train* t, const float* planes, con
   // ---- backward
   if ((rc = azg_head_train_bwd_launch(h, t->n_sm, s))) return rc;
   int cur = 0;
-  auto bn_bwd = [&](int idx, const float* gamma, float* dgamma, float* dbeta, bool want_skip, __nv_bfloat16* dz) -> int {
+  // fused_sums: the input-gradient convolution that produced g already summed dy and dy * z per channel in its epilogue
+  auto bn_bwd = [&](int idx, const float* gamma, float* dgamma, float* dbeta, bool want_skip, __nv_bfloat16* dz, bool fused_sums) -> int {
     BnBwdArgs b{};
     b.g = t->g[cur]; b.mask = t->relu_mask[idx]; b.z = t->z[idx]; b.stats = t->stats + (size_t)idx * 2 * C; b.gamma = gamma; b.n_boards = count;
     b.partial = t->partial; b.counter = t->counters + 1; b.sums = t->sums; b.dgamma = dgamma; b.dbeta = dbeta; b.dz = dz;
     b.gskip = want_skip ? t->gskip : nullptr;
-    int r = azg_bn_bwd_reduce_launch(C, b, s);
+    int r = fused_sums ? azg_bn_bwd_finalize_launch(C, b, t->conv_stat, azg_conv3x3_stat_slots(t->max_batch, t->n_sm, C), s)
+                       : azg_bn_bwd_reduce_launch(C, b, s);
     if (r) return r;
     return azg_bn_bwd_apply_launch(C, b, t->n_sm, s);
   };
@@ -384,22 +387,25 @@ extern "C" int azg_train_forward_backward(azg_train* t, const float* planes, con
   // optimiser).  The weight gradient runs on a side stream next to the HBM-bound BatchNorm passes of the layer below;
   // dz is double buffered so that those passes do not overwrite what it is still reading.
   const bool ov = t->overlap != 0;
+  const bool fuse_bwd = t->fuse_stats != 0 && t->fuse_bwd != 0;
   cudaStream_t ws = ov ? t->side : s;
   for (int i = L - 1; i >= 0; --i) {
     const int k = i & 1;
     if (ov && i + 2 <= L - 1) AZG_CUDA(cudaStreamWaitEvent(s, t->ev_join[i + 2], 0));      // the kernel that last read dzb[k] is done
-    if ((rc = bn_bwd(i + 1, t->params + l.res_bn_w[i], t->grads + l.res_bn_w[i], t->grads + l.res_bn_b[i], (i & 1) != 0, t->dzb[k]))) return rc;
+    if ((rc = bn_bwd(i + 1, t->params + l.res_bn_w[i], t->grads + l.res_bn_w[i], t->grads + l.res_bn_b[i], (i & 1) != 0, t->dzb[k],
+                     fuse_bwd && i < L - 1))) return rc;
     if (ov) { AZG_CUDA(cudaEventRecord(t->ev_fork[i], s)); AZG_CUDA(cudaStreamWaitEvent(ws, t->ev_fork[i], 0)); }
     if ((rc = launch_wgrad(t, k, i, count, t->grads + l.res_conv_w[i], ws))) return rc;
     if (ov) AZG_CUDA(cudaEventRecord(t->ev_join[i], ws));
     ConvArgs ca = conv_args(t, i, (i & 1) ? nullptr : t->gskip, t->g[cur ^ 1]);
+    if (fuse_bwd) { ca.stat_partial = t->conv_stat; ca.bwd_z = t->z[i]; ca.bwd_mask = t->relu_mask[i]; }   // g is dL/da of BatchNorm idx i
     if ((rc = azg_conv3x3_launch(C, t->conv_mode, t->tm_dz_in[k], t->tm_wb, t->tm_g_st[cur ^ 1], ca, t->n_sm, s))) return rc;
     cur ^= 1;
   }
   const int ks = L >= 2 ? 1 : (L & 1);                     // buffer of the stem's dz: the one layer 1 used (layer 0 may still be read)
   if (ov && L >= 2) AZG_CUDA(cudaStreamWaitEvent(s, t->ev_join[1], 0));
   if (ov && L == 1) AZG_CUDA(cudaStreamWaitEvent(s, t->ev_join[0], 0));
-  if ((rc = bn_bwd(0, t->params + l.bn_w, t->grads + l.bn_w, t->grads + l.bn_b, false, t->dzb[L >= 1 ? ks : 0]))) return rc;
+  if ((rc = bn_bwd(0, t->params + l.bn_w, t->grads + l.bn_w, t->grads + l.bn_b, false, t->dzb[L >= 1 ? ks : 0], fuse_bwd && L >= 1))) return rc;
   st.dz = t->dzb[L >= 1 ? ks : 0]; st.partial = t->stem_partial; st.dw = t->grads + l.conv_w;
   if ((rc = azg_stem_train_wgrad_launch(C, st, s))) return rc;
   if (ov && L >= 1) AZG_CUDA(cudaStreamWaitEvent(s, t->ev_join[0], 0));                   // join: every weight gradient has landed

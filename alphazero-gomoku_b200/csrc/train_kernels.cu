@@ -218,6 +218,28 @@ bn_finalize_kernel(BnStatsArgs p, int C, int n_slots) {
   p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)unbiased;
 }
 
+// BatchNorm backward sums from what the input-gradient convolution's epilogue collected (net_conv.cu STATS 2):
+// partial rows [0, C) hold sum(dy), rows [C, 2C) sum(dy * z) per epilogue warp; warp = channel.
+//   sum(dy * x_hat) = rstd * (sum(dy * z) - mean * sum(dy))
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(BnBwdArgs p, const float* __restrict__ conv_partial, int C, int n_slots) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int j = lane; j < n_slots; j += 32) {
+    s += (double)conv_partial[(size_t)c * AZG_CONV_STAT_SLOTS + j];
+    q += (double)conv_partial[(size_t)(C + c) * AZG_CONV_STAT_SLOTS + j];
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); q += __shfl_xor_sync(0xffffffffu, q, d); }
+  if (lane != 0) return;
+  const double xh = (double)p.stats[C + c] * (q - (double)p.stats[c] * s);
+  p.sums[c] = (float)s;
+  p.sums[C + c] = (float)xh;
+  p.dbeta[c] = (float)s;
+  p.dgamma[c] = (float)xh;
+}
+
 // a = relu(gamma * (z - mean) * rstd + beta (+ residual)), pad rows zero
 template <int C>
 __global__ void __launch_bounds__(kEwThreads)
@@ -1004,6 +1026,11 @@ int azg_bn_apply_launch(int C, const BnApplyArgs& a, int n_sm, cudaStream_t s) {
     bn_apply_kernel<CC><<<ew_grid(a.n_boards, CC, n_sm), kEwThreads, 0, s>>>(a);
     return azg_check_launch("bn_apply_kernel");
   });
+}
+
+int azg_bn_bwd_finalize_launch(int C, const BnBwdArgs& a, const float* conv_partial, int n_slots, cudaStream_t s) {
+  bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(a, conv_partial, C, n_slots);
+  return azg_check_launch("bn_bwd_finalize_kernel");
 }
 
 int azg_bn_bwd_reduce_launch(int C, const BnBwdArgs& a, cudaStream_t s) {

@@ -284,3 +284,29 @@ def test_ragged_batch_sizes_against_oracle(ch, n):
             assert cos(got[k].cpu(), grads[k]) >= (0.9 if m < 8 else TOL["grad_cos"]), (m, k, cos(got[k].cpu(), grads[k]))
         # the running statistics were touched by the forward pass: restore them for the second size
         model.net.load_state_dict(sd)
+
+
+@pytest.mark.parametrize("blocks,ch", [(2, 64), (3, 128)])
+def test_fused_and_standalone_batchnorm_backward_sums_agree(blocks, ch, monkeypatch):
+    """The BatchNorm backward reductions (sum dy, sum dy * x_hat) collected in the input-gradient convolution's epilogue
+    (net_conv.cu STATS 2, the default) against the pass of their own (AZG_TRAIN_FUSE_BWD=0): same inputs, same weights.
+    They sum the same bf16 values in a different order, and dz is rounded to bf16 after them, so the gradients agree
+    to rounding, not bit for bit."""
+    z = load_golden("train_steps.npz")
+    X, P, Z = unpack_planes(z["batch/planes_bits"]), z["batch/pi"], z["batch/z"]
+    grads = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("AZG_TRAIN_FUSE_BWD", fuse)
+        model = make_model(blocks, ch, seed=2)
+        tr = model._ensure_trainer(len(X))
+        losses = tr.forward_backward(torch.from_numpy(X), torch.from_numpy(P), torch.from_numpy(Z)).cpu().numpy()
+        tr.check()
+        grads.append(({k: v.detach().cpu().clone() for k, v in tr.gradients().items()}, losses))
+    (ga, la), (gb, lb) = grads
+    assert np.array_equal(la, lb)                                     # the forward pass is the same code
+    worst = 0.0
+    for k in ga:
+        c, r = cos(ga[k], gb[k]), rel(ga[k], gb[k])
+        worst = max(worst, r)
+        assert c >= 0.9999 and r <= 5e-3, (k, c, r)                   # measured worst: 3.3e-4 (2x64), 1.5e-3 (3x128)
+    print(f"{blocks}x{ch}: fused vs standalone backward sums, worst relative gradient difference {worst:.2e}")

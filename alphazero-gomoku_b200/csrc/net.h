@@ -92,6 +92,7 @@ struct WgradArgs {
   float* dw;                      // [9][C][C]
   int* error;                     // watchdog flag
   int desc_variant;               // experiment switch for the MN-major descriptor fields (0 = documented layout)
+  int ct;                         // channels of the TENSORS when wider than the kernel's tile (256: four 128 x 128 quadrants); 0 = tile width
 };
 int azg_wgrad3x3_a_rows();
 int azg_wgrad3x3_launch(int C, const CUtensorMap& tm_dz, const CUtensorMap& tm_a, const WgradArgs& a, int n_sm, cudaStream_t stream);

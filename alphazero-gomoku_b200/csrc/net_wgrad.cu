@@ -84,6 +84,9 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
   int my_boards = 0;
   for (int b = s; b < n_boards; b += S) ++my_boards;
   const int n_chunks = my_boards * 4;
+  // Tensors wider than the tile (256 channels, C = 128 tiles): blockIdx.y picks the (output-channel, input-channel) quadrant
+  const int ldw = p.ct > 0 ? p.ct : C, nq = ldw / C;
+  const int co0 = ((int)blockIdx.y / nq) * C, ci0 = ((int)blockIdx.y % nq) * C;
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_dz); ptx::prefetch_tmap(&tm_a); }
   if (warp == 1) {
@@ -112,8 +115,8 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
           uint8_t* sB = sA + K::A_BYTES;
           ptx::mbar_arrive_expect_tx(&full[stage], (uint32_t)K::TX);
           for (int kc = 0; kc < K::KC; ++kc) {
-            ptx::tma_load_2d(sA + kc * K::A_SLICE, &tm_dz, &full[stage], kc * 64, r0);
-            ptx::tma_load_2d(sB + kc * K::B_SLICE, &tm_a, &full[stage], kc * 64, r0 + 16 * (tg - 1) - 1);
+            ptx::tma_load_2d(sA + kc * K::A_SLICE, &tm_dz, &full[stage], co0 + kc * 64, r0);
+            ptx::tma_load_2d(sB + kc * K::B_SLICE, &tm_a, &full[stage], ci0 + kc * 64, r0 + 16 * (tg - 1) - 1);
           }
           if (++stage == K::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -155,7 +158,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
       if (quad * 32 < C) {          // with 64 channels the upper two quadrants hold nothing
 #pragma unroll 1
         for (int t = 0; t < 3; ++t) {
-          float* dst = p.dw + ((size_t)(tg * 3 + t) * C + co) * C;
+          float* dst = p.dw + ((size_t)(tg * 3 + t) * ldw + co0 + co) * ldw + ci0;
 #pragma unroll 1
           for (int c = 0; c < C / 32; ++c) {
             uint32_t v[32];
@@ -180,10 +183,11 @@ int launch_wgrad(const CUtensorMap& tm_dz, const CUtensorMap& tm_a, const WgradA
   using K = WCfg<C>;
   cudaError_t e = cudaFuncSetAttribute(wgrad3x3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) return azg_fail(AZG_E_CUDA, cudaGetErrorString(e));
-  int S = n_sm / 3;
+  const int nq = a.ct > 0 ? a.ct / C : 1;           // 256-channel tensors: four quadrants of 128 x 128 channels (grid.y)
+  int S = n_sm / (3 * nq * nq);
   if (S > a.n_boards) S = a.n_boards;
   if (S < 1) S = 1;
-  wgrad3x3_kernel<C><<<3 * S, kWThreads, K::SMEM, stream>>>(tm_dz, tm_a, a);
+  wgrad3x3_kernel<C><<<dim3(3 * S, nq * nq), kWThreads, K::SMEM, stream>>>(tm_dz, tm_a, a);
   return azg_check_launch("wgrad3x3_kernel");
 }
 
@@ -354,7 +358,8 @@ int azg_wgrad3x3_a_rows() { return WCfg<128>::B_ROWS; }
 int azg_wgrad3x3_launch(int C, const CUtensorMap& tm_dz, const CUtensorMap& tm_a, const WgradArgs& a, int n_sm, cudaStream_t stream) {
   if (C == 64) return launch_wgrad<64>(tm_dz, tm_a, a, n_sm, stream);
   if (C == 128) return launch_wgrad<128>(tm_dz, tm_a, a, n_sm, stream);
-  return azg_fail(AZG_E_ARG, "wgrad3x3: channels must be 64 or 128");
+  if (C == 256) { WgradArgs b = a; b.ct = 256; return launch_wgrad<128>(tm_dz, tm_a, b, n_sm, stream); }
+  return azg_fail(AZG_E_ARG, "wgrad3x3: channels must be 64, 128 or 256");
 }
 
 // Cluster variant: tm = {dz box 24 rows, dz box 16 rows, a box 32 rows, a box 34 rows} (all 64 channels wide, SWIZZLE_128B).

@@ -130,7 +130,7 @@ extern "C" int azg_train_destroy(azg_train* t) {
 
 extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   if (!cfg || !out) return azg_fail(AZG_E_ARG, "azg_train_create: null argument");
-  if (cfg->channels != 64 && cfg->channels != 128) return azg_fail(AZG_E_ARG, "azg_train_create: channels must be 64 or 128");
+  if (cfg->channels != 64 && cfg->channels != 128 && cfg->channels != 256) return azg_fail(AZG_E_ARG, "azg_train_create: channels must be 64, 128 or 256");
   if (cfg->n_blocks < 0 || cfg->n_blocks > AZG_NET_MAX_BLOCKS || cfg->max_batch < 1) return azg_fail(AZG_E_ARG, "azg_train_create: bad argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
@@ -154,6 +154,7 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   // 71 vs 41 us per launch alone, the same step time when overlapped - the kernel is not bound by L2 traffic but by the
   // 128 x 128 x 16 cta_group::1 UMMA reading 8 KB of shared memory per 64 cycles, and the clusters add lock-step latency.
   { const char* v = getenv("AZG_WGRAD_CLUSTER"); t->wgrad_cluster = v ? atoi(v) : 0; }
+  if (t->C == 256) { t->fuse_stats = 0; t->fuse_bwd = 0; t->wgrad_cluster = 0; }          // the 256-channel convolution (streamed weights) has no statistics epilogue
   const int C = t->C, L = t->L, B = t->max_batch;
   layout_params(t->lay, C, L);
   t->rows = AZG_NET_FRONT + (size_t)B * 256 + AZG_NET_BACK;
@@ -315,7 +316,7 @@ static HeadTrainArgs head_args(azg_train* t, int count, const float* pi, const f
 
 // weight gradient of trunk layer `layer` from dzb[k] and a[layer] into dw ([9][C][C], accumulated)
 static int launch_wgrad(azg_train* t, int k, int layer, int count, float* dw, cudaStream_t s) {
-  WgradArgs wa{count, dw, t->error_dev, t->wgrad_variant};
+  WgradArgs wa{count, dw, t->error_dev, t->wgrad_variant, 0};
   if (t->wgrad_cluster) {
     const CUtensorMap tm[4] = {t->tm_dz_c24[k], t->tm_dz_c16[k], t->tm_a_c32[layer], t->tm_a_c34[layer]};
     return azg_wgrad3x3_cluster_launch(t->C, tm, wa, t->n_sm, s);

@@ -977,7 +977,8 @@ template <typename F>
 int dispatch_c(int C, F&& f) {
   if (C == 64) return f(std::integral_constant<int, 64>{});
   if (C == 128) return f(std::integral_constant<int, 128>{});
-  return azg_fail(AZG_E_ARG, "training kernels: channels must be 64 or 128");
+  if (C == 256) return f(std::integral_constant<int, 256>{});
+  return azg_fail(AZG_E_ARG, "training kernels: channels must be 64, 128 or 256");
 }
 
 int ew_grid(int n_boards, int C, int n_sm) {

@@ -12,8 +12,8 @@ raises if the CUDA library or a B200 is missing (no eager PyTorch fallback).
 ``train_batch`` (network.py:199-235) runs in the CUDA library too: tensor-core
 forward / input-gradient / weight-gradient convolutions, training-mode BatchNorm, the reference's
 KLDiv + MSE loss, clip 3.0 and Adam on fp32 master weights (``trainer.TrainEngine``).  The torch
-autograd formulation of the same step is kept as ``train_batch_autograd`` (256-channel networks,
-which the training kernels do not cover, and the cross-check in the tests).
+autograd formulation of the same step is kept as ``train_batch_autograd`` (other channel counts than
+64 / 128 / 256, and the cross-check in the tests).
 """
 from __future__ import annotations
 
@@ -184,8 +184,8 @@ class PyTorchModel:
         return self.policy_loss_fn(F.log_softmax(logits, dim=1), target_pis), self.value_loss_fn(values, target_vs)
 
     def _ensure_trainer(self, batch: int):
-        """The CUDA training engine for batches of up to ``batch`` positions (None for 256 channels)."""
-        if self.net.channels not in (64, 128):
+        """The CUDA training engine for batches of up to ``batch`` positions (None for channel counts other than 64 / 128 / 256)."""
+        if self.net.channels not in (64, 128, 256):
             return None
         if self._trainer is None or self._trainer.max_batch < batch:
             from .trainer import TrainEngine
@@ -201,7 +201,7 @@ class PyTorchModel:
         x, pi, z = self._to_device(states), self._to_device(target_pis), self._to_device(target_vs)
         tr = self._ensure_trainer(x.shape[0])
         if tr is None:
-            raise _lib.AzgError("the CUDA training step covers 64 and 128 channels; use train_batch_autograd")
+            raise _lib.AzgError("the CUDA training step covers 64, 128 and 256 channels; use train_batch_autograd")
         self.net.train()
         if self.train_graphs:
             losses = tr.step_graph(x, pi, z, world, reduce_grads)
@@ -216,7 +216,7 @@ class PyTorchModel:
     def train_batch(self, states, target_pis, target_vs, epochs: int = 1) -> dict:
         """``epochs`` Adam steps on one batch: loss = KL + MSE, gradient norm clipped at 3.0 (network.py:199-235).
         Accepts numpy arrays (as the reference) or device tensors (no host copy)."""
-        if self.net.channels not in (64, 128):
+        if self.net.channels not in (64, 128, 256):
             return self.train_batch_autograd(states, target_pis, target_vs, epochs)
         x, pi, z = self._to_device(states), self._to_device(target_pis), self._to_device(target_vs)
         sums = torch.zeros(2, dtype=torch.float32, device=x.device)

@@ -412,7 +412,7 @@ def train_batch_dp(model: PyTorchModel, states, pis, zs) -> dict:
     world, _ = _world()
     if world == 1:
         return model.train_batch(states, pis, zs, epochs=1)
-    if getattr(model, "_ensure_trainer", None) is not None and model.net.channels in (64, 128):
+    if getattr(model, "_ensure_trainer", None) is not None and model.net.channels in (64, 128, 256):
         # CUDA training step: one all-reduce over the flat gradient vector between backward and clip + Adam
         losses = model.train_batch_async(states, pis, zs, world=world, reduce_grads=lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM))
         p, v = losses.tolist()

@@ -56,7 +56,7 @@ def make_model(blocks, ch, seed=0):
     return PyTorchModel(n_res_blocks=blocks, channels=ch, device="cuda:0")
 
 
-@pytest.mark.parametrize("ch,n", [(64, 5), (128, 3), (128, 67), (64, 150)])
+@pytest.mark.parametrize("ch,n", [(64, 5), (128, 3), (128, 67), (64, 150), (256, 5), (256, 40)])
 def test_tensor_core_gradient_kernels_exact(ch, n):
     """The weight-gradient kernel (tcgen05, MN-major operands, net_wgrad.cu) and the input-gradient convolution
     (net_conv.cu on transposed, tap-flipped weights) ALONE, on random bf16-representable tensors: against
@@ -82,7 +82,7 @@ def test_tensor_core_gradient_kernels_exact(ch, n):
         assert float((da.cpu() - want_da).abs().max()) <= 2 ** -8 * float(want_da.abs().max()) + 1e-6
 
 
-@pytest.mark.parametrize("blocks,ch", [(0, 64), (2, 64), (2, 128), (3, 128)])
+@pytest.mark.parametrize("blocks,ch", [(0, 64), (2, 64), (2, 128), (3, 128), (0, 256), (2, 256)])
 def test_forward_and_gradients_match_oracle(blocks, ch):
     """One forward/backward pass, no update: every layer's activation, both losses and the gradient of every
     parameter tensor against the fp32 oracle (autograd over the functional restatement of the reference's step)."""
@@ -258,7 +258,7 @@ def test_world_average_and_checkpoint_roundtrip(tmp_path):
     assert np.isfinite(out["total_loss"])
 
 
-@pytest.mark.parametrize("ch,n", [(64, 2), (128, 33), (64, 129), (128, 300)])
+@pytest.mark.parametrize("ch,n", [(64, 2), (128, 33), (64, 129), (128, 300), (256, 37)])
 def test_ragged_batch_sizes_against_oracle(ch, n):
     """Batch sizes that are no multiple of anything the kernels tile by (2 = the smallest BatchNorm allows, 33, 129, 300:
     partly filled clusters, CTAs without boards in the weight-gradient grid, head blocks with one board): losses against

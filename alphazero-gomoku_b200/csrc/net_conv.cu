@@ -592,11 +592,13 @@ int azg_conv3x3_launch(int C, int mode, const CUtensorMap& tm_act, const CUtenso
       if (!args.bwd_mask) return azg_fail(AZG_E_ARG, "conv3x3: bwd_z needs bwd_mask");
       if (C == 128 && mode == 1) return launch_conv<128, false, 1, 2>(tm_act, tm_w, tm_out, args, n_sm, stream);
       if (C == 64 && mode == 3) return launch_conv<64, false, 3, 2>(tm_act, tm_w, tm_out, args, n_sm, stream);
-      return azg_fail(AZG_E_ARG, "conv3x3: the statistics epilogue is built for (128 channels, mode 1) and (64 channels, mode 3)");
+      if (C == 256 && mode == 1) return launch_conv<256, false, 1, 2>(tm_act, tm_w, tm_out, args, n_sm, stream);
+      return azg_fail(AZG_E_ARG, "conv3x3: the statistics epilogue is built for (128 / 256 channels, mode 1) and (64 channels, mode 3)");
     }
     if (C == 128 && mode == 1) return launch_conv<128, false, 1, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
     if (C == 64 && mode == 3) return launch_conv<64, false, 3, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
-    return azg_fail(AZG_E_ARG, "conv3x3: the statistics epilogue is built for (128 channels, mode 1) and (64 channels, mode 3)");
+    if (C == 256 && mode == 1) return launch_conv<256, false, 1, 1>(tm_act, tm_w, tm_out, args, n_sm, stream);
+    return azg_fail(AZG_E_ARG, "conv3x3: the statistics epilogue is built for (128 / 256 channels, mode 1) and (64 channels, mode 3)");
   }
   if (C == 128) {
     if (mode == 0) return launch_conv_heads<128, 0>(tm_act, tm_w, tm_out, args, n_sm, stream);

@@ -154,7 +154,7 @@ extern "C" int azg_train_create(const azg_train_config* cfg, azg_train** out) {
   // 71 vs 41 us per launch alone, the same step time when overlapped - the kernel is not bound by L2 traffic but by the
   // 128 x 128 x 16 cta_group::1 UMMA reading 8 KB of shared memory per 64 cycles, and the clusters add lock-step latency.
   { const char* v = getenv("AZG_WGRAD_CLUSTER"); t->wgrad_cluster = v ? atoi(v) : 0; }
-  if (t->C == 256) { t->fuse_stats = 0; t->fuse_bwd = 0; t->wgrad_cluster = 0; }          // the 256-channel convolution (streamed weights) has no statistics epilogue
+  if (t->C == 256) t->wgrad_cluster = 0;                                                   // the cluster experiment is built for one tile per tensor
   const int C = t->C, L = t->L, B = t->max_batch;
   layout_params(t->lay, C, L);
   t->rows = AZG_NET_FRONT + (size_t)B * 256 + AZG_NET_BACK;

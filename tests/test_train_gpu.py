@@ -286,7 +286,7 @@ def test_ragged_batch_sizes_against_oracle(ch, n):
         model.net.load_state_dict(sd)
 
 
-@pytest.mark.parametrize("blocks,ch", [(2, 64), (3, 128)])
+@pytest.mark.parametrize("blocks,ch", [(2, 64), (3, 128), (2, 256)])
 def test_fused_and_standalone_batchnorm_backward_sums_agree(blocks, ch, monkeypatch):
     """The BatchNorm backward reductions (sum dy, sum dy * x_hat) collected in the input-gradient convolution's epilogue
     (net_conv.cu STATS 2, the default) against the pass of their own (AZG_TRAIN_FUSE_BWD=0): same inputs, same weights.

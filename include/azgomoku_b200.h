@@ -216,7 +216,7 @@ typedef struct azg_net_weights {
   const float* value_fc2_b;                     /* [1] */
 } azg_net_weights;
 
-/* channels: 64 or 128; max_batch: positions per forward pass the activation buffers hold. */
+/* channels: 64, 128 or 256; max_batch: positions per forward pass the activation buffers hold. */
 int azg_net_create(int device, int n_blocks, int channels, int max_batch, azg_net** out);
 int azg_net_destroy(azg_net* n);
 int64_t azg_net_memory_bytes(const azg_net* n);
@@ -256,7 +256,7 @@ typedef struct azg_train azg_train;
 typedef struct azg_train_config {
   int32_t device;
   int32_t n_blocks;
-  int32_t channels;        /* 64 or 128 */
+  int32_t channels;        /* 64, 128 or 256 */
   int32_t max_batch;       /* positions per step the activation buffers hold */
   double lr;               /* Adam, network.py:141 defaults: 1e-3 */
   double weight_decay;     /* 1e-4, added to the gradient (torch.optim.Adam) */

@@ -405,18 +405,14 @@ def gather_rows(rows: torch.Tensor) -> torch.Tensor:
     return torch.cat([parts[r, :c] for r, c in enumerate(counts)], dim=0)
 
 
-def train_batch_dp(model: PyTorchModel, states, pis, zs) -> dict:
-    """``PyTorchModel.train_batch`` (network.py:199-235: KLDiv(batchmean) + MSE, clip 3.0, Adam) on this
-    rank's micro-batch with the gradients averaged over all ranks before the clip and the step, so
-    every rank applies the identical update."""
-    world, _ = _world()
-    if world == 1:
-        return model.train_batch(states, pis, zs, epochs=1)
+def train_step_device(model: PyTorchModel, states, pis, zs, world: int = 1) -> torch.Tensor:
+    """One ``train_batch`` step (network.py:199-235: KLDiv(batchmean) + MSE, clip 3.0, Adam) WITHOUT a host
+    synchronisation: returns the device tensor [policy_loss, value_loss].  ``world`` > 1: this rank's micro-batch,
+    gradients averaged over all ranks before the clip and the step, so every rank applies the identical update."""
     if getattr(model, "_ensure_trainer", None) is not None and model.net.channels in (64, 128, 256):
         # CUDA training step: one all-reduce over the flat gradient vector between backward and clip + Adam
-        losses = model.train_batch_async(states, pis, zs, world=world, reduce_grads=lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM))
-        p, v = losses.tolist()
-        return {"policy_loss": p, "value_loss": v, "total_loss": p + v}
+        reduce = (lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)) if world > 1 else None
+        return model.train_batch_async(states, pis, zs, world=world, reduce_grads=reduce)
     net, dev = model.net, model.device
     to = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.asarray(a, dtype=np.float32))).to(dev, torch.float32)
     net.train()
@@ -424,19 +420,29 @@ def train_batch_dp(model: PyTorchModel, states, pis, zs) -> dict:
     logits, values = net(to(states))
     pl = model.policy_loss_fn(F.log_softmax(logits, dim=1), to(pis))
     vl = model.value_loss_fn(values, to(zs))
-    loss = pl + vl
-    loss.backward()
-    grads = [p.grad for p in net.parameters() if p.grad is not None]
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat /= world
-    o = 0
-    for g in grads:
-        g.copy_(flat[o:o + g.numel()].view_as(g))
-        o += g.numel()
+    (pl + vl).backward()
+    if world > 1:
+        grads = [p.grad for p in net.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= world
+        o = 0
+        for g in grads:
+            g.copy_(flat[o:o + g.numel()].view_as(g))
+            o += g.numel()
     torch.nn.utils.clip_grad_norm_(net.parameters(), 3.0)
-    model.optimizer.step()
-    return {"policy_loss": float(pl.item()), "value_loss": float(vl.item()), "total_loss": float(loss.item())}
+    model.optimizer.step()          # in-place parameter writes bump the tensor versions: the inference cache repacks on its own
+    return torch.stack([pl.detach(), vl.detach()])
+
+
+def train_batch_dp(model: PyTorchModel, states, pis, zs) -> dict:
+    """``PyTorchModel.train_batch`` on this rank's micro-batch with the gradients averaged over all ranks
+    (``train_step_device``), returning the reference's dictionary of floats (one host synchronisation)."""
+    world, _ = _world()
+    if world == 1:
+        return model.train_batch(states, pis, zs, epochs=1)
+    p, v = train_step_device(model, states, pis, zs, world).tolist()
+    return {"policy_loss": p, "value_loss": v, "total_loss": p + v}
 
 
 def broadcast_model(model: PyTorchModel, src: int = 0):
@@ -447,6 +453,35 @@ def broadcast_model(model: PyTorchModel, src: int = 0):
         for t in list(model.net.parameters()) + list(model.net.buffers()):
             dist.broadcast(t, src)
     model.invalidate()
+
+
+def broadcast_optimizer(model: PyTorchModel, src: int = 0):
+    """Adam's moments and step counters from ``src`` to every rank (after a replicated training phase)."""
+    world, _ = _world()
+    if world == 1:
+        return
+    with torch.no_grad():
+        for p in model.net.parameters():
+            st = model.optimizer.state.get(p)
+            if not st:
+                continue
+            for k in ("exp_avg", "exp_avg_sq", "step"):
+                v = st.get(k)
+                if torch.is_tensor(v):
+                    if v.device.type == "cpu" and dist.get_backend() == "nccl":       # torch keeps `step` on the host by default
+                        t = v.to(model.device)
+                        dist.broadcast(t, src)
+                        v.copy_(t.cpu())
+                    else:
+                        dist.broadcast(v, src)
+
+
+# Data-parallel training splits a batch over the ranks and BatchNorm then normalises every slice with its own
+# statistics (as torch's DistributedDataParallel does without SyncBatchNorm).  The reference normalises the WHOLE batch
+# (network.py:210-226, default batch_size 128): below this many positions per rank the loop keeps the reference's
+# arithmetic instead - every rank trains the whole batch (same buffer, same draws) and rank 0's result is broadcast
+# after the phase (the ranks differ only in the summation order of the weight gradients until then).
+DP_MIN_POSITIONS_PER_RANK = 64
 
 
 def sync_batchnorm_buffers(model: PyTorchModel):
@@ -529,15 +564,23 @@ def train_alphazero(game_name: str = "gomoku", board_size: int = 15, num_iterati
         # ---- training (train.py:754-763): every rank draws the same batches (shared seed) and takes its slice
         n_batches = len(buffer) // batch_size
         sample_gen.manual_seed(1000003 * it + 17)      # identical buffers + identical draws on every rank
+        replicated = world > 1 and batch_size // world < DP_MIN_POSITIONS_PER_RANK
         for ep in range(epochs_per_iter):
-            tot = 0.0
+            tot = torch.zeros((), dtype=torch.float32, device=dev)      # losses stay on the device: one host read per epoch
             for _ in range(n_batches):
                 states, pis, zs = buffer.sample(batch_size, generator=sample_gen)
-                sl = slice(rank * batch_size // world, (rank + 1) * batch_size // world)
-                tot += train_batch_dp(model_candidate, states[sl], pis[sl], zs[sl])["total_loss"]
+                if world == 1 or replicated:
+                    tot += train_step_device(model_candidate, states, pis, zs).sum()
+                else:
+                    sl = slice(rank * batch_size // world, (rank + 1) * batch_size // world)
+                    tot += train_step_device(model_candidate, states[sl], pis[sl], zs[sl], world).sum()
             if rank == 0 and n_batches:
-                print(f"[train] epoch {ep + 1}/{epochs_per_iter} mean loss {tot / n_batches:.4f}")
-        sync_batchnorm_buffers(model_candidate)
+                print(f"[train] epoch {ep + 1}/{epochs_per_iter} mean loss {float(tot) / n_batches:.4f}")
+        if replicated:
+            broadcast_model(model_candidate)
+            broadcast_optimizer(model_candidate)
+        else:
+            sync_batchnorm_buffers(model_candidate)
         # ---- evaluation and accept / reject (train.py:768-827), rank 0 decides
         accept = torch.zeros(1, dtype=torch.int32, device=dev)
         # every rank plays its slice of the match (collective inside: all ranks must call it)

@@ -112,6 +112,27 @@ def _worker(rank, world, port, out):
     parts = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(parts, flat)
     same = same and bool(torch.equal(parts[0], parts[1]))
+    # replicated phase (small batches: every rank trains the WHOLE batch, train.DP_MIN_POSITIONS_PER_RANK): the ranks
+    # step on their own - here even on different data - and rank 0's parameters, buffers and Adam state are broadcast after
+    xr, pir, zr = _batch(100 + rank, 8)
+    lo = tr.train_step_device(model, xr, pir, zr)                      # world = 1: no collective inside
+    assert lo.shape == (2,) and bool(torch.isfinite(lo).all())
+    def moments():
+        return torch.cat([model.optimizer.state[p][k].detach().reshape(-1).double() for p in model.net.parameters()
+                          for k in ("exp_avg", "exp_avg_sq")] +
+                         [torch.as_tensor(model.optimizer.state[p]["step"]).double().reshape(-1) for p in model.net.parameters()])
+    parts = [torch.empty_like(moments()) for _ in range(world)]
+    dist.all_gather(parts, moments())
+    assert not torch.equal(parts[0], parts[1])
+    tr.broadcast_model(model, 0)
+    tr.broadcast_optimizer(model, 0)
+    parts = [torch.empty_like(moments()) for _ in range(world)]
+    dist.all_gather(parts, moments())
+    same = same and bool(torch.equal(parts[0], parts[1]))
+    full = torch.cat([t.detach().reshape(-1).double() for t in list(model.net.parameters()) + list(model.net.buffers())])
+    parts = [torch.empty_like(full) for _ in range(world)]
+    dist.all_gather(parts, full)
+    same = same and bool(torch.equal(parts[0], parts[1]))
     out.put((rank, worst, same))
     dist.destroy_process_group()
 

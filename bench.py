@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--soak", type=int, default=0, metavar="PLIES",
                     help="instead of the benchmark: play PLIES plies of the configured workload from the empty board with respawn, "
                          "then print {max_nodes_per_game, dropped_trees, games_finished, ...} and exit 1 if any tree was dropped")
+    ap.add_argument("--no-train-probe", action="store_true", help="skip the training-step probe printed next to the metric (N = 1 only)")
     ap.add_argument("--pipeline", type=int, default=1, choices=[1, 2],
                     help="game groups per GPU: 2 overlaps one group's tree walk with the other group's leaf evaluation "
                          "(+1.6 %% sims/s when first measured, -0.6 %% with the final kernels; the per-launch CUDA-event timing of the trunk kernel, and with it the "
@@ -532,12 +533,51 @@ def run_ours(args):
                        "dropped_trees": stats["dropped_trees"], "engine_gb": sum(u.engine.memory_bytes for u in units) / 1e9,
                        "net_gb": sum(u.net.memory_bytes for u in units) / 1e9},
         }
+        if world == 1 and not args.no_train_probe:
+            try:
+                line["train_step"] = train_probe(args, dev)
+            except Exception as e:                      # a probe: never costs the bench line
+                line["train_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def train_probe(args, dev):
+    """Not part of the metric: the next row of SURVEY 8(f), PyTorchModel.train_batch (network.py:199-235), timed on the same
+    network after the self-play measurement - the tensor-core training step replayed from CUDA graphs, batch resident in HBM,
+    CUDA events over 20 steps after 5 warm-up steps.  Useful FLOPs = 3 x the forward trunk FLOPs on the 225 real pixels."""
+    import torch
+    from alphazero_gomoku_b200.network import PyTorchModel
+    from alphazero_gomoku_b200.selfplay import trunk_flops
+    torch.manual_seed(1)
+    model = PyTorchModel(n_res_blocks=args.blocks, channels=args.channels, device=str(dev))
+    g = torch.Generator(device=dev).manual_seed(1)
+    flops_pos = 3 * trunk_flops(args.channels) * 2 * args.blocks
+    rows = []
+    for B in (128, 1024):
+        x = (torch.rand((B, 3, 15, 15), device=dev, generator=g) < 0.15).float()
+        x[:, 1] *= (1 - x[:, 0])
+        x[:, 2] = 1.0
+        pi = torch.softmax(torch.randn((B, 225), device=dev, generator=g), dim=1)
+        z = torch.randint(-1, 2, (B, 1), device=dev, generator=g).float()
+        for _ in range(5):
+            model.train_batch_async(x, pi, z)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            losses = model.train_batch_async(x, pi, z)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 20
+        rows.append({"batch": B, "ms_per_step": round(ms, 4), "positions_per_s": round(B / (ms * 1e-3), 1),
+                     "useful_tflops": round(B * flops_pos / (ms * 1e-3) / 1e12, 1), "last_losses": [round(float(v), 4) for v in losses.tolist()]})
+    return {"what": "PyTorchModel.train_batch (forward, loss, backward, clip 3.0, Adam) on tensor cores, CUDA-graph replay, batch resident in HBM; "
+                    "a probe next to the metric, not part of it", "net": f"{args.blocks}x{args.channels}", "steps": 20, "warmup": 5, "results": rows}
 
 
 def main():

@@ -158,16 +158,26 @@ __device__ __forceinline__ bool node_key_matches(const NodeData& nd, const WPos&
 // Transposition lookup that also fetches the node: the candidate's arrays are requested together
 // with its key, so a hit costs two dependent memory round trips (probe window, node) instead of
 // three.  The full key is always compared (the tag only selects candidates).
-template <bool L1 = false, bool CC = false>
+// This lane's slot of the first probe window of hash h: issued by the caller BEFORE the win test of the position, so
+// that the test's ~300 cycles of shuffles and ballots run under the load's latency (table_find_load takes it as `first`).
+template <bool L1 = false>
+__device__ __forceinline__ unsigned long long table_first_window(const azg_dev& e, int g, unsigned long long h) {
+  const unsigned long long* tab = e.slots + (size_t)g * (size_t)e.hcap;
+  const int nwin = e.hcap >> 5;
+  const int win = (int)((uint32_t)h & (uint32_t)(nwin - 1));
+  return ldx<L1>(&tab[(win << 5) + lane_id()]);
+}
+
+template <bool L1 = false, bool CC = false, bool PRE = false>
 __device__ __forceinline__ int table_find_load(const azg_dev& e, int g, const WPos& p, unsigned long long h, int* ins,
-                                               NodeData& nd) {
+                                               NodeData& nd, unsigned long long first = 0ULL) {
   const unsigned long long* tab = e.slots + (size_t)g * (size_t)e.hcap;
   const uint32_t tag = (uint32_t)(h >> 32);
   const int nwin = e.hcap >> 5;
   int win = (int)((uint32_t)h & (uint32_t)(nwin - 1));
   const int l = lane_id();
   for (int t = 0; t < nwin; ++t) {
-    const unsigned long long s = ldx<L1>(&tab[(win << 5) + l]);
+    const unsigned long long s = (PRE && t == 0) ? first : ldx<L1>(&tab[(win << 5) + l]);
     uint32_t mm = __ballot_sync(AZG_FULL, s != 0ULL && (uint32_t)(s >> 32) == tag);
     while (mm) {
       const int src = __ffs(mm) - 1;
@@ -305,13 +315,16 @@ __device__ __forceinline__ void fill_body(const azg_dev& e) {
     for (;;) {
       if (!select_here) {
         ++visits;
+        // hash and first probe window first: the load is in flight while the win test runs (a terminal position wastes it)
+        const bool at_root = depth == 0 && root_node >= 0;
+        const unsigned long long h = wpos_hash(pos);
+        const unsigned long long first = at_root ? 0ULL : table_first_window<L1>(e, g, h);
         const int won = wpos_winner(pos, e.rule);            // new_mcts_alpha.py:106-112
         if (won != 0) { v = -1; if (CC && par_node >= 0 && l == 0) e.child[azg_node_off(e, g, par_node) * AZG_ROW + par_a] = AZG_CHILD_WON; break; }
         if (!wpos_any_empty(pos)) { v = 0; if (CC && par_node >= 0 && l == 0) e.child[azg_node_off(e, g, par_node) * AZG_ROW + par_a] = AZG_CHILD_DRAW; break; }
-        const unsigned long long h = wpos_hash(pos);
         int ins = -1;
-        if (depth == 0 && root_node >= 0) { node = root_node; node_load<L1, CC>(e, g, node, nd); }   // the root key is fixed for the run
-        else node = table_find_load<L1, CC>(e, g, pos, h, &ins, nd);
+        if (at_root) { node = root_node; node_load<L1, CC>(e, g, node, nd); }   // the root key is fixed for the run
+        else node = table_find_load<L1, CC, true>(e, g, pos, h, &ins, nd, first);
         if (CC && node >= 0 && par_node >= 0 && l == 0) e.child[azg_node_off(e, g, par_node) * AZG_ROW + par_a] = node + AZG_CHILD_NODE0;
         if (node < 0) {                                        // new_mcts_alpha.py:114-132
           if (ins < 0) { err |= AZG_ERR_HASH; break; }

@@ -170,7 +170,7 @@ __device__ __forceinline__ unsigned long long table_first_window(const azg_dev& 
 
 template <bool L1 = false, bool CC = false, bool PRE = false>
 __device__ __forceinline__ int table_find_load(const azg_dev& e, int g, const WPos& p, unsigned long long h, int* ins,
-                                               NodeData& nd, unsigned long long first = 0ULL) {
+                                               NodeData& nd, unsigned long long first = 0ULL, unsigned long long* snap = nullptr) {
   const unsigned long long* tab = e.slots + (size_t)g * (size_t)e.hcap;
   const uint32_t tag = (uint32_t)(h >> 32);
   const int nwin = e.hcap >> 5;
@@ -187,7 +187,7 @@ __device__ __forceinline__ int table_find_load(const azg_dev& e, int g, const WP
       if (node_key_matches(nd, p)) return node;
     }
     const uint32_t em = __ballot_sync(AZG_FULL, s == 0ULL);
-    if (em) { *ins = (win << 5) + __ffs(em) - 1; return -1; }
+    if (em) { *ins = (win << 5) + __ffs(em) - 1; if (snap) *snap = s; return -1; }      // snap: this lane's slot of the window of *ins
     win = (win + 1) & (nwin - 1);
   }
   *ins = -1;
@@ -437,6 +437,7 @@ extern "C" __global__ void __launch_bounds__(32 * AZG_FAST_MAX_WARPS) azg_fill_f
   __shared__ int s_state, s_sims_left, s_n_pending, s_lock, s_n_nodes, s_n_free, s_n_live, s_err, s_stop, s_root_node;
   __shared__ unsigned int s_visits, s_sims;
   __shared__ uint32_t s_path[AZG_FAST_MAX_WARPS][AZG_FAST_MAX_DEPTH];
+  __shared__ int s_spare[AZG_FAST_MAX_WARPS];
   const int g = blockIdx.x;
   const int l = lane_id(), wib = threadIdx.x >> 5;
   azg_ctl* ctl = e.ctl + g;
@@ -452,6 +453,7 @@ extern "C" __global__ void __launch_bounds__(32 * AZG_FAST_MAX_WARPS) azg_fill_f
   int32_t* freelist = e.freelist + (size_t)g * e.cap;
   const WPos root = wpos_load(&ctl->root);
   uint32_t* path = s_path[wib];
+  int spare = -1;                         // a slab node this warp built but did not publish (somebody else made the position first)
 
   while (true) {
     int go = 0;
@@ -473,11 +475,36 @@ extern "C" __global__ void __launch_bounds__(32 * AZG_FAST_MAX_WARPS) azg_fill_f
       if (!wpos_any_empty(pos)) { v = 0; break; }
       const unsigned long long h = wpos_hash(pos);
       int ins = -1, node;
+      unsigned long long snap = 0ULL;
       const int rn = *(volatile int*)&s_root_node;
       if (depth == 0 && rn >= 0) { node = rn; node_load(e, g, node, nd); }
-      else node = table_find_load(e, g, pos, h, &ins, nd);
+      else node = table_find_load(e, g, pos, h, &ins, nd, 0ULL, &snap);
       if (node < 0) {
-        // ---- create the leaf under the game's lock
+        // ---- create the leaf.  The node is taken from the slab and BUILT (key, placeholder priors, zeroed statistics)
+        // outside the lock - nobody can find it yet; the lock only covers "is the position still missing?" (one reload of
+        // the probe window: slots are only ever filled, and every warp looking for this position ends at this window),
+        // the table entry and the queue entry.  A node that turns out not to be needed stays with the warp as its spare.
+        if (ins < 0) { if (l == 0) atomicOr(&s_err, AZG_ERR_HASH); abort = true; break; }
+        int nn = spare;
+        if (nn < 0) {
+          int got = -1, fail = 0;
+          if (l == 0) {
+            const int old = atomicSub(&s_n_free, 1);
+            if (old > 0) got = __ldcg(&freelist[old - 1]);
+            else {
+              atomicAdd(&s_n_free, 1);
+              const int n = atomicAdd(&s_n_nodes, 1);
+              if (n < e.cap) got = n; else { atomicSub(&s_n_nodes, 1); fail = AZG_ERR_NODES; }
+            }
+          }
+          nn = __shfl_sync(AZG_FULL, got, 0); fail = __shfl_sync(AZG_FULL, fail, 0);
+          if (fail) { if (l == 0) atomicOr(&s_err, fail); abort = true; break; }
+        }
+        spare = nn;
+        node_write_key(e, g, nn, pos);
+        node_fill(e, g, nn, wpos_legal_byte(pos), __fdiv_rn(1.0f, (float)wpos_count_empty(pos)));
+        __threadfence_block();
+        __syncwarp();
         int got = 0;
         if (l == 0) {
           for (int spin = 0; spin < (1 << 24); ++spin)
@@ -486,33 +513,29 @@ extern "C" __global__ void __launch_bounds__(32 * AZG_FAST_MAX_WARPS) azg_fill_f
         got = __shfl_sync(AZG_FULL, got, 0);
         if (!got) { if (l == 0) atomicOr(&s_err, AZG_ERR_HASH); abort = true; break; }
         __threadfence_block();
-        node = table_find_load(e, g, pos, h, &ins, nd);         // somebody else may have made it meanwhile
+        const unsigned long long now = __ldcg(&e.slots[(size_t)g * (size_t)e.hcap + (size_t)((ins & ~31) + l)]);
+        node = -1;
+        if (__any_sync(AZG_FULL, now != snap)) node = table_find_load(e, g, pos, h, &ins, nd);   // the window changed: look again
         bool done = false;
         if (node < 0) {
-          int np = 0, nn = -1, fail = 0;                          // lane 0 allocates under the lock, the warp follows
+          int np = 0, fail = 0;
           if (l == 0) {
             np = *(volatile int*)&s_n_pending;
             if (ins < 0) fail = AZG_ERR_HASH;
             else if (np >= e.queue_len) fail = -1;                // the queue filled up: this simulation is given back
-            else if (*(volatile int*)&s_n_free > 0) { const int k = *(volatile int*)&s_n_free - 1; nn = __ldcg(&freelist[k]); *(volatile int*)&s_n_free = k; }
-            else if (*(volatile int*)&s_n_nodes < e.cap) { nn = *(volatile int*)&s_n_nodes; *(volatile int*)&s_n_nodes = nn + 1; }
-            else fail = AZG_ERR_NODES;
           }
-          np = __shfl_sync(AZG_FULL, np, 0); nn = __shfl_sync(AZG_FULL, nn, 0); fail = __shfl_sync(AZG_FULL, fail, 0);
+          np = __shfl_sync(AZG_FULL, np, 0); fail = __shfl_sync(AZG_FULL, fail, 0);
           if (fail) { if (fail > 0 && l == 0) atomicOr(&s_err, fail); abort = true; done = true; }
           else {
-            node_write_key(e, g, nn, pos);
-            node_fill(e, g, nn, wpos_legal_byte(pos), __fdiv_rn(1.0f, (float)wpos_count_empty(pos)));
-            __threadfence_block();
-            __syncwarp();
             table_put(e, g, ins, h, nn);                          // published last: lock-free readers find a complete node
             if (l == 0) {
               ctl->pending[np] = nn;
               *(volatile int*)&s_n_pending = np + 1;
-              *(volatile int*)&s_n_live = *(volatile int*)&s_n_live + 1;
+              atomicAdd(&s_n_live, 1);
               if (depth == 0) *(volatile int*)&s_root_node = nn;
               if (np + 1 >= e.queue_len) *(volatile int*)&s_stop = 1;
             }
+            spare = -1;
             v = 0;
             done = true;
           }
@@ -552,8 +575,11 @@ extern "C" __global__ void __launch_bounds__(32 * AZG_FAST_MAX_WARPS) azg_fill_f
     }
     if (abort) break;                                           // queue full or error: this warp is done for this launch
   }
+  if (l == 0) s_spare[wib] = spare;
   __syncthreads();
   if (threadIdx.x == 0) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w)      // unused nodes go back to the free stack, marked dead for the next GC
+      if (s_spare[w] >= 0) { e.meta[azg_node_off(e, g, s_spare[w])] = 0u; freelist[s_n_free++] = s_spare[w]; }
     int state = AZG_ST_RUN;
     const int left = s_sims_left < 0 ? 0 : s_sims_left;
     if (s_err) state = AZG_ST_ERROR;

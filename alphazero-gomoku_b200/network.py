@@ -150,6 +150,8 @@ class PyTorchModel:
         """Forget the packed bf16 weights: the next predict / search repacks from ``self.net``.  Needed after
         writes the version counters cannot see (``tensor.data`` views, raw device copies)."""
         self._packed_version = None
+        if getattr(self, "_trainer", None) is not None:         # the training engine keeps bf16 copies of the convolution weights too
+            self._trainer._param_version = None                 # (collectives such as dist.broadcast do not bump tensor versions)
 
     def predict_device(self, planes: torch.Tensor, validate: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """planes float32[B,3,15,15] on the device -> (probs f32[B,225], values f32[B,1]) on the device.
@@ -210,7 +212,7 @@ class PyTorchModel:
             if reduce_grads is not None:
                 reduce_grads(tr.flat_grads)
             tr.apply(world)
-        self.invalidate()               # the kernels wrote the parameters: the inference engine must repack
+        self._packed_version = None     # the kernels wrote the parameters: the inference engine must repack (the trainer's own copies are current)
         return losses
 
     def train_batch(self, states, target_pis, target_vs, epochs: int = 1) -> dict:

@@ -588,11 +588,14 @@ head_fc_fwd_kernel(HeadTrainArgs p) {
   if (j < 225) {
 #pragma unroll
     for (int k = 0; k < kFcBoards; ++k) logit[k] = p.bp[j];
-#pragma unroll 10
-    for (int i = 0; i < 450; ++i) {
-      const float w = p.wp_t[(size_t)i * 225 + j];
+    for (int i0 = 0; i0 < 450; i0 += 30) {      // 30 weight loads in flight per thread: the loop is a chain of L2 round trips otherwise
+      float w[30];
 #pragma unroll
-      for (int k = 0; k < kFcBoards; ++k) logit[k] = fmaf(hs[k][i], w, logit[k]);
+      for (int u = 0; u < 30; ++u) w[u] = p.wp_t[(size_t)(i0 + u) * 225 + j];
+#pragma unroll
+      for (int u = 0; u < 30; ++u)
+#pragma unroll
+        for (int k = 0; k < kFcBoards; ++k) logit[k] = fmaf(hs[k][i0 + u], w[u], logit[k]);
     }
   } else {
 #pragma unroll
@@ -602,11 +605,14 @@ head_fc_fwd_kernel(HeadTrainArgs p) {
     float acc[kFcBoards];
 #pragma unroll
     for (int k = 0; k < kFcBoards; ++k) acc[k] = p.bv1[tid];
-#pragma unroll 9
-    for (int i = 0; i < 225; ++i) {
-      const float w = p.wv1_t[(size_t)i * 64 + tid];
+    for (int i0 = 0; i0 < 225; i0 += 25) {
+      float w[25];
 #pragma unroll
-      for (int k = 0; k < kFcBoards; ++k) acc[k] = fmaf(hs[k][450 + i], w, acc[k]);
+      for (int u = 0; u < 25; ++u) w[u] = p.wv1_t[(size_t)(i0 + u) * 64 + tid];
+#pragma unroll
+      for (int u = 0; u < 25; ++u)
+#pragma unroll
+        for (int k = 0; k < kFcBoards; ++k) acc[k] = fmaf(hs[k][450 + i0 + u], w[u], acc[k]);
     }
 #pragma unroll
     for (int k = 0; k < kFcBoards; ++k) {
@@ -707,15 +713,25 @@ head_fc_bwd_data_kernel(HeadTrainArgs p) {
   __syncthreads();
   if (tid < 450) {
     float acc = 0.f;
-#pragma unroll 9
-    for (int jj = 0; jj < 225; ++jj) acc = fmaf(dl[jj], p.wp[(size_t)jj * 450 + tid], acc);
+    for (int j0 = 0; j0 < 225; j0 += 25) {        // 25 weight loads in flight (see head_fc_fwd_kernel)
+      float w[25];
+#pragma unroll
+      for (int u = 0; u < 25; ++u) w[u] = p.wp[(size_t)(j0 + u) * 450 + tid];
+#pragma unroll
+      for (int u = 0; u < 25; ++u) acc = fmaf(dl[j0 + u], w[u], acc);
+    }
     const size_t o = (size_t)b * 675 + tid;
     p.dhid[o] = p.hidden[o] > 0.f ? acc : 0.f;
   }
   if (tid < 225) {
     float acc = 0.f;
-#pragma unroll 8
-    for (int t = 0; t < 64; ++t) acc = fmaf(dh1[t], p.wv1[(size_t)t * 225 + tid], acc);
+    for (int t0 = 0; t0 < 64; t0 += 32) {
+      float w[32];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) w[u] = p.wv1[(size_t)(t0 + u) * 225 + tid];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) acc = fmaf(dh1[t0 + u], w[u], acc);
+    }
     const size_t o = (size_t)b * 675 + 450 + tid;
     p.dhid[o] = p.hidden[o] > 0.f ? acc : 0.f;
   }

@@ -633,13 +633,85 @@ def build_train():
     np.savez_compressed(os.path.join(OUT, "ref_replay_rows.npz"), planes_bits=bits, pi=pis, z=zs)
 
 
+def _capture_moves(board, player):
+    """Empty cells from which `player` flanks exactly two opposing stones in some direction (pente.py:114-152)."""
+    opp, out = 3 - player, []
+    for r in range(15):
+        for c in range(15):
+            if board[r, c] != 0:
+                continue
+            for dr in (-1, 0, 1):
+                for dc in (-1, 0, 1):
+                    if dr == 0 and dc == 0:
+                        continue
+                    r3, c3 = r + 3 * dr, c + 3 * dc
+                    if 0 <= r3 < 15 and 0 <= c3 < 15 and board[r + dr, c + dc] == opp and board[r + 2 * dr, c + 2 * dc] == opp \
+                            and board[r3, c3] == player:
+                        out.append((r, c))
+    return out
+
+
+def build_undo():
+    """do_move / undo_move sequences on the reference's game objects (gomoku.py:57-98, pente.py:57-109): after every
+    operation the board, the side to move, the last move and (Pente) the capture counts.  undo_move is off the search
+    path (the search clones), but it is part of the drop-in classes - including pente.py:100-103, which restores captured
+    stones in the capturer's colour."""
+    rng = np.random.default_rng(20260202)
+    out = {}
+    for rule, cls, tag in ((rules.GOMOKU, Gomoku, "g"), (rules.PENTE, Pente, "p")):
+        for k in range(3):
+            g = cls(size=15)
+            ops, boards, players, lasts, caps, oks = [], [], [], [], [], []
+            for _ in range(220 if rule == rules.PENTE else 140):
+                undo = len(g.move_history) > 0 and rng.random() < 0.3
+                if undo:
+                    g.undo_move()
+                    ops.append(-1); oks.append(1)
+                else:
+                    empties = np.argwhere(np.asarray(g.board) == 0)
+                    if rng.random() < 0.04 or len(empties) == 0:        # an occupied or off-board cell: refused, nothing changes
+                        r, c = (int(rng.integers(0, 15)), int(rng.integers(0, 15))) if rng.random() < 0.5 else (15, 3)
+                        if 0 <= r < 15 and g.board[r][c] == 0:
+                            r, c = 15, 3
+                    elif rule == rules.PENTE and rng.random() < 0.7 and _capture_moves(np.asarray(g.board), g.current_player):
+                        cm = _capture_moves(np.asarray(g.board), g.current_player)       # a move that captures: its undo is the case to pin
+                        r, c = cm[int(rng.integers(0, len(cm)))]
+                    elif rule == rules.PENTE and rng.random() < 0.5:
+                        # next to an existing stone: makes custodial captures (and their undo) likely
+                        stones = np.argwhere(np.asarray(g.board) != 0)
+                        r, c = empties[int(rng.integers(0, len(empties)))]
+                        if len(stones):
+                            sr, sc = stones[int(rng.integers(0, len(stones)))]
+                            cand = [(sr + dr, sc + dc) for dr in (-3, -1, 0, 1, 3) for dc in (-3, -1, 0, 1, 3)
+                                    if 0 <= sr + dr < 15 and 0 <= sc + dc < 15 and g.board[sr + dr][sc + dc] == 0]
+                            if cand:
+                                r, c = cand[int(rng.integers(0, len(cand)))]
+                    else:
+                        r, c = empties[int(rng.integers(0, len(empties)))]
+                    ok = g.do_move((int(r), int(c)))
+                    ops.append(int(r) * 16 + int(c)); oks.append(int(bool(ok)))
+                boards.append(np.asarray(g.board, dtype=np.int8).copy())
+                players.append(int(g.current_player))
+                lasts.append(-1 if g.last_move is None else int(g.last_move[0]) * 15 + int(g.last_move[1]))
+                caps.append(ref_caps(g))
+            n_undo_caps = sum(1 for i, o in enumerate(ops) if o == -1 and i > 0 and caps[i] != caps[i - 1])
+            print(f"undo trace {tag}{k}: {len(ops)} ops, {ops.count(-1)} undos, {n_undo_caps} of them undo a capture")
+            out[f"{tag}{k}/ops"] = np.array(ops, np.int32)          # -1 = undo_move, else row * 16 + col (row 15 = off the board)
+            out[f"{tag}{k}/ok"] = np.array(oks, np.int8)
+            out[f"{tag}{k}/boards"] = np.stack(boards)
+            out[f"{tag}{k}/players"] = np.array(players, np.int8)
+            out[f"{tag}{k}/last"] = np.array(lasts, np.int16)
+            out[f"{tag}{k}/caps"] = np.array(caps, np.int16)
+    np.savez_compressed(os.path.join(OUT, "undo_traces.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["rules", "search", "noise", "misc", "net", "api", "game", "arena", "train"]
+    which = sys.argv[1:] or ["rules", "search", "noise", "misc", "net", "api", "game", "arena", "train", "undo"]
     for w in which:
         print(f"== {w}")
         {"rules": build_rules, "search": build_search, "noise": build_noise, "misc": build_misc, "net": build_net, "api": build_api,
-         "game": build_game, "arena": build_arena, "train": build_train}[w]()
+         "game": build_game, "arena": build_arena, "train": build_train, "undo": build_undo}[w]()
 
 
 if __name__ == "__main__":

@@ -39,6 +39,35 @@ def test_game_objects_follow_golden_traces():
     assert sorted(p.capture_history[-1]) == [(7, 8), (7, 9)] and p.captures == {1: 1, 2: 0}
 
 
+def test_undo_move_follows_reference_traces():
+    """do_move / undo_move sequences recorded from the reference's classes (tests/golden/undo_traces.npz, oracle/make_golden.py
+    build_undo): board, side to move, last move and capture counts after every operation - including pente.py:100-103,
+    which puts captured stones back in the CAPTURER's colour (20 such undos in the Pente traces)."""
+    from alphazero_gomoku_b200.games import Gomoku, Pente
+    z = load_golden("undo_traces.npz")
+    undone_captures = 0
+    for tag, cls in (("g", Gomoku), ("p", Pente)):
+        for k in range(3):
+            g = cls(15)
+            ops, oks = z[f"{tag}{k}/ops"], z[f"{tag}{k}/ok"]
+            prev_caps = [0, 0]
+            for i, op in enumerate(ops):
+                if op < 0:
+                    g.undo_move()
+                else:
+                    assert g.do_move((int(op) // 16, int(op) % 16)) == bool(oks[i]), (tag, k, i)
+                assert np.array_equal(np.asarray(g.board), z[f"{tag}{k}/boards"][i]), (tag, k, i)
+                assert g.current_player == int(z[f"{tag}{k}/players"][i]), (tag, k, i)
+                last = -1 if g.last_move is None else g.last_move[0] * 15 + g.last_move[1]
+                assert last == int(z[f"{tag}{k}/last"][i]), (tag, k, i)
+                caps = [g.captures[1], g.captures[2]] if tag == "p" else [0, 0]
+                assert caps == z[f"{tag}{k}/caps"][i].tolist(), (tag, k, i)
+                if op < 0 and caps != prev_caps:
+                    undone_captures += 1
+                prev_caps = caps
+    assert undone_captures >= 15
+
+
 def test_checkpoint_roundtrip_and_player(tmp_path):
     """network.py:240-258 format: {"net","opt","board_size","action_size"}; Player loads it and moves."""
     from alphazero_gomoku_b200.network import PyTorchModel
